@@ -1,0 +1,98 @@
+// ftmpc_block.cuh -- the cooperative-group abstraction every per-instance routine is written against.
+//
+// All solver routines (condensing, Cholesky, the dual active-set QP) are written once, in
+// "strided loop + barrier" form, against a Block type:
+//
+//     for (int i = blk.tid(); i < n; i += blk.nthreads()) { ... }   blk.sync();
+//
+//   * CudaBlock  : one CUDA thread block per MPC instance (the product path).
+//   * SerialBlock: one host thread per instance.  Used ONLY by the CPU port that tests and
+//                  bench.py's cpu_baseline build from these same headers (oracle/cpu_port); the
+//                  product library never instantiates it.
+//
+// Reductions return the block-wide result to every thread, in a fixed order, so that all threads
+// take identical branches (the solver control flow is uniform across the block).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FT_HD __host__ __device__ __forceinline__
+#define FT_D __device__ __forceinline__
+#else
+#define FT_HD inline
+#endif
+
+namespace ftmpc {
+
+struct SerialBlock {
+    FT_HD int tid() const { return 0; }
+    FT_HD int nthreads() const { return 1; }
+    FT_HD void sync() const {}
+    FT_HD double sum(double v) { return v; }
+    FT_HD double max(double v) { return v; }
+    // (value, index) pair with the smallest value; ties -> smallest index
+    FT_HD void argmin(double& v, int& idx) { (void)v; (void)idx; }
+    FT_HD int any(int pred) { return pred; }
+};
+
+#if defined(__CUDACC__)
+// scratch: >= 2 * 32 * 2 doubles of shared memory (double-buffered so one barrier per reduction suffices)
+struct CudaBlock {
+    double* scratch;
+    int phase;
+    __device__ __forceinline__ explicit CudaBlock(double* s) : scratch(s), phase(0) {}
+    __device__ __forceinline__ int tid() const { return threadIdx.x; }
+    __device__ __forceinline__ int nthreads() const { return blockDim.x; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+
+    __device__ __forceinline__ double* buf() {
+        double* b = scratch + phase * 64;
+        phase ^= 1;
+        return b;
+    }
+    __device__ __forceinline__ double sum(double v) {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        double* b = buf();
+        const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        if ((threadIdx.x & 31) == 0) b[w] = v;
+        __syncthreads();
+        double r = 0.0;
+        for (int i = 0; i < nw; ++i) r += b[i];
+        return r;
+    }
+    __device__ __forceinline__ double max(double v) {
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        double* b = buf();
+        const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        if ((threadIdx.x & 31) == 0) b[w] = v;
+        __syncthreads();
+        double r = b[0];
+        for (int i = 1; i < nw; ++i) r = fmax(r, b[i]);
+        return r;
+    }
+    __device__ __forceinline__ void argmin(double& v, int& idx) {
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+        }
+        double* b = buf();
+        const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        if ((threadIdx.x & 31) == 0) { b[w] = v; b[32 + w] = (double)idx; }
+        __syncthreads();
+        double rv = b[0];
+        int ri = (int)b[32];
+        for (int i = 1; i < nw; ++i) {
+            const double ov = b[i];
+            const int oi = (int)b[32 + i];
+            if (ov < rv || (ov == rv && oi < ri)) { rv = ov; ri = oi; }
+        }
+        v = rv;
+        idx = ri;
+    }
+    __device__ __forceinline__ int any(int pred) { return __syncthreads_or(pred); }
+};
+#endif
+
+}  // namespace ftmpc

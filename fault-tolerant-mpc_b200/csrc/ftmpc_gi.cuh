@@ -1,0 +1,289 @@
+// ftmpc_gi.cuh -- dense dual active-set QP (Goldfarb-Idnani) written for one cooperative block.
+//
+//     min 1/2 x'Gx + a'x    s.t.   n_i' x >= beta_i,  i = 0..m-1   (first `meq` rows are equalities)
+//
+// Replaces the QP machinery the reference reaches through third-party solvers:
+//   IPOPT/MUMPS inside  self.solver(**args)      ft_mpc/controllers/spiraling_mpc.py:346
+//   OSQP via CVXPY in   ControlAllocator          ft_mpc/controllers/tools/control_allocator.py:28-40,86
+//
+// GPU-specific formulation (nothing here needs a triangular solve, the latency killer at n~120):
+//   * E  (ne x nv, row-major, odd ld) holds J = L^-T Q in its first nv rows and  X*J  in its last
+//     ne-nv rows, where X maps the primal to "extended" coordinates in which every constraint normal
+//     is SPARSE (for the MPC QP: X = d x_N / d U, so the 72 terminal rows have <= 10 non-zeros).
+//   * Ui = R^-1 (packed upper triangular, by columns) is maintained instead of R:
+//       add    : new column [-r/rho ; 1/rho]      (r = R^-1 d1 is needed by the step anyway)
+//       drop l : the Givens coefficients come from prefix norms of row l of R^-1 (no recurrence
+//                across threads), applied to columns of E and of R^-1 row-parallel.
+//   * the "add" update of J is ONE Householder reflector:  E2 -= (2/v'v)(E2 v)v',  E2 v = z + s*alpha*E[:,q].
+// Every inner iteration is therefore a handful of mat-vecs over shared memory.
+#pragma once
+#include "ftmpc_block.cuh"
+
+namespace ftmpc {
+
+#define FTMPC_GI_MAXNNZ 12
+struct SparseRow {
+    int nnz;
+    int idx[FTMPC_GI_MAXNNZ];
+    double val[FTMPC_GI_MAXNNZ];
+    double beta;
+};
+
+enum { GI_OK = 0, GI_MAXIT = 1, GI_INFEASIBLE = 2 };
+
+struct GiWork {
+    double* E;      // ne x ld
+    double* Ui;     // packed upper triangular, capacity nv*(nv+1)/2
+    double* xe;     // ne   extended primal  [x ; X x]
+    double* s;      // m    slack  n_i' x - beta_i
+    double* u;      // nv+1 multipliers of the working set (+ candidate)
+    double* d;      // nv
+    double* ze;     // ne
+    double* r;      // nv
+    double* cs;     // 2*nv rotation coefficients
+    double* tmp;    // nv+1
+    double* sub;    // nv   sub-diagonal fill during a drop
+    int* act;       // nv+1 working set (constraint ids)
+    int* pos;       // m    position in working set or -1
+    int* itmp;      // nv+1
+    double* esign;  // meq  orientation used for each equality row
+};
+
+FT_HD int gi_tri(int j) { return (j * (j + 1)) >> 1; }
+
+// drop the l-th member of the working set
+template <class Blk>
+FT_HD void gi_drop(Blk& blk, const GiWork& w, int nv, int ne, int ld, int& q, int l) {
+    const int tid = blk.tid(), nt = blk.nthreads();
+    // rotation coefficients from prefix norms of row l of R^-1
+    for (int k = l + tid; k <= q - 2; k += nt) {
+        double ss = 0.0;
+        for (int j = l; j <= k; ++j) {
+            const double a = w.Ui[gi_tri(j) + l];
+            ss += a * a;
+        }
+        const double b = w.Ui[gi_tri(k + 1) + l];
+        const double carry = (k == l) ? w.Ui[gi_tri(l) + l] : sqrt(ss);
+        const double h = sqrt(ss + b * b);
+        double c = 1.0, s = 0.0;
+        if (h > 0.0) { c = b / h; s = carry / h; }
+        w.cs[2 * k] = c;
+        w.cs[2 * k + 1] = s;
+    }
+    blk.sync();
+    // rotate columns l..q-1 of E (all rows) and of R^-1 (rows != l)
+    for (int row = tid; row < ne + q; row += nt) {
+        if (row < ne) {
+            double* e = w.E + (size_t)row * ld;
+            double carry = e[l];
+            for (int k = l; k <= q - 2; ++k) {
+                const double c = w.cs[2 * k], s = w.cs[2 * k + 1], b = e[k + 1];
+                e[k] = c * carry - s * b;
+                carry = s * carry + c * b;
+            }
+            e[q - 1] = carry;
+        } else {
+            const int j = row - ne;
+            if (j < l) {
+                double carry = w.Ui[gi_tri(l) + j];
+                for (int k = l; k <= q - 2; ++k) {
+                    const double c = w.cs[2 * k], s = w.cs[2 * k + 1], b = w.Ui[gi_tri(k + 1) + j];
+                    w.Ui[gi_tri(k) + j] = c * carry - s * b;
+                    carry = s * carry + c * b;
+                }
+            } else if (j > l) {
+                double carry = 0.0;
+                for (int k = j - 1; k <= q - 2; ++k) {
+                    const double c = w.cs[2 * k], s = w.cs[2 * k + 1], b = w.Ui[gi_tri(k + 1) + j];
+                    const double nk = c * carry - s * b;
+                    if (k == j - 1) w.sub[j] = nk; else w.Ui[gi_tri(k) + j] = nk;
+                    carry = s * carry + c * b;
+                }
+            }
+        }
+    }
+    // save shifted multipliers / ids
+    for (int i = l + tid; i < q; i += nt) { w.tmp[i] = w.u[i + 1]; w.itmp[i] = (i + 1 < q) ? w.act[i + 1] : -1; }
+    if (tid == 0) w.pos[w.act[l]] = -1;
+    blk.sync();
+    // shift rows l+1.. of R^-1 up by one (thread per column) and commit the shifted lists
+    for (int k = l + tid; k <= q - 2; k += nt) {
+        double* col = w.Ui + gi_tri(k);
+        for (int j = l; j < k; ++j) col[j] = col[j + 1];
+        col[k] = w.sub[k + 1];
+    }
+    for (int i = l + tid; i < q; i += nt) {
+        w.u[i] = w.tmp[i];
+        if (i < q - 1) { w.act[i] = w.itmp[i]; w.pos[w.itmp[i]] = i; }
+    }
+    blk.sync();
+    q -= 1;
+}
+
+// On entry: E = [J ; X J] with J J' = G^-1, xe = [x ; X x] the unconstrained minimiser.
+// On exit : xe the solution, lam[m] multipliers (>=0 for inequalities), returns GI_* status.
+template <class Blk, class Cons>
+FT_HD int gi_solve(Blk& blk, const Cons& cons, const GiWork& w, int nv, int ne, int ld, int m, int meq,
+                   double* lam, int maxit, double tol, int* iters_out, int* nact_out) {
+    const int tid = blk.tid(), nt = blk.nthreads();
+    int q = 0, iters = 0, status = GI_OK;
+    // slack of every constraint at the unconstrained minimiser
+    for (int i = tid; i < m; i += nt) {
+        SparseRow row;
+        cons.row(i, row);
+        double v = -row.beta;
+        for (int k = 0; k < row.nnz; ++k) v += row.val[k] * w.xe[row.idx[k]];
+        w.s[i] = v;
+        w.pos[i] = -1;
+    }
+    blk.sync();
+    int eq_next = 0;
+    for (;;) {
+        // ---- choose the constraint to add: pending equalities first, then the most violated row
+        int p = -1;
+        double sp = 0.0;
+        bool is_eq = false;
+        if (eq_next < meq) {
+            p = eq_next++;
+            sp = w.s[p];
+            is_eq = true;
+        } else {
+            double best = 0.0;
+            int bi = 0x7fffffff;
+            for (int i = meq + tid; i < m; i += nt) {
+                if (w.pos[i] < 0) {
+                    const double v = w.s[i];
+                    if (v < best || (v == best && i < bi)) { best = v; bi = i; }
+                }
+            }
+            blk.argmin(best, bi);
+            if (bi == 0x7fffffff || best >= -tol) break;      // primal feasible -> optimal
+            p = bi;
+            sp = best;
+        }
+        SparseRow np;
+        cons.row(p, np);
+        if (is_eq) {
+            const bool rev = sp > 0.0;      // equality violated from above: use the reversed normal
+            if (rev) {
+                for (int k = 0; k < np.nnz; ++k) np.val[k] = -np.val[k];
+                sp = -sp;
+            }
+            if (tid == 0) w.esign[p] = rev ? -1.0 : 1.0;
+        }
+        if (tid == 0) w.u[q] = 0.0;
+        bool added = false;
+        while (!added) {
+            ++iters;
+            if (iters > maxit) { status = GI_MAXIT; break; }
+            // d = J' n_p  (sparse combination of rows of E)
+            for (int i = tid; i < nv; i += nt) {
+                double v = 0.0;
+                for (int k = 0; k < np.nnz; ++k) v += np.val[k] * w.E[(size_t)np.idx[k] * ld + i];
+                w.d[i] = v;
+            }
+            blk.sync();
+            // ze = E[:, q:] d[q:] ;  r = R^-1 d[:q]
+            for (int row = tid; row < ne + q; row += nt) {
+                if (row < ne) {
+                    const double* e = w.E + (size_t)row * ld;
+                    double v = 0.0;
+                    for (int k = q; k < nv; ++k) v += e[k] * w.d[k];
+                    w.ze[row] = v;
+                } else {
+                    const int j = row - ne;
+                    double v = 0.0;
+                    for (int k = j; k < q; ++k) v += w.Ui[gi_tri(k) + j] * w.d[k];
+                    w.r[j] = v;
+                }
+            }
+            // |d2|^2, |d|^2
+            double p2 = 0.0, pa = 0.0;
+            for (int k = tid; k < nv; k += nt) {
+                const double v = w.d[k] * w.d[k];
+                pa += v;
+                if (k >= q) p2 += v;
+            }
+            blk.sync();      // ze, r visible
+            const double d2n = blk.sum(p2);
+            const double dn = blk.sum(pa);
+            // dual step length t1 (inequalities in the working set only)
+            double t1 = INFINITY;
+            int l = 0x7fffffff;
+            for (int j = tid; j < q; j += nt) {
+                if (w.act[j] >= meq && w.r[j] > 1e-13) {
+                    const double tj = w.u[j] / w.r[j];
+                    if (tj < t1 || (tj == t1 && j < l)) { t1 = tj; l = j; }
+                }
+            }
+            blk.argmin(t1, l);
+            const bool dep = (q >= nv) || (d2n <= 1e-22 * fmax(1.0, dn)) || (d2n <= 1e-28);
+            const double t2 = dep ? INFINITY : (-sp / d2n);
+            const double t = fmin(t1, t2);
+            if (t == INFINITY) {
+                if (is_eq && fabs(sp) <= 1e-9) break;      // redundant (dependent, consistent) equality: skip it
+                status = GI_INFEASIBLE;
+                break;
+            }
+            if (t2 == INFINITY) {
+                // step in dual space only, then drop l
+                for (int j = tid; j <= q; j += nt) w.u[j] += t * ((j < q) ? -w.r[j] : 1.0);
+                blk.sync();
+                gi_drop(blk, w, nv, ne, ld, q, l);
+                continue;
+            }
+            // primal + dual step
+            for (int i = tid; i < ne; i += nt) w.xe[i] += t * w.ze[i];
+            for (int j = tid; j <= q; j += nt) w.u[j] += t * ((j < q) ? -w.r[j] : 1.0);
+            for (int i = tid; i < m; i += nt) {
+                SparseRow row;
+                cons.row(i, row);
+                double v = 0.0;
+                for (int k = 0; k < row.nnz; ++k) v += row.val[k] * w.ze[row.idx[k]];
+                w.s[i] += t * v;
+            }
+            sp += t * d2n;
+            blk.sync();
+            if (t == t2) {
+                // full step: add p.  Householder on d[q:]
+                const double alpha = sqrt(d2n);
+                const double d0 = w.d[q];
+                const double sg = (d0 >= 0.0) ? 1.0 : -1.0;
+                const double vv = 2.0 * alpha * (alpha + fabs(d0));
+                const double rho = -sg * alpha;
+                if (vv > 0.0) {
+                    const double f = 2.0 / vv;
+                    for (int row = tid; row < ne; row += nt) {
+                        double* e = w.E + (size_t)row * ld;
+                        const double wv = f * (w.ze[row] + sg * alpha * e[q]);
+                        e[q] -= wv * (d0 + sg * alpha);
+                        for (int k = q + 1; k < nv; ++k) e[k] -= wv * w.d[k];
+                    }
+                }
+                double* col = w.Ui + gi_tri(q);
+                for (int j = tid; j < q; j += nt) col[j] = -w.r[j] / rho;
+                if (tid == 0) {
+                    col[q] = 1.0 / rho;
+                    w.act[q] = p;
+                    w.pos[p] = q;
+                }
+                blk.sync();
+                q += 1;
+                added = true;
+            } else {
+                gi_drop(blk, w, nv, ne, ld, q, l);
+            }
+        }
+        if (status != GI_OK) break;
+    }
+    // multipliers
+    for (int i = tid; i < m; i += nt) lam[i] = 0.0;
+    blk.sync();
+    for (int j = tid; j < q; j += nt) lam[w.act[j]] = (w.act[j] < meq) ? w.esign[w.act[j]] * w.u[j] : w.u[j];
+    blk.sync();
+    *iters_out = iters;
+    *nact_out = q;
+    return status;
+}
+
+}  // namespace ftmpc

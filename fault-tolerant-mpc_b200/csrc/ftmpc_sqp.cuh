@@ -1,0 +1,535 @@
+// ftmpc_sqp.cuh -- the per-instance phases of the MPC solve (SQP on the reference NLP).
+//
+// The reference builds the NLP once with CasADi and lets IPOPT iterate on it
+//   SpiralingController.build_solver   ft_mpc/controllers/spiraling_mpc.py:87-238
+//   SpiralingController.solve_mpc      ft_mpc/controllers/spiraling_mpc.py:319-354
+// Here the same NLP is solved in its reduced (single-shooting) form by an SQP whose sub-problem is
+// the condensed QP the north star names:
+//   phase_ls   : step acceptance (l1 merit), forward RK4 rollout, cost/constraint values     [thread / instance]
+//   phase_lin  : RK4 Jacobians, costates, exact stage Hessians of the Lagrangian              [warp   / instance]
+//   phase_qp   : condensing (H, g, rows), Cholesky, dual active-set QP                         [CTA    / instance]
+//   phase_out  : u0, active set, thrust allocation                                            [thread / instance]
+// Decision vector and constraint order follow the reference: z = [u_0..u_{N-1} | x_0..x_N]
+// (:110-114), inequalities [hull_0 .. hull_{N-1} | terminal] (:206-214).
+#pragma once
+#include "ftmpc.h"
+#include "ftmpc_block.cuh"
+#include "ftmpc_dyn.cuh"
+#include "ftmpc_gi.cuh"
+#include "ftmpc_linalg.cuh"
+#include "ftmpc_terminal.cuh"
+
+namespace ftmpc {
+
+// ---- per-instance workspace (global memory), offsets in doubles ------------------------------
+struct WsLayout {
+    int N, n, nv, mc, m;
+    size_t oU, oD, oX, oC, oLam, oMu, oJz, oWz, oGV, oHV, oSc, stride;
+};
+enum {      // scalar slots
+    SC_F = 0, SC_CSUM, SC_NU, SC_GD, SC_THETA, SC_DMAX, SC_DELTA, SC_LAMMAX, SC_STATUS, SC_ITER, SC_QPIT,
+    SC_NACT, SC_CHOLFAIL, SC_QPST, SC_ALPHA, SC_CMAX, SC_COUNT
+};
+FT_HD WsLayout ws_layout(int N) {
+    WsLayout L;
+    L.N = N; L.n = FTMPC_NU * N; L.nv = L.n + 1; L.mc = FTMPC_NH * N + FTMPC_NF; L.m = L.mc + 2;
+    size_t o = 0;
+    L.oU = o; o += L.n;
+    L.oD = o; o += L.nv;
+    L.oX = o; o += (size_t)(N + 1) * FTMPC_NX;
+    L.oC = o; o += L.mc;
+    L.oLam = o; o += L.m;
+    L.oMu = o; o += (size_t)(N + 1) * FTMPC_NX;
+    L.oJz = o; o += (size_t)N * 169;
+    L.oWz = o; o += (size_t)N * 169;
+    L.oGV = o; o += FTMPC_NE;
+    L.oHV = o; o += FTMPC_NE * FTMPC_NE;
+    L.oSc = o; o += SC_COUNT;
+    L.stride = (o + 7) & ~(size_t)7;
+    return L;
+}
+
+// ---- batch I/O ---------------------------------------------------------------------------------
+struct StepIO {
+    int batch;
+    const double* state;        // [B,13] robot state
+    const double* xref;         // [B,N+1,9]
+    const double* uref;         // [B,N+1,6] or null
+    const uint16_t* fault_mask; // [B]
+    const double* fault_force;  // [B,16]
+    const int32_t* hull_idx;    // [B]
+    const double* hull_table;   // device/host table
+    int warm;
+    double* z_warm;             // [B, 6N+13(N+1)]
+    double* thrust;             // [B,16]
+    double* u0;                 // [B,6]
+    uint32_t* active_set;       // [B, ceil(mc/32)]
+    int32_t* status;            // [B]
+    int32_t* iters;             // [B,2]
+    double* cost;               // [B]
+    double* ws;                 // workspace
+};
+
+FT_HD DynConsts dyn_consts(const ftmpc_config& c) {
+    DynConsts k;
+    k.dt = c.dt; k.mass = c.mass;
+    for (int i = 0; i < 3; ++i) { k.Jd[i] = c.inertia[i]; k.r[i] = c.r[i]; }
+    return k;
+}
+
+// total body wrench of stage t:  u_t + [Rot(q_t)^T ur_F ; ur_tau] + [f_virt ; 0]
+//   spiraling_mpc.py:156-172 (u_t + u_ref_rot + u_comp) + spiral_model.py:61 (+ D f_fault)  ==> fault-independent
+FT_HD void stage_wrench(const ftmpc_config& c, const double* u, const double* ur, const double* q, double* Wr) {
+    for (int i = 0; i < 3; ++i) { Wr[i] = u[i] + c.f_virt[i]; Wr[3 + i] = u[3 + i]; }
+    if (ur) {
+        double R[9], a[3];
+        rot_mat(q, R);
+        mat3_tmul(R, ur, a);
+        for (int i = 0; i < 3; ++i) { Wr[i] += a[i]; Wr[3 + i] += ur[3 + i]; }
+    }
+}
+
+// forward rollout at U + alpha*d: states, cost, constraint values (c <= 0 feasible).
+FT_HD void rollout_eval(const ftmpc_config& cfg, const WsLayout& L, const double* hull, const double* xref,
+                        const double* uref, const double* U, const double* d, double alpha, double* X, double* C,
+                        double& f, double& csum, double& cmax) {
+    const DynConsts k = dyn_consts(cfg);
+    const int N = L.N;
+    double x[FTMPC_NX], xn[FTMPC_NX], u[FTMPC_NU], Wr[FTMPC_NU];
+    for (int i = 0; i < FTMPC_NX; ++i) x[i] = X[i];
+    f = 0.0; csum = 0.0; cmax = 0.0;
+    const double* Ah = hull;
+    const double* bh = hull + FTMPC_NH * FTMPC_NU;
+    for (int t = 0; t < N; ++t) {
+        for (int j = 0; j < FTMPC_NU; ++j) u[j] = U[t * FTMPC_NU + j] + alpha * d[t * FTMPC_NU + j];
+        stage_wrench(cfg, u, uref ? uref + t * FTMPC_NU : nullptr, x + 9, Wr);
+        for (int j = 0; j < FTMPC_NE; ++j) {                            // running cost, spiraling_mpc.py:188
+            const double e = x[j] - xref[t * FTMPC_NE + j];
+            f += cfg.Q[j] * e * e;
+        }
+        for (int j = 0; j < FTMPC_NU; ++j) f += cfg.R[j] * u[j] * u[j];
+        for (int i = 0; i < FTMPC_NH; ++i) {                            // hull rows, spiraling_mpc.py:175-177
+            double v = -bh[i];
+            for (int j = 0; j < FTMPC_NU; ++j) v += Ah[i * FTMPC_NU + j] * Wr[j];
+            C[t * FTMPC_NH + i] = v;
+            if (v > 0.0) { csum += v; cmax = fmax(cmax, v); }
+        }
+        rk4_step(k, x, Wr, xn);                                        // spiraling_mpc.py:171
+        for (int i = 0; i < FTMPC_NX; ++i) { x[i] = xn[i]; X[(t + 1) * FTMPC_NX + i] = xn[i]; }
+    }
+    double e[FTMPC_NE];
+    for (int j = 0; j < FTMPC_NE; ++j) e[j] = x[j] - xref[N * FTMPC_NE + j];
+    f += terminal_value(cfg, e);                                        // spiraling_mpc.py:195-196
+    for (int i = 0; i < FTMPC_NF; ++i) {                                // terminal set, spiraling_mpc.py:199-202
+        double v = -cfg.bf[i];
+        for (int j = 0; j < FTMPC_NE; ++j) v += cfg.Af[i * FTMPC_NE + j] * e[j];
+        C[FTMPC_NH * N + i] = v;
+        if (v > 0.0) { csum += v; cmax = fmax(cmax, v); }
+    }
+    if (!(f == f) || !(csum == csum)) { f = INFINITY; csum = INFINITY; }
+}
+
+// ---- phase_ls: initialise (first != 0) or accept the QP step, then re-evaluate -----------------------
+FT_HD void phase_ls(const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst, int first) {
+    double* w = io.ws + (size_t)inst * L.stride;
+    double* sc = w + L.oSc;
+    const int N = L.N;
+    const double* xref = io.xref + (size_t)inst * (N + 1) * FTMPC_NE;
+    const double* uref = io.uref ? io.uref + (size_t)inst * (N + 1) * FTMPC_NU : nullptr;
+    const double* hull = io.hull_table + (size_t)io.hull_idx[inst] * FTMPC_HULL_STRIDE;
+    double* U = w + L.oU;
+    double* D = w + L.oD;
+    double* X = w + L.oX;
+    double* C = w + L.oC;
+    double f, csum, cmax;
+    if (first) {
+        const DynConsts k = dyn_consts(cfg);
+        robot_to_center(k, io.state + (size_t)inst * FTMPC_NX, X);          // spiraling_mpc.py:290
+        const double* zw = io.z_warm + (size_t)inst * (L.n + (size_t)(N + 1) * FTMPC_NX);
+        for (int t = 0; t < N; ++t)                                          // warm start shift, :324-331
+            for (int j = 0; j < FTMPC_NU; ++j)
+                U[t * FTMPC_NU + j] = (io.warm && t + 1 < N) ? zw[(t + 1) * FTMPC_NU + j] : 0.0;
+        for (int i = 0; i < L.nv; ++i) D[i] = 0.0;
+        for (int i = 0; i < L.m; ++i) w[L.oLam + i] = 0.0;
+        for (int i = 0; i < SC_COUNT; ++i) sc[i] = 0.0;
+        sc[SC_NU] = 1.0;
+        sc[SC_THETA] = -1.0;                       // first QP uses the Gauss-Newton model
+        sc[SC_STATUS] = FTMPC_ST_RUNNING;
+        rollout_eval(cfg, L, hull, xref, uref, U, D, 0.0, X, C, f, csum, cmax);
+        if (!(f < INFINITY)) sc[SC_STATUS] = FTMPC_ST_QPFAIL;
+    } else {
+        if (sc[SC_STATUS] != FTMPC_ST_RUNNING) return;
+        if (sc[SC_QPST] != 0.0) { sc[SC_STATUS] = FTMPC_ST_QPFAIL; return; }
+        sc[SC_ITER] += 1.0;
+        const double nu = fmax(sc[SC_NU], 1.1 * sc[SC_LAMMAX]);
+        sc[SC_NU] = nu;
+        const double phi0 = sc[SC_F] + nu * sc[SC_CSUM];
+        const double dphi = sc[SC_GD] - nu * sc[SC_CSUM];
+        double alpha = 1.0;
+        for (;;) {
+            rollout_eval(cfg, L, hull, xref, uref, U, D, alpha, X, C, f, csum, cmax);
+            const double phi = f + nu * csum;
+            if (phi <= phi0 + 1e-4 * alpha * dphi || alpha < 1e-8) break;
+            alpha *= 0.5;
+        }
+        sc[SC_ALPHA] = alpha;
+        if (!(f < INFINITY)) { sc[SC_STATUS] = FTMPC_ST_QPFAIL; return; }
+        for (int i = 0; i < L.n; ++i) U[i] += alpha * D[i];
+        if (sc[SC_DMAX] <= cfg.sqp_tol) {
+            sc[SC_STATUS] = (cmax <= cfg.feas_tol) ? FTMPC_ST_OK : FTMPC_ST_INFEASIBLE;
+        } else if (sc[SC_ITER] >= cfg.max_sqp_iter) {
+            sc[SC_STATUS] = FTMPC_ST_MAXITER;
+        }
+    }
+    sc[SC_F] = f; sc[SC_CSUM] = csum; sc[SC_CMAX] = cmax;
+    // terminal gradient / Hessian at the accepted point
+    double e[FTMPC_NE];
+    for (int j = 0; j < FTMPC_NE; ++j) e[j] = X[N * FTMPC_NX + j] - xref[N * FTMPC_NE + j];
+    terminal_eval(cfg, e, w + L.oGV, w + L.oHV);
+}
+
+// ---- phase_lin: Jacobians, costates, stage Hessians (lanes of one warp / a serial loop) -------------
+template <class Blk>
+FT_HD void phase_lin(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst) {
+    double* w = io.ws + (size_t)inst * L.stride;
+    const double* sc = w + L.oSc;
+    if (sc[SC_STATUS] != FTMPC_ST_RUNNING) return;
+    const int N = L.N, tid = blk.tid(), nt = blk.nthreads();
+    const DynConsts k = dyn_consts(cfg);
+    const double* xref = io.xref + (size_t)inst * (N + 1) * FTMPC_NE;
+    const double* uref = io.uref ? io.uref + (size_t)inst * (N + 1) * FTMPC_NU : nullptr;
+    const double* U = w + L.oU;
+    const double* X = w + L.oX;
+    double* Jz = w + L.oJz;
+    double* Wz = w + L.oWz;
+    double* Mu = w + L.oMu;
+    const double* lam = w + L.oLam;
+    // first-order columns
+    for (int it = tid; it < N * 13; it += nt) {
+        const int t = it / 13, col = it % 13;
+        double Wr[FTMPC_NU];
+        stage_wrench(cfg, U + t * FTMPC_NU, uref ? uref + t * FTMPC_NU : nullptr, X + t * FTMPC_NX + 9, Wr);
+        double jc[13];
+        rk4_column(k, X + t * FTMPC_NX, Wr, col, nullptr, jc, nullptr);
+        for (int i = 0; i < 13; ++i) Jz[(size_t)it * 13 + i] = jc[i];
+    }
+    blk.sync();
+    // costates  mu_N = [grad V_f + A_f' lam_term ; 0],  mu_t = [2Q e_t ; 0] + A_t' mu_{t+1}
+    for (int i = tid; i < FTMPC_NX; i += nt) {
+        double v = 0.0;
+        if (i < FTMPC_NE) {
+            v = w[L.oGV + i];
+            for (int r = 0; r < FTMPC_NF; ++r) v += cfg.Af[r * FTMPC_NE + i] * lam[FTMPC_NH * N + r];
+        }
+        Mu[N * FTMPC_NX + i] = v;
+    }
+    blk.sync();
+    for (int t = N - 1; t >= 1; --t) {
+        const double* mn = Mu + (t + 1) * FTMPC_NX;
+        for (int i = tid; i < FTMPC_NX; i += nt) {
+            double v = (i < FTMPC_NE) ? 2.0 * cfg.Q[i] * (X[t * FTMPC_NX + i] - xref[t * FTMPC_NE + i]) : 0.0;
+            if (i < 3) v += mn[i];
+            else if (i < 6) v += k.dt * mn[i - 3] + mn[i];
+            else {
+                const double* col = Jz + ((size_t)t * 13 + (i - 6)) * 13;
+                for (int r = 0; r < 13; ++r) v += col[r] * mn[r];
+            }
+            Mu[t * FTMPC_NX + i] = v;
+        }
+        blk.sync();
+    }
+    // second-order columns: Hessian of mu_{t+1}' RK4(x_t, W_t) in z-space
+    for (int it = tid; it < N * 13; it += nt) {
+        const int t = it / 13, col = it % 13;
+        double Wr[FTMPC_NU];
+        stage_wrench(cfg, U + t * FTMPC_NU, uref ? uref + t * FTMPC_NU : nullptr, X + t * FTMPC_NX + 9, Wr);
+        double jc[13], hc[13];
+        rk4_column(k, X + t * FTMPC_NX, Wr, col, Mu + (t + 1) * FTMPC_NX, jc, hc);
+        for (int i = 0; i < 13; ++i) Wz[(size_t)it * 13 + i] = hc[i];
+    }
+    blk.sync();
+}
+
+// ---- the MPC QP seen by the active-set solver -----------------------------------------------------
+// variables (d[0..n), delta); extended rows: [d ; delta ; dx_N[0..9)].  Row i (i < mc):
+//   J_i d - delta * max(c_i,0) <= -c_i        (Powell/Schittkowski elastic relaxation)
+struct MpcCons {
+    int N, n, nv, mc;
+    const double* Ah;       // [26][6]
+    const double* Af;       // [72][9]
+    const double* cv;       // [mc] constraint values at the linearisation point
+    FT_HD void row(int p, SparseRow& r) const {
+        int k = 0;
+        if (p < FTMPC_NH * N) {
+            const int t = p / FTMPC_NH, i = p % FTMPC_NH;
+            for (int j = 0; j < FTMPC_NU; ++j) {
+                const double a = Ah[i * FTMPC_NU + j];
+                if (a != 0.0) { r.idx[k] = t * FTMPC_NU + j; r.val[k] = -a; ++k; }
+            }
+        } else if (p < mc) {
+            const int i = p - FTMPC_NH * N;
+            for (int j = 0; j < FTMPC_NE; ++j) {
+                const double a = Af[i * FTMPC_NE + j];
+                if (a != 0.0) { r.idx[k] = nv + j; r.val[k] = -a; ++k; }
+            }
+        } else if (p == mc) {          // delta >= 0
+            r.idx[0] = n; r.val[0] = 1.0; r.nnz = 1; r.beta = 0.0;
+            return;
+        } else {                       // delta <= 1
+            r.idx[0] = n; r.val[0] = -1.0; r.nnz = 1; r.beta = -1.0;
+            return;
+        }
+        const double c = cv[p];
+        if (c > 0.0) { r.idx[k] = n; r.val[k] = c; ++k; }
+        r.nnz = k;
+        r.beta = c;
+    }
+};
+
+// per-CTA scratch carved out of one buffer of doubles (shared memory on the device)
+struct QpScratch {
+    double *E, *RS, *G, *T, *g, *cv, *hull;
+    GiWork gi;
+    double* dg;
+    size_t total;       // doubles
+};
+FT_HD size_t qp_scratch_doubles(int N) {
+    const WsLayout L = ws_layout(N);
+    const size_t nv = L.nv, ne = nv + FTMPC_NE, n = L.n;
+    size_t rs = nv * (nv + 1) / 2;
+    if ((size_t)N * 338 > rs) rs = (size_t)N * 338;
+    size_t gi_vec = ne /*xe*/ + L.m /*s*/ + (nv + 1) /*u*/ + nv /*d*/ + ne /*ze*/ + nv /*r*/ + 2 * nv /*cs*/ + (nv + 1) /*tmp*/ + nv /*sub*/ + nv /*dg*/ + 2;
+    size_t tt = (size_t)FTMPC_NE * n;
+    if (tt > gi_vec) gi_vec = tt;
+    size_t ints = ((nv + 1) + L.m + (nv + 1) + 1) / 2 + 1;
+    return ne * nv + rs + (size_t)FTMPC_NX * nv + gi_vec + nv /*g*/ + L.mc /*cv*/ + FTMPC_HULL_STRIDE + ints + 8;
+}
+FT_HD QpScratch qp_carve(double* buf, int N) {
+    const WsLayout L = ws_layout(N);
+    const size_t nv = L.nv, ne = nv + FTMPC_NE, n = L.n;
+    QpScratch s;
+    double* p = buf;
+    s.E = p; p += ne * nv;
+    size_t rs = nv * (nv + 1) / 2;
+    if ((size_t)N * 338 > rs) rs = (size_t)N * 338;
+    s.RS = p; p += rs;
+    s.G = p; p += (size_t)FTMPC_NX * nv;
+    s.g = p; p += nv;
+    s.cv = p; p += L.mc;
+    s.hull = p; p += FTMPC_HULL_STRIDE;
+    double* v = p;
+    s.T = v;                      // condensing scratch aliases the active-set vectors
+    s.gi.E = s.E; s.gi.Ui = s.RS;
+    s.gi.xe = v; v += ne;
+    s.gi.s = v; v += L.m;
+    s.gi.u = v; v += nv + 1;
+    s.gi.d = v; v += nv;
+    s.gi.ze = v; v += ne;
+    s.gi.r = v; v += nv;
+    s.gi.cs = v; v += 2 * nv;
+    s.gi.tmp = v; v += nv + 1;
+    s.gi.sub = v; v += nv;
+    s.dg = v; v += nv;
+    s.gi.esign = v; v += 2;
+    size_t gi_vec = (size_t)(v - p), tt = (size_t)FTMPC_NE * n;
+    p += (tt > gi_vec) ? tt : gi_vec;
+    int* ip = reinterpret_cast<int*>(p);
+    s.gi.act = ip; ip += nv + 1;
+    s.gi.pos = ip; ip += L.m;
+    s.gi.itmp = ip; ip += nv + 1;
+    s.total = qp_scratch_doubles(N);
+    return s;
+}
+
+// condensed Hessian (lower triangle of the n x n block of E, ld = nv) and gradient at blend theta
+template <class Blk>
+FT_HD void condense(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const QpScratch& s, const double* Jz,
+                    const double* Wz, const double* X, const double* U, const double* xref, const double* gradV,
+                    const double* hessV, double theta) {
+    const int N = L.N, n = L.n, ld = L.nv, tid = blk.tid(), nt = blk.nthreads();
+    double* H = s.E;
+    double* G = s.G;          // 13 x ld, current d x_t / d U
+    double* T = s.T;
+    for (int i = tid; i < FTMPC_NX * ld; i += nt) G[i] = 0.0;
+    for (int i = tid; i < L.nv; i += nt) s.g[i] = 0.0;
+    blk.sync();
+    for (int t = 0; t < N; ++t) {
+        const double* jz = Jz + (size_t)t * 169;     // [col][row]
+        const double* wz = Wz + (size_t)t * 169;     // [col][row], symmetrised on use
+        const int nc = FTMPC_NU * t;                 // columns of G that are live
+        // T[k][b] = theta * sum_l Wz[k][l] G[6+l][b],  k,l in (w,q)
+        for (int idx = tid; idx < 7 * nc; idx += nt) {
+            const int kk = idx / nc, b = idx % nc;
+            double v = 0.0;
+            for (int l = 0; l < 7; ++l) v += 0.5 * (wz[kk * 13 + l] + wz[l * 13 + kk]) * G[(6 + l) * ld + b];
+            T[kk * n + b] = theta * v;
+        }
+        blk.sync();
+        // accumulate into the live block  H[a][b], a,b < nc
+        for (int bi = 0; bi < t; ++bi) {
+            for (int idx = tid; idx < 36 * (bi + 1); idx += nt) {
+                const int bj = idx / 36, rem = idx % 36;
+                const int a = 6 * bi + rem / 6, b = 6 * bj + rem % 6;
+                if (b > a) continue;
+                double v = 0.0;
+                for (int kk = 0; kk < FTMPC_NE; ++kk) v += 2.0 * cfg.Q[kk] * G[kk * ld + a] * G[kk * ld + b];
+                for (int kk = 0; kk < 7; ++kk) v += G[(6 + kk) * ld + a] * T[kk * n + b];
+                H[(size_t)a * ld + b] += v;
+            }
+        }
+        // new block row t:  H[6t+j][b]
+        for (int idx = tid; idx < 6 * (nc + 6); idx += nt) {
+            const int j = idx / (nc + 6), b = idx % (nc + 6);
+            double v = 0.0;
+            if (b < nc) {
+                for (int l = 0; l < 7; ++l) v += 0.5 * (wz[(7 + j) * 13 + l] + wz[l * 13 + 7 + j]) * G[(6 + l) * ld + b];
+                v *= theta;
+            } else {
+                const int j2 = b - nc;
+                v = theta * 0.5 * (wz[(7 + j) * 13 + 7 + j2] + wz[(7 + j2) * 13 + 7 + j]);
+                if (j2 == j) v += 2.0 * cfg.R[j];
+            }
+            H[(size_t)(nc + j) * ld + b] = v;
+        }
+        // gradient
+        for (int a = tid; a < nc + 6; a += nt) {
+            if (a < nc) {
+                double v = 0.0;
+                for (int kk = 0; kk < FTMPC_NE; ++kk)
+                    v += 2.0 * cfg.Q[kk] * (X[t * FTMPC_NX + kk] - xref[t * FTMPC_NE + kk]) * G[kk * ld + a];
+                s.g[a] += v;
+            } else {
+                s.g[a] = 2.0 * cfg.R[a - nc] * U[a];
+            }
+        }
+        blk.sync();
+        // G_{t+1} = A_t G_t + B_t E_t   (thread per column)
+        for (int a = tid; a < nc + 6; a += nt) {
+            double o[13], nw[13];
+            if (a < nc) {
+                for (int r = 0; r < 13; ++r) o[r] = G[r * ld + a];
+                for (int r = 0; r < 13; ++r) {
+                    double v = (r < 3) ? o[r] + cfg.dt * o[r + 3] : ((r < 6) ? o[r] : 0.0);
+                    for (int l = 0; l < 7; ++l) v += jz[l * 13 + r] * o[6 + l];
+                    nw[r] = v;
+                }
+            } else {
+                for (int r = 0; r < 13; ++r) nw[r] = jz[(7 + a - nc) * 13 + r];
+            }
+            for (int r = 0; r < 13; ++r) G[r * ld + a] = nw[r];
+        }
+        blk.sync();
+    }
+    // terminal cost:  H += G_N' Ht G_N,  g += G_N' grad V      Ht = term_quad + theta (hessV - term_quad)
+    for (int idx = tid; idx < FTMPC_NE * n; idx += nt) {
+        const int kk = idx / n, b = idx % n;
+        double v = 0.0;
+        for (int l = 0; l < FTMPC_NE; ++l) {
+            const double q0 = cfg.term_quad[kk * FTMPC_NE + l];
+            v += (q0 + theta * (hessV[kk * FTMPC_NE + l] - q0)) * G[l * ld + b];
+        }
+        T[kk * n + b] = v;
+    }
+    blk.sync();
+    for (int bi = 0; bi < N; ++bi) {
+        for (int idx = tid; idx < 36 * (bi + 1); idx += nt) {
+            const int bj = idx / 36, rem = idx % 36;
+            const int a = 6 * bi + rem / 6, b = 6 * bj + rem % 6;
+            if (b > a) continue;
+            double v = 0.0;
+            for (int kk = 0; kk < FTMPC_NE; ++kk) v += G[kk * ld + a] * T[kk * n + b];
+            H[(size_t)a * ld + b] += v;
+        }
+    }
+    for (int a = tid; a < n; a += nt) {
+        double v = 0.0;
+        for (int kk = 0; kk < FTMPC_NE; ++kk) v += gradV[kk] * G[kk * ld + a];
+        s.g[a] += v;
+    }
+    blk.sync();
+}
+
+// ---- phase_qp ------------------------------------------------------------------------------------------
+template <class Blk>
+FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst, double* scratch) {
+    double* w = io.ws + (size_t)inst * L.stride;
+    double* sc = w + L.oSc;
+    if (sc[SC_STATUS] != FTMPC_ST_RUNNING) return;
+    const int N = L.N, n = L.n, nv = L.nv, ne = nv + FTMPC_NE, ld = nv, tid = blk.tid(), nt = blk.nthreads();
+    const QpScratch s = qp_carve(scratch, N);
+    const double* xref = io.xref + (size_t)inst * (N + 1) * FTMPC_NE;
+    const double* hull_g = io.hull_table + (size_t)io.hull_idx[inst] * FTMPC_HULL_STRIDE;
+    // stage data -> scratch (the R^-1 region is free until the active-set solve starts)
+    double* Jz = s.RS;
+    double* Wz = s.RS + (size_t)N * 169;
+    for (int i = tid; i < N * 169; i += nt) { Jz[i] = w[L.oJz + i]; Wz[i] = w[L.oWz + i]; }
+    for (int i = tid; i < L.mc; i += nt) s.cv[i] = w[L.oC + i];
+    for (int i = tid; i < FTMPC_HULL_STRIDE; i += nt) s.hull[i] = hull_g[i];
+    blk.sync();
+    // blend schedule for the exact second-order terms
+    double theta = sc[SC_THETA];
+    theta = (theta < 0.0) ? 0.0 : ((theta == 0.0) ? 0.125 : fmin(1.0, 2.0 * theta));
+    int fails = 0;
+    for (;;) {
+        condense(blk, cfg, L, s, Jz, Wz, w + L.oX, w + L.oU, xref, w + L.oGV, w + L.oHV, theta);
+        double dmaxl = 0.0;
+        for (int i = tid; i < n; i += nt) dmaxl = fmax(dmaxl, fabs(s.E[(size_t)i * ld + i]));
+        const double dscale = blk.max(dmaxl);
+        const int bad = chol_lower(blk, n, ld, s.E, 1e-10 * fmax(1.0, dscale));
+        if (!bad) break;
+        ++fails;
+        blk.sync();
+        if (theta <= 0.0) { if (tid == 0) { sc[SC_QPST] = 3.0; } return; }
+        theta = (theta > 0.125) ? 0.5 * theta : 0.0;
+    }
+    tri_inv_transpose(blk, n, ld, s.E, s.dg);
+    // slack variable column/row, extension rows  X J  (X = d x_N[0:9] / d U)
+    for (int i = tid; i < nv; i += nt) {
+        s.E[(size_t)i * ld + n] = 0.0;
+        s.E[(size_t)n * ld + i] = (i == n) ? 1.0 / sqrt(cfg.rho_slack) : 0.0;
+    }
+    blk.sync();
+    for (int idx = tid; idx < FTMPC_NE * nv; idx += nt) {
+        const int kk = idx / nv, i = idx % nv;
+        double v = 0.0;
+        if (i < n) for (int r = 0; r <= i; ++r) v += s.G[kk * ld + r] * s.E[(size_t)r * ld + i];
+        s.E[(size_t)(nv + kk) * ld + i] = v;
+    }
+    // unconstrained minimiser  x = -J J' g
+    for (int i = tid; i < nv; i += nt) {
+        double v = 0.0;
+        if (i < n) for (int r = 0; r <= i; ++r) v += s.E[(size_t)r * ld + i] * s.g[r];
+        s.gi.d[i] = v;
+    }
+    blk.sync();
+    for (int row = tid; row < ne; row += nt) {
+        double v = 0.0;
+        for (int kk = 0; kk < nv; ++kk) v += s.E[(size_t)row * ld + kk] * s.gi.d[kk];
+        s.gi.xe[row] = -v;
+    }
+    blk.sync();
+    MpcCons cons{N, n, nv, L.mc, s.hull, cfg.Af, s.cv};
+    int qit = 0, nact = 0;
+    const int st = gi_solve(blk, cons, s.gi, nv, ne, ld, L.m, 0, w + L.oLam, cfg.max_qp_iter, cfg.qp_tol, &qit, &nact);
+    // step, directional derivative, multiplier bound
+    double gd = 0.0, dmx = 0.0, lmx = 0.0;
+    for (int i = tid; i < n; i += nt) {
+        const double di = s.gi.xe[i];
+        w[L.oD + i] = di;
+        gd += s.g[i] * di;
+        dmx = fmax(dmx, fabs(di));
+    }
+    for (int i = tid; i < L.mc; i += nt) lmx = fmax(lmx, w[L.oLam + i]);
+    gd = blk.sum(gd);
+    dmx = blk.max(dmx);
+    lmx = blk.max(lmx);
+    if (tid == 0) {
+        w[L.oD + n] = s.gi.xe[n];
+        sc[SC_GD] = gd; sc[SC_DMAX] = dmx; sc[SC_LAMMAX] = lmx; sc[SC_DELTA] = s.gi.xe[n];
+        sc[SC_THETA] = theta; sc[SC_QPIT] += qit; sc[SC_NACT] = nact; sc[SC_CHOLFAIL] += fails;
+        sc[SC_QPST] = (st == GI_OK && dmx == dmx) ? 0.0 : (double)(st ? st : 4);
+    }
+    blk.sync();
+}
+
+}  // namespace ftmpc
