@@ -1,0 +1,256 @@
+"""SpiralingController -- drop-in for ft_mpc/controllers/spiraling_mpc.py:23-365 backed by libftmpc.so.
+
+Reference-facing surface kept (same names / argument meaning):
+    SpiralingController(model, params, debug=None)        spiraling_mpc.py:27-44
+    .load_trajectory(cmd, duration)                       :240-286
+    .get_control(x0, t) -> ndarray[16]                    :288-317   (B = 1, stateful warm start)
+and the batched entry the north star asks for:
+    SpiralingController(model, horizon=.., weights={"Q":..,"R":..}, fault_mask=.. | fault_sets=[..])
+    .step(state[B,13], ref[B,N+1,9], uref=None, scenario=None, warm=False) -> thrust[B,16] (torch, cuda)
+
+Python here only prepares inputs (reference window, per-fault hull table) and owns the device tensors;
+all per-step numerics run in CUDA behind include/ftmpc.h.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+from ..util.broken_thruster import BrokenThruster
+from ..util.get_trajectory import load_trajectory
+from .tools.input_bounds import hull_of_faults
+from .tools.spiral_parameters import SpiralParameters
+
+DEFAULT_Q = [1, 1, 1, 1, 1, 1, 2, 2, 2]                  # ft_mpc/config/reactive.yaml:32
+DEFAULT_R = [0.1, 0.1, 0.1, 0.01, 0.01, 0.01]           # ft_mpc/config/reactive.yaml:33
+
+
+def _require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("ft_mpc_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+    if dev.type != "cuda":
+        raise RuntimeError("ft_mpc_b200 tensors must live on a CUDA device")
+    return dev
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def hull_table_entry(A, b) -> np.ndarray:
+    """One row of the hull table: A_h padded to 26x6 with zero rows, b_h padded with 1e30 (never active)."""
+    e = np.zeros(L.HULL_STRIDE)
+    Ap, bp = np.zeros((L.NH, L.NU)), np.full(L.NH, 1e30)
+    if len(b) > L.NH:
+        raise ValueError(f"hull has {len(b)} facets, table rows hold {L.NH}")
+    Ap[:len(b)], bp[:len(b)] = A, b
+    e[:L.NH * L.NU], e[L.NH * L.NU:] = Ap.ravel(), bp
+    return e
+
+
+class BatchedMPC:
+    """Thin owner of one ftmpc handle + the device tensors of a batch.  `fault_sets` is a list of fault
+    scenarios, each a list of (thruster index, intensity); instance i uses scenario[i]."""
+
+    def __init__(self, model, horizon, Q, R, fault_sets, device=None, **solver_opts):
+        self.device = _require_cuda(device)
+        self.lib = L.lib()
+        self.N = int(horizon)
+        self.model = model
+        sp = SpiralParameters(model)
+        self.omega_des, self.f_virt, self.r = sp.omega_des, sp.f_virt, sp.r
+        # a scenario is a list of (index, intensity) or a dict {faults, A, b} carrying a precomputed hull
+        self.fault_sets = [list(fs["faults"]) if isinstance(fs, dict) else list(fs) for fs in fault_sets]
+        table, self.fault_force_tab, self.mask_tab = [], [], []
+        for fs, src in zip(self.fault_sets, fault_sets):
+            if isinstance(src, dict):
+                A, b = src["A"], src["b"]
+            else:
+                A, b = hull_of_faults(model.D, model.max_thrust, fs)       # input_bounds.py:43-76
+            table.append(hull_table_entry(A, b))
+            ff = np.zeros(L.NTHR)
+            m = 0
+            for i, inten in fs:
+                ff[i] = inten * model.max_thrust                           # sys_model.py:239
+                m |= 1 << i
+            self.fault_force_tab.append(ff)
+            self.mask_tab.append(m)
+        self.hull_table = np.ascontiguousarray(np.stack(table))
+        self.cfg = L.make_config(self.N, Q, R, dt=model.dt, mass=model.mass, inertia=model.inertia, r=self.r,
+                                 f_virt=self.f_virt, max_thrust=model.max_thrust, D=model.D,
+                                 n_hull_sets=len(self.fault_sets), **solver_opts)
+        self.handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.ftmpc_create(C.byref(self.handle), C.byref(self.cfg),
+                                          self.hull_table.ctypes.data_as(C.POINTER(C.c_double))), "ftmpc_create")
+        self.nz = self.lib.ftmpc_num_var(self.handle)
+        self.mc = self.lib.ftmpc_num_ineq(self.handle)
+        self._fault_force_dev = torch.tensor(np.stack(self.fault_force_tab), dtype=torch.float64, device=self.device)
+        self._mask_dev = torch.tensor(np.array(self.mask_tab, dtype=np.int64), device=self.device)
+        self._bufs = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and self.handle.value:
+                self.lib.ftmpc_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+    def buffers(self, B):
+        b = self._bufs.get(B)
+        if b is None:
+            nbytes = C.c_size_t()
+            L.check(self.lib.ftmpc_workspace_bytes(self.handle, B, C.byref(nbytes)), "ftmpc_workspace_bytes")
+            dev, f64 = self.device, torch.float64
+            b = dict(ws=torch.empty(nbytes.value, dtype=torch.uint8, device=dev),
+                     z=torch.zeros(B, self.nz, dtype=f64, device=dev),
+                     thrust=torch.empty(B, L.NTHR, dtype=f64, device=dev),
+                     u0=torch.empty(B, L.NU, dtype=f64, device=dev),
+                     active=torch.empty(B, (self.mc + 31) // 32, dtype=torch.int32, device=dev),
+                     status=torch.empty(B, dtype=torch.int32, device=dev),
+                     iters=torch.empty(B, 2, dtype=torch.int32, device=dev),
+                     cost=torch.empty(B, dtype=f64, device=dev))
+            self._bufs[B] = b
+        return b
+
+    def scenario_tensors(self, scenario):
+        """scenario [B] int (index into fault_sets) -> (mask uint16 [B], fault_force [B,16], hull_idx int32 [B])"""
+        scenario = scenario.to(self.device, torch.int64)
+        mask = self._mask_dev[scenario].to(torch.int16)            # bit pattern reinterpreted as uint16 by the library
+        return mask.contiguous(), self._fault_force_dev[scenario].contiguous(), scenario.to(torch.int32).contiguous()
+
+    def step(self, state, xref, uref=None, scenario=None, warm=False, out=None):
+        """All arguments are CUDA fp64 tensors; returns the dict of output tensors (no synchronisation)."""
+        B = state.shape[0]
+        b = out or self.buffers(B)
+        if scenario is None:
+            scenario = torch.zeros(B, dtype=torch.int64, device=self.device)
+        mask, ff, hidx = scenario if isinstance(scenario, tuple) else self.scenario_tensors(scenario)
+        assert state.shape == (B, L.NX) and xref.shape == (B, self.N + 1, L.NE)
+        assert state.is_contiguous() and xref.is_contiguous() and state.dtype == torch.float64
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        L.check(self.lib.ftmpc_step(self.handle, B, _ptr(state), _ptr(xref), _ptr(uref), _ptr(mask), _ptr(ff),
+                                    _ptr(hidx), int(bool(warm)), _ptr(b["z"]), _ptr(b["thrust"]), _ptr(b["u0"]),
+                                    _ptr(b["active"]), _ptr(b["status"]), _ptr(b["iters"]), _ptr(b["cost"]),
+                                    _ptr(b["ws"]), b["ws"].numel(), C.c_void_p(stream)), "ftmpc_step")
+        return b
+
+    def plant_step(self, state, thrust, scenario=None, noise=None, normalize=True):
+        B = state.shape[0]
+        if scenario is None:
+            scenario = torch.zeros(B, dtype=torch.int64, device=self.device)
+        mask, ff, _ = scenario if isinstance(scenario, tuple) else self.scenario_tensors(scenario)
+        nxt = torch.empty_like(state)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        L.check(self.lib.ftmpc_plant_step(self.handle, B, _ptr(state), _ptr(thrust), _ptr(mask), _ptr(ff), _ptr(noise),
+                                          int(bool(normalize)), _ptr(nxt), C.c_void_p(stream)), "ftmpc_plant_step")
+        return nxt
+
+
+class _PlantStepper:
+    """model.dynamics(x, u) for the host-facing SystemModel (sim_env.py:85): one un-normalised RK4 step."""
+
+    def __init__(self, model):
+        faults = [(bt.index, bt.intensity) for bt in model.broken_thrusters]
+        self.eng = BatchedMPC(model, 1, DEFAULT_Q, DEFAULT_R, [faults])
+
+    def __call__(self, x, u):
+        dev = self.eng.device
+        xs = torch.tensor(x, dtype=torch.float64, device=dev)
+        us = torch.tensor(u, dtype=torch.float64, device=dev)
+        return self.eng.plant_step(xs, us, normalize=False).cpu().numpy()
+
+
+class SpiralingController:
+    """Controller implementing micro-orbiting (reference: spiraling_mpc.py:23)."""
+
+    def __init__(self, model, params=None, debug=None, *, horizon=None, weights=None, fault_mask=None,
+                 fault_intensity=None, fault_sets=None, device=None, **solver_opts):
+        self.model = model
+        self.debug = debug
+        params = dict(params or {})
+        if horizon is not None:
+            params["horizon"] = int(horizon)
+        if weights is not None:
+            params["param_set"] = "P1"
+            params["P1"] = {"Q": list(weights["Q"]), "R": list(weights["R"])}
+        params.setdefault("horizon", 15)                                  # reactive.yaml:26
+        params.setdefault("param_set", "P1")
+        params.setdefault(params["param_set"], {"Q": DEFAULT_Q, "R": DEFAULT_R})
+        if params.get("xub") is not None or params.get("xlb") is not None:
+            raise NotImplementedError("state bounds (xub/xlb) are not configured by the reference and not supported")
+        self.params = params
+        self.Nt = params["horizon"]
+        ps = params[params["param_set"]]
+        self.Q, self.R = np.diag(ps["Q"]), np.diag(ps["R"])               # spiraling_mpc.py:91-93
+        self.spiral_params = SpiralParameters(model)
+        self.mass, self.J, self.dt = model.mass, model.inertia, model.dt
+        self.Nx, self.Nu, self.Nopt = 13, 6, 9
+        if fault_sets is None:
+            if fault_mask is not None:
+                inten = fault_intensity if fault_intensity is not None else [0.0] * 16
+                fault_sets = [[(i, float(inten[i])) for i in range(16) if (int(fault_mask) >> i) & 1]]
+            else:
+                fault_sets = [[(bt.index, bt.intensity) for bt in model.broken_thrusters]]
+        opts = dict(params.get("solver_opts") or {})
+        opts.update(solver_opts)
+        self.engine = BatchedMPC(model, self.Nt, ps["Q"], ps["R"], fault_sets, device=device, **opts)
+        self.device = self.engine.device
+        self.trajectory = None
+        self.nominal_input = None
+        self.optimal_solution = None
+        self.last_status = None
+
+    # ---- reference trajectory ------------------------------------------------- spiraling_mpc.py:240-286
+    def load_trajectory(self, cmd, duration):
+        self.assign_trajectory(load_trajectory(cmd, duration, self.dt))
+
+    def assign_trajectory(self, trajectory):
+        N = self.Nt
+        orig = np.hstack((trajectory, np.tile(trajectory[:, -1:], (1, N))))                     # :264
+        om = np.tile(self.spiral_params.omega_des, (orig.shape[1], 1)).T                        # :269-272
+        self.trajectory = np.concatenate((orig[0:6, :], om))                                    # :274-277
+        second = np.gradient(np.gradient(self.trajectory[0:3, :], axis=1), axis=1) / self.dt ** 2   # :283
+        self.nominal_input = np.vstack((second * self.mass, np.zeros_like(second)))             # :285
+        if np.abs(self.nominal_input[0:3]).max() > 1e-12:
+            raise NotImplementedError("references with non-zero nominal force (accelerating trajectories) are the "
+                                      "'next' row f-3 of SURVEY.md section 8 and not supported yet")
+        self._traj_dev = torch.tensor(self.trajectory.T.copy(), dtype=torch.float64, device=self.device)
+
+    def get_next_trajectory_part(self, t):
+        """Window of N+1 reference points starting at int(t/dt) (spiraling_mpc.py:356-365)."""
+        i = int(t / self.dt)
+        return self.trajectory[:, i:i + self.Nt + 1], self.nominal_input[:, i:i + self.Nt + 1]
+
+    def reference_window(self, step_index, batch=1):
+        """[batch, N+1, 9] device window at an integer step index (avoids the int(t/dt) rounding quirk)."""
+        w = self._traj_dev[step_index:step_index + self.Nt + 1]
+        return w.unsqueeze(0).expand(batch, -1, -1).contiguous()
+
+    # ---- single-instance reference API ------------------------------------------ spiraling_mpc.py:288-317
+    def get_control(self, x0, t):
+        x0 = np.asarray(x0, float).reshape(1, 13)
+        state = torch.tensor(x0, dtype=torch.float64, device=self.device)
+        xref = self.reference_window(int(t / self.dt))
+        out = self.engine.step(state, xref, warm=self.optimal_solution is not None)
+        self.optimal_solution = out["z"]
+        self.last_status = int(out["status"][0].item())
+        self.last_u0 = out["u0"][0].cpu().numpy()
+        return out["thrust"][0].cpu().numpy()
+
+    # ---- batched API -------------------------------------------------------------------------------------
+    def step(self, state, ref, uref=None, scenario=None, warm=False):
+        """state [B,13] robot states, ref [B,N+1,9] reference windows -> thrust [B,16] (CUDA tensor).
+        Other outputs of the solve are in `self.last` (u0, active, status, iters, cost, z)."""
+        state = torch.as_tensor(state, dtype=torch.float64, device=self.device).contiguous()
+        ref = torch.as_tensor(ref, dtype=torch.float64, device=self.device).contiguous()
+        self.last = self.engine.step(state, ref, uref, scenario, warm)
+        return self.last["thrust"]
+
+
+__all__ = ["SpiralingController", "BatchedMPC", "BrokenThruster", "hull_table_entry"]

@@ -121,7 +121,7 @@ FT_HD void phase_out(const ftmpc_config& cfg, const WsLayout& L, const StepIO& i
     }
     // u_res = u*_0 + RotFullInv(q_0) ur_0 + u_comp                     spiraling_mpc.py:301-306
     const double* ff = io.fault_force + (size_t)inst * FTMPC_NTHR;
-    double Df[FTMPC_NU], ures[FTMPC_NU], v[FTMPC_NU], vc[FTMPC_NU], ub[FTMPC_NTHR];
+    double Df[FTMPC_NU], v[FTMPC_NU], vc[FTMPC_NU], ub[FTMPC_NTHR];
     for (int i = 0; i < FTMPC_NU; ++i) {
         double a = 0.0;
         for (int j = 0; j < FTMPC_NTHR; ++j) a += cfg.D[i * FTMPC_NTHR + j] * ff[j];      // sys_model.py:241
@@ -129,7 +129,7 @@ FT_HD void phase_out(const ftmpc_config& cfg, const WsLayout& L, const StepIO& i
     }
     double Wr[FTMPC_NU];
     stage_wrench(cfg, U, uref, X + 9, Wr);                 // u_0 + u_ref_rot + [f_virt;0]
-    for (int i = 0; i < FTMPC_NU; ++i) { ures[i] = Wr[i] - Df[i]; v[i] = Wr[i]; }          // u_comp = [f_virt;0] - D f
+    for (int i = 0; i < FTMPC_NU; ++i) v[i] = Wr[i];        // = u_res + D f   (u_comp = [f_virt;0] - D f)
     // u_des = clip(u_res + D f) - D f                                  control_allocator.py:79
     int st_clip = clip_to_hull(cfg, hull, v, vc);
     double udes[FTMPC_NU];
@@ -151,7 +151,6 @@ FT_HD void phase_out(const ftmpc_config& cfg, const WsLayout& L, const StepIO& i
     io.iters[2 * inst] = (int)sc[SC_ITER];
     io.iters[2 * inst + 1] = (int)sc[SC_QPIT];
     if (io.cost) io.cost[inst] = sc[SC_F];
-    (void)ures;
 }
 
 }  // namespace ftmpc

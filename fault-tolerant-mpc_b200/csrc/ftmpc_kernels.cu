@@ -1,0 +1,449 @@
+// ftmpc_kernels.cu -- CUDA kernels (sm_100a) and the C ABI of include/ftmpc.h.
+//
+// Kernel map:
+//   K1  k_lin / k_rk4_jac : RK4 rollout Jacobians + costates + exact stage Hessians, ONE WARP PER INSTANCE
+//   K4  k_ls              : SQP step acceptance (l1 merit) + forward rollout, one thread per instance
+//   K2+K3 k_qp            : condensing -> Cholesky -> dual active-set QP, ONE CTA PER INSTANCE, every
+//                           matrix resident in shared memory (223 KB at N=20), dynamic work queue
+//   K5  k_out             : u0, active set, thrust allocation QP, one thread per instance
+//   K6  k_plant           : plant step for closed-loop rollouts
+// There is no CPU fallback in this translation unit: without a CUDA device ftmpc_create fails.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "ftmpc.h"
+#include "ftmpc_alloc.cuh"
+#include "ftmpc_plant.cuh"
+
+using namespace ftmpc;
+
+struct WarpBlock {
+    __device__ __forceinline__ int tid() const { return threadIdx.x & 31; }
+    __device__ __forceinline__ int nthreads() const { return 32; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
+
+struct ftmpc_ctx {
+    ftmpc_config cfg;          // host copy
+    ftmpc_config* d_cfg;       // device copy
+    double* d_hull;            // device hull table
+    int* d_ctr;                // device counters: [0..K) running instances after iteration k, [K..2K) work queue heads
+    int* h_ctr;                // pinned host mirror for polling
+    int n_ctr;
+    int device, num_sms;
+    size_t smem_optin;
+    WsLayout L;
+};
+
+// -------------------------------------------------------------------------------------------------
+// kernels
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_ls(const ftmpc_config* __restrict__ cfg, WsLayout L, StepIO io, int first,
+                                           int* run_ctr) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= io.batch) return;
+    phase_ls(*cfg, L, io, inst, first);
+    if (io.ws[(size_t)inst * L.stride + L.oSc + SC_STATUS] == (double)FTMPC_ST_RUNNING) atomicAdd(run_ctr, 1);
+}
+
+__global__ void __launch_bounds__(128) k_lin(const ftmpc_config* __restrict__ cfg, WsLayout L, StepIO io) {
+    const int inst = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (inst >= io.batch) return;
+    WarpBlock wb;
+    phase_lin(wb, *cfg, L, io, inst);
+}
+
+#define FTMPC_QP_THREADS 256
+__global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
+    k_qp(const ftmpc_config* __restrict__ cfg, WsLayout L, StepIO io, int* queue, double* gscratch, size_t sdoubles) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double red[128];
+    __shared__ int s_inst;
+    double* scratch = gscratch ? gscratch + (size_t)blockIdx.x * sdoubles : smem;
+    CudaBlock blk(red);
+    for (;;) {
+        if (threadIdx.x == 0) s_inst = atomicAdd(queue, 1);
+        __syncthreads();
+        const int inst = s_inst;
+        __syncthreads();
+        if (inst >= io.batch) break;
+        phase_qp(blk, *cfg, L, io, inst, scratch);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(64) k_out(const ftmpc_config* __restrict__ cfg, WsLayout L, StepIO io) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= io.batch) return;
+    phase_out(*cfg, L, io, inst);
+}
+
+// ---- stage kernels --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_rk4_jac(const ftmpc_config* __restrict__ cfg, int batch, double* x,
+                                                const double* __restrict__ wrench, double* jac,
+                                                const double* __restrict__ lam, double* hess) {
+    const int inst = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (inst >= batch) return;
+    const int lane = threadIdx.x & 31, N = cfg->horizon;
+    const DynConsts k = dyn_consts(*cfg);
+    double* X = x + (size_t)inst * (N + 1) * 13;
+    const double* W = wrench + (size_t)inst * N * 6;
+    // rollout: every lane carries the state in registers, lane 0 stores it
+    double xs[13], xn[13];
+    for (int i = 0; i < 13; ++i) xs[i] = X[i];
+    for (int t = 0; t < N; ++t) {
+        rk4_step(k, xs, W + t * 6, xn);
+        for (int i = 0; i < 13; ++i) xs[i] = xn[i];
+        if (lane == 0) for (int i = 0; i < 13; ++i) X[(t + 1) * 13 + i] = xn[i];
+    }
+    __syncwarp();
+    for (int it = lane; it < N * 13; it += 32) {
+        const int t = it / 13, c = it % 13;
+        double jc[13], hc[13];
+        rk4_column(k, X + t * 13, W + t * 6, c, lam ? lam + ((size_t)inst * (N + 1) + t + 1) * 13 : nullptr, jc, hc);
+        double* jo = jac + ((size_t)inst * N * 13 + it) * 13;
+        for (int i = 0; i < 13; ++i) jo[i] = jc[i];
+        if (lam && hess) {
+            double* ho = hess + ((size_t)inst * N * 13 + it) * 13;
+            for (int i = 0; i < 13; ++i) ho[i] = hc[i];
+        }
+    }
+}
+
+__global__ void k_r2c(const ftmpc_config* __restrict__ cfg, int batch, const double* state, double* center) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    robot_to_center(dyn_consts(*cfg), state + (size_t)i * 13, center + (size_t)i * 13);
+}
+
+__global__ void k_terminal(const ftmpc_config* __restrict__ cfg, int batch, const double* e, double* V, double* grad,
+                           double* hess) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    double g[9], H[81];
+    V[i] = terminal_eval(*cfg, e + (size_t)i * 9, g, H);
+    for (int k = 0; k < 9; ++k) grad[(size_t)i * 9 + k] = g[k];
+    for (int k = 0; k < 81; ++k) hess[(size_t)i * 81 + k] = H[k];
+}
+
+__global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
+    k_condense(const ftmpc_config* __restrict__ cfg, WsLayout L, int batch, const double* jac, const double* hess,
+               const double* x, const double* u, const double* xref, const double* gradV, const double* hessV,
+               double theta, double* H, double* g, double* gscratch, size_t sdoubles) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double red[128];
+    double* scratch = gscratch ? gscratch + (size_t)blockIdx.x * sdoubles : smem;
+    CudaBlock blk(red);
+    const int N = L.N, n = L.n, ld = L.nv;
+    for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
+        const QpScratch s = qp_carve(scratch, N);
+        double* Jz = s.RS;
+        double* Wz = s.RS + (size_t)N * 169;
+        for (int i = threadIdx.x; i < N * 169; i += blockDim.x) {
+            Jz[i] = jac[(size_t)inst * N * 169 + i];
+            Wz[i] = hess ? hess[(size_t)inst * N * 169 + i] : 0.0;
+        }
+        __syncthreads();
+        condense(blk, *cfg, L, s, Jz, Wz, x + (size_t)inst * (N + 1) * 13, u + (size_t)inst * n,
+                 xref + (size_t)inst * (N + 1) * 9, gradV + (size_t)inst * 9, hessV + (size_t)inst * 81, theta);
+        for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+            const int a = idx / n, b = idx % n;
+            H[(size_t)inst * n * n + idx] = (b <= a) ? s.E[(size_t)a * ld + b] : s.E[(size_t)b * ld + a];
+        }
+        for (int a = threadIdx.x; a < n; a += blockDim.x) g[(size_t)inst * n + a] = s.g[a];
+        __syncthreads();
+    }
+}
+
+struct CsrCons {
+    const int32_t* ptr;
+    const int32_t* idx;
+    const double* val;
+    const double* b;
+    __device__ __forceinline__ void row(int p, SparseRow& r) const {      // C x <= b  ->  -C x >= -b
+        const int s = ptr[p];
+        int k = ptr[p + 1] - s;
+        if (k > FTMPC_GI_MAXNNZ) k = FTMPC_GI_MAXNNZ;
+        for (int j = 0; j < k; ++j) { r.idx[j] = idx[s + j]; r.val[j] = -val[s + j]; }
+        r.nnz = k;
+        r.beta = -b[p];
+    }
+};
+
+__global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
+    k_qp_generic(int batch, int n, int m, const double* H, const double* g, const int32_t* ptr, const int32_t* idx,
+                 const double* val, const double* b, double* x, double* lam, int32_t* status, int maxit, double tol) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double red[128];
+    CudaBlock blk(red);
+    const int ld = n | 1, tid = threadIdx.x, nt = blockDim.x;
+    double* p = smem;
+    GiWork w;
+    w.E = p; p += (size_t)n * ld;
+    w.Ui = p; p += (size_t)n * (n + 1) / 2 + 1;
+    w.xe = p; p += n;
+    w.s = p; p += m;
+    w.u = p; p += n + 2;
+    w.d = p; p += n;
+    w.ze = p; p += n;
+    w.r = p; p += n;
+    w.cs = p; p += 2 * n + 2;
+    w.tmp = p; p += n + 2;
+    w.sub = p; p += n + 2;
+    double* dg = p; p += n;
+    w.esign = p; p += 2;
+    int* ip = reinterpret_cast<int*>(p);
+    w.act = ip; ip += n + 2;
+    w.pos = ip; ip += m;
+    w.itmp = ip; ip += n + 2;
+    for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
+        const double* Hi = H + (size_t)inst * n * n;
+        const double* gi = g + (size_t)inst * n;
+        for (int i = tid; i < n * n; i += nt) w.E[(size_t)(i / n) * ld + (i % n)] = Hi[i];
+        __syncthreads();
+        int st;
+        if (chol_lower(blk, n, ld, w.E, 1e-300)) {
+            st = 3;
+        } else {
+            tri_inv_transpose(blk, n, ld, w.E, dg);
+            for (int i = tid; i < n; i += nt) {
+                double v = 0.0;
+                for (int r = 0; r <= i; ++r) v += w.E[(size_t)r * ld + i] * gi[r];
+                w.d[i] = v;
+            }
+            __syncthreads();
+            for (int row = tid; row < n; row += nt) {
+                double v = 0.0;
+                for (int k = 0; k < n; ++k) v += w.E[(size_t)row * ld + k] * w.d[k];
+                w.xe[row] = -v;
+            }
+            __syncthreads();
+            CsrCons cons{ptr, idx, val, b + (size_t)inst * m};
+            int it = 0, na = 0;
+            st = gi_solve(blk, cons, w, n, n, ld, m, 0, lam + (size_t)inst * m, maxit, tol, &it, &na);
+            for (int i = tid; i < n; i += nt) x[(size_t)inst * n + i] = w.xe[i];
+        }
+        if (tid == 0) status[inst] = st;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(64) k_allocate(const ftmpc_config* __restrict__ cfg, int batch, const double* udes,
+                                                const double* ub, double* thrust, int32_t* status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    double th[16];
+    status[i] = allocate_thrust(*cfg, udes + (size_t)i * 6, ub + (size_t)i * 16, th);
+    for (int j = 0; j < 16; ++j) thrust[(size_t)i * 16 + j] = th[j];
+}
+
+__global__ void k_plant(const ftmpc_config* __restrict__ cfg, int batch, const double* state, const double* thrust,
+                        const uint16_t* mask, const double* ff, const double* noise, int normalize, double* next) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    double xn[13];
+    plant_step(*cfg, state + (size_t)i * 13, thrust + (size_t)i * 16, mask[i], ff + (size_t)i * 16,
+               noise ? noise + (size_t)i * 13 : nullptr, normalize, xn);
+    for (int k = 0; k < 13; ++k) next[(size_t)i * 13 + k] = xn[k];
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+#define CU(x)                                   \
+    do {                                        \
+        cudaError_t e_ = (x);                   \
+        if (e_ != cudaSuccess) return FTMPC_ERR_CUDA; \
+    } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static size_t qp_smem_bytes(int N) { return qp_scratch_doubles(N) * sizeof(double); }
+
+static int qp_grid(const ftmpc_ctx* h, int batch, bool use_global) {
+    int g = h->num_sms * (use_global ? 2 : 1);
+    return batch < g ? batch : g;
+}
+
+extern "C" {
+
+const char* ftmpc_strerror(int code) {
+    switch (code) {
+        case FTMPC_OK: return "ok";
+        case FTMPC_ERR_ARG: return "invalid argument";
+        case FTMPC_ERR_CUDA: return "CUDA error";
+        case FTMPC_ERR_WORKSPACE: return "workspace too small";
+        case FTMPC_ERR_UNSUPPORTED: return "unsupported configuration";
+        case FTMPC_ERR_NO_DEVICE: return "no CUDA device (ft_mpc_b200 has no CPU fallback)";
+        default: return "unknown error";
+    }
+}
+
+int ftmpc_create(ftmpc_handle* out, const ftmpc_config* cfg, const double* hull_table) {
+    if (!out || !cfg || !hull_table) return FTMPC_ERR_ARG;
+    if (cfg->horizon < 1 || cfg->horizon > 512 || cfg->n_hull_sets < 1 || cfg->n_poly > FTMPC_MAX_POLY ||
+        cfg->n_root > FTMPC_MAX_ROOT || cfg->max_sqp_iter < 1)
+        return FTMPC_ERR_ARG;
+    if (cfg->dtype != 0) return FTMPC_ERR_UNSUPPORTED;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return FTMPC_ERR_NO_DEVICE;
+    ftmpc_ctx* h = new (std::nothrow) ftmpc_ctx;
+    if (!h) return FTMPC_ERR_ARG;
+    std::memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    h->L = ws_layout(cfg->horizon);
+    CU(cudaGetDevice(&h->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, h->device));
+    h->num_sms = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    CU(cudaMalloc(&h->d_cfg, sizeof(ftmpc_config)));
+    CU(cudaMemcpy(h->d_cfg, cfg, sizeof(ftmpc_config), cudaMemcpyHostToDevice));
+    const size_t hb = (size_t)cfg->n_hull_sets * FTMPC_HULL_STRIDE * sizeof(double);
+    CU(cudaMalloc(&h->d_hull, hb));
+    CU(cudaMemcpy(h->d_hull, hull_table, hb, cudaMemcpyHostToDevice));
+    h->n_ctr = 2 * (cfg->max_sqp_iter + 2);
+    CU(cudaMalloc(&h->d_ctr, h->n_ctr * sizeof(int)));
+    CU(cudaMallocHost(&h->h_ctr, h->n_ctr * sizeof(int)));
+    const size_t need = qp_smem_bytes(cfg->horizon);
+    if (need <= h->smem_optin) {
+        CU(cudaFuncSetAttribute(k_qp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+        CU(cudaFuncSetAttribute(k_condense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    }
+    *out = h;
+    return FTMPC_OK;
+}
+
+void ftmpc_destroy(ftmpc_handle h) {
+    if (!h) return;
+    cudaFree(h->d_cfg);
+    cudaFree(h->d_hull);
+    cudaFree(h->d_ctr);
+    cudaFreeHost(h->h_ctr);
+    delete h;
+}
+
+int ftmpc_num_var(ftmpc_handle h) { return h ? h->L.n + (h->L.N + 1) * FTMPC_NX : FTMPC_ERR_ARG; }
+int ftmpc_num_ineq(ftmpc_handle h) { return h ? h->L.mc : FTMPC_ERR_ARG; }
+
+int ftmpc_workspace_bytes(ftmpc_handle h, int batch, size_t* out) {
+    if (!h || !out || batch < 1) return FTMPC_ERR_ARG;
+    size_t b = align_up(h->L.stride * sizeof(double) * (size_t)batch, 256);
+    const size_t need = qp_smem_bytes(h->cfg.horizon);
+    if (need > h->smem_optin) b += align_up(need, 256) * (size_t)qp_grid(h, batch, true);
+    *out = b;
+    return FTMPC_OK;
+}
+
+int ftmpc_step(ftmpc_handle h, int batch, const double* state, const double* xref, const double* uref,
+               const uint16_t* fault_mask, const double* fault_force, const int32_t* hull_idx, int warm,
+               double* z_warm, double* thrust, double* u0, uint32_t* active_set, int32_t* status, int32_t* iters,
+               double* cost, void* workspace, size_t workspace_bytes, void* stream_) {
+    if (!h || batch < 1 || !state || !xref || !fault_mask || !fault_force || !hull_idx || !z_warm || !thrust || !u0 ||
+        !active_set || !status || !iters || !workspace)
+        return FTMPC_ERR_ARG;
+    size_t need_ws = 0;
+    ftmpc_workspace_bytes(h, batch, &need_ws);
+    if (workspace_bytes < need_ws) return FTMPC_ERR_WORKSPACE;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const WsLayout L = h->L;
+    StepIO io{batch, state, xref, uref, fault_mask, fault_force, hull_idx, h->d_hull, warm, z_warm, thrust, u0,
+              active_set, status, iters, cost, (double*)workspace};
+    const size_t smem = qp_smem_bytes(h->cfg.horizon);
+    const bool use_global = smem > h->smem_optin;
+    double* gscratch = use_global ? (double*)((char*)workspace + align_up(L.stride * sizeof(double) * (size_t)batch, 256)) : nullptr;
+    const size_t sdoubles = align_up(smem, 256) / sizeof(double);
+    const int K = h->cfg.max_sqp_iter;
+    CU(cudaMemsetAsync(h->d_ctr, 0, h->n_ctr * sizeof(int), stream));
+    int* run_ctr = h->d_ctr;
+    int* queue = h->d_ctr + (K + 2);
+    const int g128 = (batch + 127) / 128;
+    k_ls<<<g128, 128, 0, stream>>>(h->d_cfg, L, io, 1, run_ctr + 0);
+    const int gq = qp_grid(h, batch, use_global);
+    for (int it = 0; it < K; ++it) {
+        k_lin<<<(batch + 3) / 4, 128, 0, stream>>>(h->d_cfg, L, io);
+        k_qp<<<gq, FTMPC_QP_THREADS, use_global ? 0 : smem, stream>>>(h->d_cfg, L, io, queue + it, gscratch, sdoubles);
+        k_ls<<<g128, 128, 0, stream>>>(h->d_cfg, L, io, 0, run_ctr + it + 1);
+        if (h->cfg.poll_every > 0 && (it + 1) % h->cfg.poll_every == 0 && it + 1 < K) {
+            CU(cudaMemcpyAsync(h->h_ctr, run_ctr + it + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+            if (h->h_ctr[0] == 0) break;
+        }
+    }
+    k_out<<<(batch + 63) / 64, 64, 0, stream>>>(h->d_cfg, L, io);
+    CU(cudaGetLastError());
+    return FTMPC_OK;
+}
+
+int ftmpc_rk4_jac(ftmpc_handle h, int batch, double* x, const double* wrench, double* jac, const double* lam,
+                  double* hess, void* stream) {
+    if (!h || batch < 1 || !x || !wrench || !jac) return FTMPC_ERR_ARG;
+    k_rk4_jac<<<(batch + 3) / 4, 128, 0, (cudaStream_t)stream>>>(h->d_cfg, batch, x, wrench, jac, lam, hess);
+    CU(cudaGetLastError());
+    return FTMPC_OK;
+}
+
+int ftmpc_robot_to_center(ftmpc_handle h, int batch, const double* state, double* center, void* stream) {
+    if (!h || batch < 1 || !state || !center) return FTMPC_ERR_ARG;
+    k_r2c<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d_cfg, batch, state, center);
+    CU(cudaGetLastError());
+    return FTMPC_OK;
+}
+
+int ftmpc_terminal(ftmpc_handle h, int batch, const double* e, double* V, double* grad, double* hess, void* stream) {
+    if (!h || batch < 1 || !e || !V || !grad || !hess) return FTMPC_ERR_ARG;
+    k_terminal<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d_cfg, batch, e, V, grad, hess);
+    CU(cudaGetLastError());
+    return FTMPC_OK;
+}
+
+int ftmpc_condense(ftmpc_handle h, int batch, const double* jac, const double* hess, const double* x, const double* u,
+                   const double* xref, const double* gradV, const double* hessV, double theta, double* H, double* g,
+                   void* stream) {
+    if (!h || batch < 1 || !jac || !x || !u || !xref || !gradV || !hessV || !H || !g) return FTMPC_ERR_ARG;
+    const size_t smem = qp_smem_bytes(h->cfg.horizon);
+    if (smem > h->smem_optin) return FTMPC_ERR_UNSUPPORTED;
+    const int grid = batch < h->num_sms ? batch : h->num_sms;
+    k_condense<<<grid, FTMPC_QP_THREADS, smem, (cudaStream_t)stream>>>(h->d_cfg, h->L, batch, jac, hess, x, u, xref,
+                                                                         gradV, hessV, theta, H, g, nullptr, 0);
+    CU(cudaGetLastError());
+    return FTMPC_OK;
+}
+
+int ftmpc_qp_solve(ftmpc_handle h, int batch, int n, int m, const double* H, const double* g, const int32_t* row_ptr,
+                   const int32_t* col_idx, const double* val, const double* b, double* x, double* lam,
+                   int32_t* status, void* stream) {
+    if (!h || batch < 1 || n < 1 || m < 0 || !H || !g || !row_ptr || !col_idx || !val || !b || !x || !lam || !status)
+        return FTMPC_ERR_ARG;
+    const int ld = n | 1;
+    const size_t doubles = (size_t)n * ld + (size_t)n * (n + 1) / 2 + 1 + 12 * (size_t)n + m + 16;
+    const size_t bytes = doubles * 8 + ((size_t)2 * n + m + 8) * 4;
+    if (bytes > h->smem_optin) return FTMPC_ERR_UNSUPPORTED;
+    CU(cudaFuncSetAttribute(k_qp_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    const int grid = batch < h->num_sms ? batch : h->num_sms;
+    k_qp_generic<<<grid, FTMPC_QP_THREADS, bytes, (cudaStream_t)stream>>>(batch, n, m, H, g, row_ptr, col_idx, val, b, x,
+                                                                            lam, status, 20 * (n + m), 1e-11);
+    CU(cudaGetLastError());
+    return FTMPC_OK;
+}
+
+int ftmpc_allocate(ftmpc_handle h, int batch, const double* u_des, const double* ub, double* thrust, int32_t* status,
+                   void* stream) {
+    if (!h || batch < 1 || !u_des || !ub || !thrust || !status) return FTMPC_ERR_ARG;
+    k_allocate<<<(batch + 63) / 64, 64, 0, (cudaStream_t)stream>>>(h->d_cfg, batch, u_des, ub, thrust, status);
+    CU(cudaGetLastError());
+    return FTMPC_OK;
+}
+
+int ftmpc_plant_step(ftmpc_handle h, int batch, const double* state, const double* thrust, const uint16_t* fault_mask,
+                     const double* fault_force, const double* noise, int normalize, double* next, void* stream) {
+    if (!h || batch < 1 || !state || !thrust || !fault_mask || !fault_force || !next) return FTMPC_ERR_ARG;
+    k_plant<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d_cfg, batch, state, thrust, fault_mask,
+                                                                     fault_force, noise, normalize, next);
+    CU(cudaGetLastError());
+    return FTMPC_OK;
+}
+
+}  // extern "C"

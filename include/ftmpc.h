@@ -130,10 +130,12 @@ int ftmpc_qp_solve(ftmpc_handle h, int batch, int n, int m, const double* H, con
 /* K5: control allocation  min |u|^2 s.t. D u = u_des, 0 <= u <= ub   (control_allocator.py:28-40) */
 int ftmpc_allocate(ftmpc_handle h, int batch, const double* u_des, const double* ub, double* thrust,
                    int32_t* status, void* stream);
-/* K6: plant step (16 thrusters, robot state) incl. quaternion renormalisation (sys_model.py:138-243,164-175) */
+/* K6: plant step (16 thrusters, robot state): RK4 of SystemModel.dx_dt (sys_model.py:138-243);
+ *     noise [B,13] or NULL is added after the step (sim_env.py:88-91); normalize != 0 renormalises the
+ *     quaternion (sys_model.py:164-175, sim_env.py:93).  normalize = 0, noise = NULL == model.dynamics(x,u). */
 int ftmpc_plant_step(ftmpc_handle h, int batch, const double* state, const double* thrust,
-                     const uint16_t* fault_mask, const double* fault_force, const double* noise, double* next,
-                     void* stream);
+                     const uint16_t* fault_mask, const double* fault_force, const double* noise, int normalize,
+                     double* next, void* stream);
 
 #ifdef __cplusplus
 }
