@@ -128,7 +128,10 @@ def lib() -> C.CDLL:
     L.ftmpc_qp_solve.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp, ip, ip, dp, dp, dp, dp, ip, vp]
     L.ftmpc_allocate.argtypes = [vp, C.c_int, dp, dp, dp, ip, vp]
     L.ftmpc_plant_step.argtypes = [vp, C.c_int, dp, dp, ip, dp, dp, C.c_int, dp, vp]
-    for name in ("ftmpc_create", "ftmpc_workspace_bytes", "ftmpc_num_var", "ftmpc_num_ineq", "ftmpc_step",
+    L.ftmpc_profile_enable.argtypes = [vp, C.c_int]
+    L.ftmpc_profile_read.argtypes = [vp, vp, dp, ip, ip, C.c_int]
+    L.ftmpc_last_launches.argtypes = [vp]
+    for name in ("ftmpc_profile_enable", "ftmpc_profile_read", "ftmpc_last_launches", "ftmpc_create", "ftmpc_workspace_bytes", "ftmpc_num_var", "ftmpc_num_ineq", "ftmpc_step",
                  "ftmpc_rk4_jac", "ftmpc_robot_to_center", "ftmpc_terminal", "ftmpc_condense", "ftmpc_qp_solve",
                  "ftmpc_allocate", "ftmpc_plant_step"):
         getattr(L, name).restype = C.c_int

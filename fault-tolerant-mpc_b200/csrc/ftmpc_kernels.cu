@@ -35,6 +35,9 @@ struct ftmpc_ctx {
     int device, num_sms;
     size_t smem_optin;
     WsLayout L;
+    int profile, last_launches, n_ev, last_iters;
+    cudaEvent_t* ev;           // 2 events per launch slot
+    int* ev_class;             // kernel class of each slot
 };
 
 // -------------------------------------------------------------------------------------------------
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
         }
         __syncthreads();
         condense(blk, *cfg, L, s, Jz, Wz, x + (size_t)inst * (N + 1) * 13, u + (size_t)inst * n,
-                 xref + (size_t)inst * (N + 1) * 9, gradV + (size_t)inst * 9, hessV + (size_t)inst * 81, theta);
+                 xref + (size_t)inst * (N + 1) * 9, gradV + (size_t)inst * 9, hessV + (size_t)inst * 81, theta, 0.0, nullptr);
         for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
             const int a = idx / n, b = idx % n;
             H[(size_t)inst * n * n + idx] = (b <= a) ? s.E[(size_t)a * ld + b] : s.E[(size_t)b * ld + a];
@@ -312,12 +315,49 @@ int ftmpc_create(ftmpc_handle* out, const ftmpc_config* cfg, const double* hull_
         CU(cudaFuncSetAttribute(k_qp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
         CU(cudaFuncSetAttribute(k_condense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     }
+    h->n_ev = 3 * cfg->max_sqp_iter + 2;
+    h->ev = new cudaEvent_t[2 * h->n_ev];
+    h->ev_class = new int[h->n_ev];
+    for (int i = 0; i < 2 * h->n_ev; ++i) CU(cudaEventCreate(&h->ev[i]));
     *out = h;
+    return FTMPC_OK;
+}
+
+int ftmpc_profile_enable(ftmpc_handle h, int enable) {
+    if (!h) return FTMPC_ERR_ARG;
+    h->profile = enable;
+    return FTMPC_OK;
+}
+
+int ftmpc_last_launches(ftmpc_handle h) { return h ? h->last_launches : FTMPC_ERR_ARG; }
+
+int ftmpc_profile_read(ftmpc_handle h, void* stream, double* ms, int32_t* launches, int32_t* running, int n_running) {
+    if (!h || !ms || !launches) return FTMPC_ERR_ARG;
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int c = 0; c < 4; ++c) { ms[c] = 0.0; launches[c] = 0; }
+    if (h->profile) {
+        for (int i = 0; i < h->last_launches && i < h->n_ev; ++i) {
+            float t = 0.f;
+            CU(cudaEventElapsedTime(&t, h->ev[2 * i], h->ev[2 * i + 1]));
+            ms[h->ev_class[i]] += t;
+            launches[h->ev_class[i]] += 1;
+        }
+    }
+    if (running && n_running > 0) {
+        const int K = h->cfg.max_sqp_iter;
+        CU(cudaMemcpy(h->h_ctr, h->d_ctr, (K + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < n_running; ++k) running[k] = (k <= h->last_iters && k <= K) ? h->h_ctr[k] : -1;
+    }
     return FTMPC_OK;
 }
 
 void ftmpc_destroy(ftmpc_handle h) {
     if (!h) return;
+    if (h->ev) {
+        for (int i = 0; i < 2 * h->n_ev; ++i) cudaEventDestroy(h->ev[i]);
+        delete[] h->ev;
+        delete[] h->ev_class;
+    }
     cudaFree(h->d_cfg);
     cudaFree(h->d_hull);
     cudaFree(h->d_ctr);
@@ -360,19 +400,31 @@ int ftmpc_step(ftmpc_handle h, int batch, const double* state, const double* xre
     int* run_ctr = h->d_ctr;
     int* queue = h->d_ctr + (K + 2);
     const int g128 = (batch + 127) / 128;
-    k_ls<<<g128, 128, 0, stream>>>(h->d_cfg, L, io, 1, run_ctr + 0);
+    int slot = 0;
+#define FT_LAUNCH(cls, ...)                                                     \
+    do {                                                                        \
+        if (h->profile && slot < h->n_ev) cudaEventRecord(h->ev[2 * slot], stream); \
+        __VA_ARGS__;                                                            \
+        if (h->profile && slot < h->n_ev) { cudaEventRecord(h->ev[2 * slot + 1], stream); h->ev_class[slot] = cls; } \
+        ++slot;                                                                 \
+    } while (0)
+    FT_LAUNCH(0, (k_ls<<<g128, 128, 0, stream>>>(h->d_cfg, L, io, 1, run_ctr + 0)));
     const int gq = qp_grid(h, batch, use_global);
-    for (int it = 0; it < K; ++it) {
-        k_lin<<<(batch + 3) / 4, 128, 0, stream>>>(h->d_cfg, L, io);
-        k_qp<<<gq, FTMPC_QP_THREADS, use_global ? 0 : smem, stream>>>(h->d_cfg, L, io, queue + it, gscratch, sdoubles);
-        k_ls<<<g128, 128, 0, stream>>>(h->d_cfg, L, io, 0, run_ctr + it + 1);
+    int it = 0;
+    for (; it < K; ++it) {
+        FT_LAUNCH(1, (k_lin<<<(batch + 3) / 4, 128, 0, stream>>>(h->d_cfg, L, io)));
+        FT_LAUNCH(2, (k_qp<<<gq, FTMPC_QP_THREADS, use_global ? 0 : smem, stream>>>(h->d_cfg, L, io, queue + it, gscratch, sdoubles)));
+        FT_LAUNCH(0, (k_ls<<<g128, 128, 0, stream>>>(h->d_cfg, L, io, 0, run_ctr + it + 1)));
         if (h->cfg.poll_every > 0 && (it + 1) % h->cfg.poll_every == 0 && it + 1 < K) {
             CU(cudaMemcpyAsync(h->h_ctr, run_ctr + it + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
             CU(cudaStreamSynchronize(stream));
-            if (h->h_ctr[0] == 0) break;
+            if (h->h_ctr[0] == 0) { ++it; break; }
         }
     }
-    k_out<<<(batch + 63) / 64, 64, 0, stream>>>(h->d_cfg, L, io);
+    h->last_iters = it;
+    FT_LAUNCH(3, (k_out<<<(batch + 63) / 64, 64, 0, stream>>>(h->d_cfg, L, io)));
+#undef FT_LAUNCH
+    h->last_launches = slot;
     CU(cudaGetLastError());
     return FTMPC_OK;
 }

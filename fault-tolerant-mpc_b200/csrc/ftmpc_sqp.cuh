@@ -28,7 +28,7 @@ struct WsLayout {
 };
 enum {      // scalar slots
     SC_F = 0, SC_CSUM, SC_NU, SC_GD, SC_THETA, SC_DMAX, SC_DELTA, SC_LAMMAX, SC_STATUS, SC_ITER, SC_QPIT,
-    SC_NACT, SC_CHOLFAIL, SC_QPST, SC_ALPHA, SC_CMAX, SC_COUNT
+    SC_NACT, SC_CHOLFAIL, SC_QPST, SC_ALPHA, SC_CMAX, SC_SIGMA, SC_COUNT
 };
 FT_HD WsLayout ws_layout(int N) {
     WsLayout L;
@@ -38,7 +38,7 @@ FT_HD WsLayout ws_layout(int N) {
     L.oD = o; o += L.nv;
     L.oX = o; o += (size_t)(N + 1) * FTMPC_NX;
     L.oC = o; o += L.mc;
-    L.oLam = o; o += L.m;
+    L.oLam = o; o += 2 * (size_t)L.m;       // multipliers + the QP's output copy
     L.oMu = o; o += (size_t)(N + 1) * FTMPC_NX;
     L.oJz = o; o += (size_t)N * 169;
     L.oWz = o; o += (size_t)N * 169;
@@ -288,7 +288,7 @@ struct MpcCons {
 
 // per-CTA scratch carved out of one buffer of doubles (shared memory on the device)
 struct QpScratch {
-    double *E, *RS, *G, *T, *g, *cv, *hull;
+    double *E, *RS, *G, *T, *g, *ga, *taug, *cv, *hull;
     GiWork gi;
     double* dg;
     size_t total;       // doubles
@@ -302,7 +302,7 @@ FT_HD size_t qp_scratch_doubles(int N) {
     size_t tt = (size_t)FTMPC_NE * n;
     if (tt > gi_vec) gi_vec = tt;
     size_t ints = ((nv + 1) + L.m + (nv + 1) + 1) / 2 + 1;
-    return ne * nv + rs + (size_t)FTMPC_NX * nv + gi_vec + nv /*g*/ + L.mc /*cv*/ + FTMPC_HULL_STRIDE + ints + 8;
+    return ne * nv + rs + (size_t)FTMPC_NX * nv + gi_vec + 2 * nv /*g, ga*/ + 90 /*taug*/ + L.mc /*cv*/ + FTMPC_HULL_STRIDE + ints + 8;
 }
 FT_HD QpScratch qp_carve(double* buf, int N) {
     const WsLayout L = ws_layout(N);
@@ -315,6 +315,8 @@ FT_HD QpScratch qp_carve(double* buf, int N) {
     s.RS = p; p += rs;
     s.G = p; p += (size_t)FTMPC_NX * nv;
     s.g = p; p += nv;
+    s.ga = p; p += nv;
+    s.taug = p; p += 90;
     s.cv = p; p += L.mc;
     s.hull = p; p += FTMPC_HULL_STRIDE;
     double* v = p;
@@ -345,13 +347,31 @@ FT_HD QpScratch qp_carve(double* buf, int N) {
 template <class Blk>
 FT_HD void condense(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const QpScratch& s, const double* Jz,
                     const double* Wz, const double* X, const double* U, const double* xref, const double* gradV,
-                    const double* hessV, double theta) {
+                    const double* hessV, double theta, double sigma, const double* lam_prev) {
     const int N = L.N, n = L.n, ld = L.nv, tid = blk.tid(), nt = blk.nthreads();
     double* H = s.E;
     double* G = s.G;          // 13 x ld, current d x_t / d U
     double* T = s.T;
+    // Augmented-Lagrangian convexification on the predicted active set A (rows with lam_prev > 0):
+    //   H += sigma * sum_A a_i a_i',  ga = g + sigma * sum_A c_i a_i.   If every row of A is active in the QP
+    //   solution this leaves the QP solution and its multipliers unchanged, but makes H positive definite
+    //   whenever the second-order sufficient condition holds (the exact Hessian alone need not be).
+    const double* Ah = s.hull;
     for (int i = tid; i < FTMPC_NX * ld; i += nt) G[i] = 0.0;
-    for (int i = tid; i < L.nv; i += nt) s.g[i] = 0.0;
+    for (int i = tid; i < L.nv; i += nt) { s.g[i] = 0.0; s.ga[i] = 0.0; }
+    for (int idx = tid; idx < 90; idx += nt) {       // terminal rows: 9x9 matrix + 9-vector
+        double v = 0.0;
+        if (sigma > 0.0) {
+            const int kk = idx / 9, l = idx % 9;
+            for (int i = 0; i < FTMPC_NF; ++i) {
+                if (lam_prev[FTMPC_NH * N + i] > 0.0) {
+                    const double a = cfg.Af[i * FTMPC_NE + l];
+                    v += (idx < 81) ? cfg.Af[i * FTMPC_NE + kk] * a : s.cv[FTMPC_NH * N + i] * a;
+                }
+            }
+        }
+        s.taug[idx] = sigma * v;
+    }
     blk.sync();
     for (int t = 0; t < N; ++t) {
         const double* jz = Jz + (size_t)t * 169;     // [col][row]
@@ -388,6 +408,12 @@ FT_HD void condense(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
                 const int j2 = b - nc;
                 v = theta * 0.5 * (wz[(7 + j) * 13 + 7 + j2] + wz[(7 + j2) * 13 + 7 + j]);
                 if (j2 == j) v += 2.0 * cfg.R[j];
+                if (sigma > 0.0) {
+                    double av = 0.0;
+                    for (int i = 0; i < FTMPC_NH; ++i)
+                        if (lam_prev[t * FTMPC_NH + i] > 0.0) av += Ah[i * FTMPC_NU + j] * Ah[i * FTMPC_NU + j2];
+                    v += sigma * av;
+                }
             }
             H[(size_t)(nc + j) * ld + b] = v;
         }
@@ -400,6 +426,12 @@ FT_HD void condense(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
                 s.g[a] += v;
             } else {
                 s.g[a] = 2.0 * cfg.R[a - nc] * U[a];
+                if (sigma > 0.0) {
+                    double av = 0.0;
+                    for (int i = 0; i < FTMPC_NH; ++i)
+                        if (lam_prev[t * FTMPC_NH + i] > 0.0) av += s.cv[t * FTMPC_NH + i] * Ah[i * FTMPC_NU + a - nc];
+                    s.ga[a] = sigma * av;
+                }
             }
         }
         blk.sync();
@@ -426,7 +458,7 @@ FT_HD void condense(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         double v = 0.0;
         for (int l = 0; l < FTMPC_NE; ++l) {
             const double q0 = cfg.term_quad[kk * FTMPC_NE + l];
-            v += (q0 + theta * (hessV[kk * FTMPC_NE + l] - q0)) * G[l * ld + b];
+            v += (q0 + theta * (hessV[kk * FTMPC_NE + l] - q0) + s.taug[kk * FTMPC_NE + l]) * G[l * ld + b];
         }
         T[kk * n + b] = v;
     }
@@ -442,9 +474,13 @@ FT_HD void condense(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         }
     }
     for (int a = tid; a < n; a += nt) {
-        double v = 0.0;
-        for (int kk = 0; kk < FTMPC_NE; ++kk) v += gradV[kk] * G[kk * ld + a];
+        double v = 0.0, va = 0.0;
+        for (int kk = 0; kk < FTMPC_NE; ++kk) {
+            v += gradV[kk] * G[kk * ld + a];
+            va += s.taug[81 + kk] * G[kk * ld + a];
+        }
         s.g[a] += v;
+        s.ga[a] += s.g[a] + va;
     }
     blk.sync();
 }
@@ -462,16 +498,24 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     // stage data -> scratch (the R^-1 region is free until the active-set solve starts)
     double* Jz = s.RS;
     double* Wz = s.RS + (size_t)N * 169;
-    for (int i = tid; i < N * 169; i += nt) { Jz[i] = w[L.oJz + i]; Wz[i] = w[L.oWz + i]; }
     for (int i = tid; i < L.mc; i += nt) s.cv[i] = w[L.oC + i];
     for (int i = tid; i < FTMPC_HULL_STRIDE; i += nt) s.hull[i] = hull_g[i];
     blk.sync();
-    // blend schedule for the exact second-order terms
-    double theta = sc[SC_THETA];
+    // Hessian schedule: exact second-order terms blended by theta; when the exact Hessian is indefinite,
+    // first try the augmented-Lagrangian convexification (sigma > 0), then fall back to smaller theta.
+    const double* lam_prev = w + L.oLam;
+    const bool can_aug = (sc[SC_ITER] > 0.0 || sc[SC_THETA] >= 0.0) && sc[SC_CSUM] <= 1e-6;
+    double theta = sc[SC_THETA], sigma = 0.0;
     theta = (theta < 0.0) ? 0.0 : ((theta == 0.0) ? 0.125 : fmin(1.0, 2.0 * theta));
-    int fails = 0;
+    if (can_aug && sc[SC_SIGMA] > 0.0) { theta = 1.0; sigma = sc[SC_SIGMA]; }
+    bool aug_allowed = can_aug;
+    int fails = 0, qit = 0, nact = 0, st = GI_OK;
+    for (;;) {        // QP attempts (re-solved without augmentation if a predicted-active row came out inactive)
+    double sig0 = 0.0;
+    for (int i = tid; i < N * 169; i += nt) { Jz[i] = w[L.oJz + i]; Wz[i] = w[L.oWz + i]; }    // (the QP reuses this region)
+    blk.sync();
     for (;;) {
-        condense(blk, cfg, L, s, Jz, Wz, w + L.oX, w + L.oU, xref, w + L.oGV, w + L.oHV, theta);
+        condense(blk, cfg, L, s, Jz, Wz, w + L.oX, w + L.oU, xref, w + L.oGV, w + L.oHV, theta, sigma, lam_prev);
         double dmaxl = 0.0;
         for (int i = tid; i < n; i += nt) dmaxl = fmax(dmaxl, fabs(s.E[(size_t)i * ld + i]));
         const double dscale = blk.max(dmaxl);
@@ -479,8 +523,11 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         if (!bad) break;
         ++fails;
         blk.sync();
-        if (theta <= 0.0) { if (tid == 0) { sc[SC_QPST] = 3.0; } return; }
-        theta = (theta > 0.125) ? 0.5 * theta : 0.0;
+        if (sigma == 0.0 && theta == 1.0 && aug_allowed) { sig0 = 10.0 * dscale; sigma = sig0; }
+        else if (sigma > 0.0 && sig0 > 0.0 && sigma < 50.0 * sig0) sigma *= 10.0;
+        else if (sigma > 0.0) { sigma = 0.0; theta = 0.5; aug_allowed = false; }
+        else if (theta <= 0.0) { if (tid == 0) { sc[SC_QPST] = 3.0; } return; }
+        else theta = (theta > 0.125) ? 0.5 * theta : 0.0;
     }
     tri_inv_transpose(blk, n, ld, s.E, s.dg);
     // slack variable column/row, extension rows  X J  (X = d x_N[0:9] / d U)
@@ -495,10 +542,10 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         if (i < n) for (int r = 0; r <= i; ++r) v += s.G[kk * ld + r] * s.E[(size_t)r * ld + i];
         s.E[(size_t)(nv + kk) * ld + i] = v;
     }
-    // unconstrained minimiser  x = -J J' g
+    // unconstrained minimiser  x = -J J' ga
     for (int i = tid; i < nv; i += nt) {
         double v = 0.0;
-        if (i < n) for (int r = 0; r <= i; ++r) v += s.E[(size_t)r * ld + i] * s.g[r];
+        if (i < n) for (int r = 0; r <= i; ++r) v += s.E[(size_t)r * ld + i] * s.ga[r];
         s.gi.d[i] = v;
     }
     blk.sync();
@@ -509,8 +556,20 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     }
     blk.sync();
     MpcCons cons{N, n, nv, L.mc, s.hull, cfg.Af, s.cv};
-    int qit = 0, nact = 0;
-    const int st = gi_solve(blk, cons, s.gi, nv, ne, ld, L.m, 0, w + L.oLam, cfg.max_qp_iter, cfg.qp_tol, &qit, &nact);
+    int qit1 = 0;
+    // the previous multipliers are still needed if this attempt is rejected: the QP writes to the spare copy
+    st = gi_solve(blk, cons, s.gi, nv, ne, ld, L.m, 0, w + L.oLam + L.m, cfg.max_qp_iter, cfg.qp_tol, &qit1, &nact);
+    qit += qit1;
+    if (sigma > 0.0 && st == GI_OK) {       // every predicted-active row must be active in the QP solution
+        int viol = 0;
+        for (int i = tid; i < L.mc; i += nt)
+            if (lam_prev[i] > 0.0 && s.gi.pos[i] < 0 && s.gi.s[i] > 1e-9) viol = 1;
+        if (blk.any(viol)) { sigma = 0.0; theta = 0.5; aug_allowed = false; ++fails; continue; }
+    }
+    break;
+    }
+    for (int i = tid; i < L.m; i += nt) w[L.oLam + i] = w[L.oLam + L.m + i];
+    blk.sync();
     // step, directional derivative, multiplier bound
     double gd = 0.0, dmx = 0.0, lmx = 0.0;
     for (int i = tid; i < n; i += nt) {
@@ -526,7 +585,7 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     if (tid == 0) {
         w[L.oD + n] = s.gi.xe[n];
         sc[SC_GD] = gd; sc[SC_DMAX] = dmx; sc[SC_LAMMAX] = lmx; sc[SC_DELTA] = s.gi.xe[n];
-        sc[SC_THETA] = theta; sc[SC_QPIT] += qit; sc[SC_NACT] = nact; sc[SC_CHOLFAIL] += fails;
+        sc[SC_THETA] = theta; sc[SC_SIGMA] = sigma; sc[SC_QPIT] += qit; sc[SC_NACT] = nact; sc[SC_CHOLFAIL] += fails;
         sc[SC_QPST] = (st == GI_OK && dmx == dmx) ? 0.0 : (double)(st ? st : 4);
     }
     blk.sync();

@@ -107,6 +107,15 @@ int ftmpc_step(ftmpc_handle h, int batch, const double* state, const double* xre
                double* z_warm, double* thrust, double* u0, uint32_t* active_set, int32_t* status,
                int32_t* iters, double* cost, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Profiling hooks used by bench.py: when enabled, ftmpc_step brackets every kernel launch with CUDA
+ * events on `stream`.  ftmpc_profile_read synchronises the stream and returns, for the LAST ftmpc_step:
+ *   ms[0..3]   total device time of k_ls, k_lin, k_qp, k_out      launches[0..3] their launch counts
+ *   running[k] instances still iterating after SQP iteration k (k < max_sqp_iter+1, -1 = not launched) */
+int ftmpc_profile_enable(ftmpc_handle h, int enable);
+int ftmpc_profile_read(ftmpc_handle h, void* stream, double* ms, int32_t* launches, int32_t* running, int n_running);
+/* number of kernels ftmpc_step launched on its last call */
+int ftmpc_last_launches(ftmpc_handle h);
+
 /* ---- stage entry points (unit parity tests; same device code as ftmpc_step) ------------------ */
 /* K1: RK4 rollout + Jacobians, one warp per instance.  wrench [B,N,6] = total body wrench per stage.
  *     x [B,N+1,13] (x[:,0] given), jac [B,N,13,13] column-major per stage in z-order [w q F tau]

@@ -37,6 +37,7 @@ int ftmpc_cpu_step(const ftmpc_config* cfg, const double* hull_table, int batch,
     StepIO io{batch, state, xref, uref, fault_mask, fault_force, hull_idx, hull_table, warm, z_warm, thrust, u0,
               active_set, status, iters, cost, ws};
     const size_t sdoubles = qp_scratch_doubles(cfg->horizon);
+    const bool trace = std::getenv("FTMPC_TRACE") != nullptr;
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
@@ -52,6 +53,12 @@ int ftmpc_cpu_step(const ftmpc_config* cfg, const double* hull_table, int batch,
                 phase_lin(blk, *cfg, L, io, inst);
                 phase_qp(blk, *cfg, L, io, inst, scratch.data());
                 phase_ls(*cfg, L, io, inst, 0);
+                if (trace) {
+                    const double* sc = ws + (size_t)inst * L.stride + L.oSc;
+                    std::printf("inst %d it %2d f %.9f csum %.3e cmax %.3e nu %.3g theta %.3g dmax %.3e delta %.3e lammax %.3g alpha %.3g qpit %g nact %g cholfail %g qpst %g st %g\n",
+                                inst, it, sc[SC_F], sc[SC_CSUM], sc[SC_CMAX], sc[SC_NU], sc[SC_THETA], sc[SC_DMAX], sc[SC_DELTA],
+                                sc[SC_LAMMAX], sc[SC_ALPHA], sc[SC_QPIT], sc[SC_NACT], sc[SC_CHOLFAIL], sc[SC_QPST], sc[SC_STATUS]);
+                }
             }
             phase_out(*cfg, L, io, inst);
         }
