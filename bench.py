@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- batched MPC solves/s of the B200-native ft_mpc drop-in (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B_per_gpu] [--horizon 20] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[3], the one the 1e6 solves/s target is quoted on; weak scaling: the per-GPU
+shard is fixed at 65,536 / 8 = 8,192 instances): Monte-Carlo fault scenarios -- all well-posed single and
+double thruster failures (dead / stuck-on), seeded random initial robot states, hover reference, horizon
+N = 20, cold start.  One "step" = one ftmpc_step over the rank's shard = B complete get_control equivalents
+(state -> SQP on the reference NLP -> 16 thrusts).  Only converged instances (status 0) count as solves.
+
+One JSON line on stdout (rank 0).  `value` is device-resident throughput, `e2e` goes through the public
+SpiralingController.step with pinned HOST buffers (H2D of the inputs and D2H of thrust/status inside the timed
+region), `roofline` compares the dominant kernel with the measured FP64 FMA peak of the device (the solve is
+FP64-compute/latency bound) and reports the HBM side too, `cpu_baseline` / `--impl reference`
+time the same algorithm on the host cores (oracle/cpu_port -- the reference's own casadi/IPOPT stack is not
+installable offline).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "batched MPC solves/sec (fault-scenario get_control equivalents, N=20)"
+UNIT = "solves/s"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# workload + flop/byte model
+# ---------------------------------------------------------------------------------------------------------
+def make_workload(batch_total: int, N: int, seed: int = 1):
+    import ftmpc_import
+    ftmpc_import.load()
+    from ft_mpc_b200.util import scenarios
+    cells = scenarios.load_cells(kinds=("single", "double"))
+    states = scenarios.random_states(batch_total, seed)
+    scen = (np.arange(batch_total) * 7919) % len(cells)          # every cell appears, decorrelated from the state index
+    xref = scenarios.hover_reference(batch_total, N)
+    return cells, states, scen, xref
+
+
+def algorithmic_flops(N: int, k_sqp: np.ndarray, k_qp: np.ndarray) -> dict:
+    """F = K_sqp (F_lin + F_cond + F_chol) + K_qp F_iter + F_alloc, per instance."""
+    n, m = 6 * N, 26 * N + 72
+    f_lin = N * 29000.0
+    f_cond = N * (N + 1) / 2 * (2 * 169 * 6) + N * N / 2 * (2 * 169 * 6 + 2 * 13 * 36) + 288.0 * n
+    f_chol = n ** 3 / 3.0
+    f_iter = 2.0 * n * n + 624.0 * N + 36.0 * n + 10.0 * (n + m)
+    f_alloc = 5000.0
+    ks, kq = float(k_sqp.sum()), float(k_qp.sum())
+    return dict(total=ks * (f_lin + f_cond + f_chol) + kq * f_iter + f_alloc * len(k_sqp),
+                qp_kernel=ks * (f_cond + f_chol) + kq * f_iter, lin_kernel=ks * f_lin,
+                per_sqp_iter=f_lin + f_cond + f_chol, per_qp_iter=f_iter)
+
+
+def algorithmic_bytes(N: int) -> float:
+    """compulsory HBM I/O per solve: inputs + warm start in/out + outputs."""
+    nz, m = 6 * N + 13 * (N + 1), 26 * N + 72
+    return 8.0 * (13 + 9 * (N + 1) + 6 * (N + 1) + nz) + 8 + 8.0 * (nz + 16 + 6) + 4.0 * ((m + 31) // 32) + 12
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(6)
+
+    def summary(self) -> dict:
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm (reference arm and cpu_baseline): the same NLP solved on the host cores by oracle/cpu_port
+# ---------------------------------------------------------------------------------------------------------
+def cpu_solve_rate(N: int, cells, states, scen, xref, sample: int, steps: int, warmup: int):
+    """Times `steps` passes over the first `sample` instances with all host threads.  Returns (solves/s, ms/step, cores, ok_frac)."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import helpers as H                      # ctypes binding of oracle/_cpu/libftmpc_cpu.so (checker code)
+    import ftmpc_import
+    ftmpc_import.load()
+    from ft_mpc_b200 import _lib as L
+    from ft_mpc_b200.controllers.spiraling_mpc import DEFAULT_Q, DEFAULT_R, hull_table_entry
+    from ft_mpc_b200.controllers.tools.spiral_parameters import SpiralParameters
+    from ft_mpc_b200.models import SystemModel
+    if not H.CPU_LIB.exists():
+        subprocess.run(["make", "-s", "-C", str(ROOT / "oracle")], check=True)
+    port = H.CpuPort()
+    model = SystemModel(0.1)
+    sp = SpiralParameters(model)
+    table = np.ascontiguousarray(np.stack([hull_table_entry(c["A"], c["b"]) for c in cells]))
+    cfg = L.make_config(N, DEFAULT_Q, DEFAULT_R, dt=model.dt, mass=model.mass, inertia=model.inertia, r=sp.r, f_virt=sp.f_virt,
+                        max_thrust=model.max_thrust, D=model.D, n_hull_sets=len(cells))
+    masks = np.zeros(len(cells), np.uint16)
+    ffs = np.zeros((len(cells), 16))
+    for k, c in enumerate(cells):
+        for i, a in c["faults"]:
+            masks[k] |= np.uint16(1 << i)
+            ffs[k, i] = a * model.max_thrust
+    s = slice(0, sample)
+    args = (cfg, table, states[s], xref[s], None, masks[scen[s]], ffs[scen[s]], scen[s])
+    cores = port.lib.ftmpc_cpu_num_threads()
+    for _ in range(warmup):
+        port.step(*args)
+    t0 = time.perf_counter()
+    ok = 0
+    for _ in range(steps):
+        out = port.step(*args)
+        ok += int((out["status"] == 0).sum())
+    dt = time.perf_counter() - t0
+    return ok / dt, dt / steps * 1e3, cores, ok / (steps * sample)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8192, help="instances per GPU (weak scaling)")
+    ap.add_argument("--horizon", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="instances per CPU step (0 = auto)")
+    ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    N = a.horizon
+    W = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+    config = {"workload": f"mc_fault_scenarios single+double(dead|stuck) well-posed cells, N={N}, cold start, hover, "
+                          f"{a.batch} instances per GPU (BASELINE configs[3] shard)", "horizon": N, "batch_per_gpu": a.batch,
+              "global_batch": a.batch * world, "seed": 1, "parallelism": f"dp{world} (independent instances, no data-path collective)",
+              "l2_policy": "per-step working set (inputs + per-instance workspace) exceeds the 126 MB L2"}
+
+    # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        sample = a.cpu_sample or 2048
+        cells, states, scen, xref = make_workload(sample, N)
+        rate, ms, cores, okf = cpu_solve_rate(N, cells, states, scen, xref, sample, a.steps, a.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": f"{sample} instances of the workload per step, all {cores} host threads (OpenMP, one instance per thread); "
+                                           "the reference's casadi/IPOPT solve is not installable offline, this is the C++ port of the same SQP "
+                                           "on the reference NLP (oracle/cpu_port)", "converged_frac": okf},
+                "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    import ftmpc_import
+    ftmpc_import.load()
+    from ft_mpc_b200 import _lib as L
+    from ft_mpc_b200.controllers import SpiralingController
+    from ft_mpc_b200.distributed import gather_results, pack_results, shard_bounds
+    from ft_mpc_b200.models import SystemModel
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: ft_mpc_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    devs = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(devs))
+    B = a.batch
+    Btot = B * world
+    cells, states, scen, xref = make_workload(Btot, N)
+    lo, hi = shard_bounds(Btot, rank, world)
+    ctrl = SpiralingController(SystemModel(0.1), horizon=N, weights={"Q": [1, 1, 1, 1, 1, 1, 2, 2, 2], "R": [.1, .1, .1, .01, .01, .01]},
+                               fault_sets=cells, device=devs)
+    eng = ctrl.engine
+    f64 = torch.float64
+    st_d = torch.tensor(states[lo:hi], dtype=f64, device=devs)
+    xr_d = torch.tensor(xref[lo:hi], dtype=f64, device=devs)
+    sc_t = eng.scenario_tensors(torch.tensor(scen[lo:hi], device=devs))
+    stream = torch.cuda.current_stream()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(W):
+        eng.step(st_d, xr_d, scenario=sc_t)
+    sync_all()
+    # ---- timed region: device-resident inputs
+    L.check(eng.lib.ftmpc_profile_enable(eng.handle, 1))
+    ms_cls = np.zeros(4); n_cls = np.zeros(4, np.int64)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        sync_all()
+        e0.record(stream)
+        launches = 0
+        for _ in range(a.steps):
+            out = eng.step(st_d, xr_d, scenario=sc_t)
+            launches += eng.lib.ftmpc_last_launches(eng.handle)
+        e1.record(stream)
+        sync_all()
+    ms_total = e0.elapsed_time(e1)
+    # per-kernel-class device time of the LAST timed step (events recorded on the launching stream by ftmpc_step)
+    msb = (C.c_double * 4)(); lb = (C.c_int32 * 4)()
+    L.check(eng.lib.ftmpc_profile_read(eng.handle, C.c_void_p(stream.cuda_stream), msb, lb, None, 0))
+    ms_cls[:] = list(msb); n_cls[:] = list(lb)
+    L.check(eng.lib.ftmpc_profile_enable(eng.handle, 0))
+    status = out["status"].cpu().numpy()
+    iters = out["iters"].cpu().numpy()
+    ok_local = int((status == 0).sum())
+    t = torch.tensor([ms_total, float(ok_local)], dtype=f64, device=devs)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms_total, ok_total = float(tmax[0]), float(tsum[1])
+    else:
+        ok_total = float(ok_local)
+    value = ok_total * a.steps / (ms_total * 1e-3)
+
+    # ---- the one collective of the path: all-gather of the per-instance result records (outside the timed solve)
+    rec = pack_results(st_d, out["cost"], out["status"], torch.ones(hi - lo, dtype=torch.int32, device=devs))
+    full = gather_results(rec, Btot)
+    assert full.shape[0] == Btot
+
+    # ---- e2e: public API, pinned host buffers, H2D + D2H inside the timed region
+    st_h = torch.tensor(states[lo:hi], dtype=f64).pin_memory()
+    xr_h = torch.tensor(xref[lo:hi], dtype=f64).pin_memory()
+    sc_h = torch.tensor(scen[lo:hi], dtype=torch.int64).pin_memory()
+    th_h = torch.empty(hi - lo, 16, dtype=f64).pin_memory()
+    stt_h = torch.empty(hi - lo, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        thrust = ctrl.step(st_h.to(devs, non_blocking=True), xr_h.to(devs, non_blocking=True), scenario=sc_h.to(devs, non_blocking=True))
+        th_h.copy_(thrust, non_blocking=True)
+        stt_h.copy_(ctrl.last["status"], non_blocking=True)
+
+    e2e_steps = min(a.steps, 3)
+    e2e_step(); sync_all()
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record(stream)
+    sync_all()
+    ms_e2e = e0.elapsed_time(e1)
+    ok_e2e = float((stt_h.numpy() == 0).sum())
+    te = torch.tensor([ms_e2e, ok_e2e], dtype=f64, device=devs)
+    if world > 1:
+        temax = te.clone(); dist.all_reduce(temax, op=dist.ReduceOp.MAX)
+        tesum = te.clone(); dist.all_reduce(tesum, op=dist.ReduceOp.SUM)
+        ms_e2e, ok_e2e = float(temax[0]), float(tesum[1])
+    e2e = {"value": ok_e2e * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
+           "h2d_bytes_per_step": int((st_h.nbytes + xr_h.nbytes + sc_h.nbytes) * world),
+           "d2h_bytes_per_step": int((th_h.nbytes + stt_h.nbytes) * world), "steps": e2e_steps,
+           "api": "SpiralingController.step(state, ref, scenario=...) -> thrust (pinned host tensors in / out)"}
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (rank 0's shard, last timed step)
+    names = ["k_ls (merit line search + rollout)", "k_lin (RK4 Jacobians / costates / stage Hessians)",
+             "k_qp (condense + Cholesky + dual active-set QP)", "k_out (u0, active set, thrust allocation)"]
+    fl = algorithmic_flops(N, iters[:, 0], iters[:, 1])
+    peak = C.c_double()
+    L.check(eng.lib.ftmpc_fp64_peak(eng.handle, C.byref(peak), C.c_void_p(stream.cuda_stream)))
+    dom = int(np.argmax(ms_cls))
+    dom_flops = {0: 0.0, 1: fl["lin_kernel"], 2: fl["qp_kernel"], 3: 5000.0 * B}[dom] if n_cls.sum() > 1 else fl["total"]
+    dom_ms = ms_cls[dom] if ms_cls[dom] > 0 else ms_total / a.steps
+    achieved = dom_flops / (dom_ms * 1e-3) * 1e-12
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_ach = algorithmic_bytes(N) * B / (ms_total / a.steps * 1e-3) * 1e-9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "fp64", "kernel": names[dom].split(" ")[0], "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
+                "frac": achieved / peak.value if peak.value > 0 else None, "traffic": traffic,
+                "peak_source": "FP64 FMA probe run live on this device (ftmpc_fp64_peak); MEASURED_PEAKS.json has no fp64 figure",
+                "flops_model": "SURVEY.md 8d: K_sqp(F_lin+F_cond+F_chol)+K_qp F_iter+F_alloc with the kernel's own iteration counters",
+                "algorithmic_flops_per_step": fl["total"], "kernel_ms": {names[i].split(" ")[0]: float(ms_cls[i]) for i in range(4)},
+                "kernel_launches": {names[i].split(" ")[0]: int(n_cls[i]) for i in range(4)},
+                "whole_step_tflops": fl["total"] / (ms_total / a.steps * 1e-3) * 1e-12,
+                "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                        "algorithmic_bytes_per_solve": algorithmic_bytes(N),
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"}}
+
+    # ---- single-instance latency (BASELINE configs[1]): examples/sim.py default scenario, closed loop, warm start
+    latency = None
+    if not a.no_latency:
+        from ft_mpc_b200.models import SpiralModel
+        from ft_mpc_b200.util import BrokenThruster
+        m1 = SystemModel(0.1)
+        m1.set_fault(BrokenThruster(10, 1.0)); m1.set_fault(BrokenThruster(11, 1.0))
+        c1 = SpiralingController(SpiralModel.from_system_model(m1), {"horizon": 15}, None, device=devs, poll_every=1)
+        c1.load_trajectory("hover", 30)
+        from scipy.spatial.transform import Rotation
+        x = np.concatenate([[1, 0, 1], [1, .5, 0], Rotation.from_euler("zyx", [50, 30, -10], degrees=True).as_quat(), [.3, .8, -.1]])
+        lat = []
+        for k in range(60):
+            t0 = time.perf_counter()
+            u = c1.get_control(x, 0.1 * k)
+            lat.append((time.perf_counter() - t0) * 1e3)
+            x = m1.normalize_quaternion(m1.dynamics(x, u))
+        lat = np.array(lat[5:])
+        latency = {"p50_ms": float(np.percentile(lat, 50)), "p95_ms": float(np.percentile(lat, 95)), "steps": len(lat),
+                   "workload": "examples/sim.py default scenario, N=15, closed loop, warm start, get_control(x,t) host call"}
+
+    # ---- CPU baseline (same algorithm on the host cores), bounded sample
+    cpu = None
+    if not a.no_cpu_baseline and world == 1:
+        probe = min(B, 256)
+        r0, *_ = cpu_solve_rate(N, cells, states, scen, xref, probe, 1, 0)
+        sample = a.cpu_sample or int(min(B, max(probe, r0 * 12)))
+        rate, ms, cores, okf = cpu_solve_rate(N, cells, states, scen, xref, sample, 1, 0)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {sample} instances of the same batch, one pass, OpenMP over instances ({cores} threads), "
+                         "C++ port of the same SQP on the reference NLP (oracle/cpu_port); the reference's casadi/IPOPT stack is not installable offline",
+               "converged_frac": okf}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W,
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config, "converged_frac": ok_total / Btot,
+            "sqp_iters_mean": float(iters[:, 0].mean()), "qp_iters_mean": float(iters[:, 1].mean()),
+            "status_hist": np.bincount(status, minlength=5).tolist(), "clocks": clk.summary(), "e2e": e2e,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "latency": latency,
+            "target": {"solves_per_s_8gpu": 1e6, "per_gpu": 125000.0}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -11,4 +11,4 @@ Everything numeric on the per-step path runs in ``csrc/libftmpc.so`` (CUDA, sm_1
 ``include/ftmpc.h``.  There is no CPU fallback: constructing a controller without the library or
 without a CUDA device raises.
 """
-__all__ = ["models", "controllers", "util", "_lib"]
+__all__ = ["models", "controllers", "util", "distributed", "_lib"]

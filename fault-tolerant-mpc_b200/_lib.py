@@ -131,6 +131,8 @@ def lib() -> C.CDLL:
     L.ftmpc_profile_enable.argtypes = [vp, C.c_int]
     L.ftmpc_profile_read.argtypes = [vp, vp, dp, ip, ip, C.c_int]
     L.ftmpc_last_launches.argtypes = [vp]
+    L.ftmpc_fp64_peak.argtypes = [vp, C.POINTER(C.c_double), vp]
+    L.ftmpc_fp64_peak.restype = C.c_int
     for name in ("ftmpc_profile_enable", "ftmpc_profile_read", "ftmpc_last_launches", "ftmpc_create", "ftmpc_workspace_bytes", "ftmpc_num_var", "ftmpc_num_ineq", "ftmpc_step",
                  "ftmpc_rk4_jac", "ftmpc_robot_to_center", "ftmpc_terminal", "ftmpc_condense", "ftmpc_qp_solve",
                  "ftmpc_allocate", "ftmpc_plant_step"):

@@ -151,6 +151,29 @@ class BatchedMPC:
                                           int(bool(normalize)), _ptr(nxt), C.c_void_p(stream)), "ftmpc_plant_step")
         return nxt
 
+    def closed_loop(self, state0, trajectory, scenario=None, steps=1, noise=None, start_step=0):
+        """`steps` x (ftmpc_step -> ftmpc_plant_step) entirely on the device: SimulationEnvironment.run_simulation
+        (sim_env.py:77-112) for a batch.  trajectory: [T,9] device reference table (assign_trajectory), shared by
+        all instances; noise: optional [steps,B,13] tensor added after each plant step (the reference draws
+        unseeded U(0,1e-3), sim_env.py:88-91).  Warm start from the second step on (spiraling_mpc.py:324-331).
+        Returns (final_state [B,13], cumulative optimal cost [B], worst status [B], steps done [B])."""
+        B = state0.shape[0]
+        if scenario is None:
+            scenario = torch.zeros(B, dtype=torch.int64, device=self.device)
+        sc = scenario if isinstance(scenario, tuple) else self.scenario_tensors(scenario)
+        state = state0.clone()
+        cost = torch.zeros(B, dtype=torch.float64, device=self.device)
+        worst = torch.zeros(B, dtype=torch.int32, device=self.device)
+        for k in range(steps):
+            w = trajectory[start_step + k: start_step + k + self.N + 1]
+            xref = w.unsqueeze(0).expand(B, -1, -1).contiguous()
+            out = self.step(state, xref, scenario=sc, warm=k > 0)
+            cost += out["cost"]
+            worst = torch.maximum(worst, out["status"])
+            state = self.plant_step(state, out["thrust"], sc, noise[k] if noise is not None else None, True)
+        done = torch.full((B,), steps, dtype=torch.int32, device=self.device)
+        return state, cost, worst, done
+
 
 class _PlantStepper:
     """model.dynamics(x, u) for the host-facing SystemModel (sim_env.py:85): one un-normalised RK4 step."""

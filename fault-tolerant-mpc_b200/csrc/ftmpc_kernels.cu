@@ -252,6 +252,18 @@ __global__ void k_plant(const ftmpc_config* __restrict__ cfg, int batch, const d
     for (int k = 0; k < 13; ++k) next[(size_t)i * 13 + k] = xn[k];
 }
 
+// FP64 FMA throughput probe (roofline denominator for bench.py: MEASURED_PEAKS.json has no fp64 figure).
+// 8 independent DFMA chains per thread, 8 resident warps per scheduler.
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a, double b) {
+    double r0 = threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        r0 = fma(r0, a, b); r1 = fma(r1, a, b); r2 = fma(r2, a, b); r3 = fma(r3, a, b);
+        r4 = fma(r4, a, b); r5 = fma(r5, a, b); r6 = fma(r6, a, b); r7 = fma(r7, a, b);
+    }
+    const double s = r0 + r1 + r2 + r3 + r4 + r5 + r6 + r7;
+    if (s == 12345.6789) out[0] = s;
+}
+
 // -------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------
@@ -495,6 +507,33 @@ int ftmpc_plant_step(ftmpc_handle h, int batch, const double* state, const doubl
     k_plant<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d_cfg, batch, state, thrust, fault_mask,
                                                                      fault_force, noise, normalize, next);
     CU(cudaGetLastError());
+    return FTMPC_OK;
+}
+
+int ftmpc_fp64_peak(ftmpc_handle h, double* tflops, void* stream_) {
+    if (!h || !tflops) return FTMPC_ERR_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    double* d = nullptr;
+    CU(cudaMalloc(&d, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int iters = 1 << 16, grid = h->num_sms * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(cudaEventRecord(e0, stream));
+        k_fp64_peak<<<grid, 256, 0, stream>>>(d, iters, 0.999999, 1e-9);
+        CU(cudaEventRecord(e1, stream));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 8.0 * iters * 256.0 * grid / (ms * 1e-3) * 1e-12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
     return FTMPC_OK;
 }
 

@@ -116,6 +116,10 @@ int ftmpc_profile_read(ftmpc_handle h, void* stream, double* ms, int32_t* launch
 /* number of kernels ftmpc_step launched on its last call */
 int ftmpc_last_launches(ftmpc_handle h);
 
+/* Measurement helper for bench.py: sustained FP64 FMA throughput of this device (TFLOP/s, 2 flop per DFMA),
+ * the roofline denominator of the solve (MEASURED_PEAKS.json carries no fp64 figure).  Synchronises. */
+int ftmpc_fp64_peak(ftmpc_handle h, double* tflops, void* stream);
+
 /* ---- stage entry points (unit parity tests; same device code as ftmpc_step) ------------------ */
 /* K1: RK4 rollout + Jacobians, one warp per instance.  wrench [B,N,6] = total body wrench per stage.
  *     x [B,N+1,13] (x[:,0] given), jac [B,N,13,13] column-major per stage in z-order [w q F tau]
