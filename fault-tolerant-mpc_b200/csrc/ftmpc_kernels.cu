@@ -322,11 +322,6 @@ int ftmpc_create(ftmpc_handle* out, const ftmpc_config* cfg, const double* hull_
     h->n_ctr = 2 * (cfg->max_sqp_iter + 2);
     CU(cudaMalloc(&h->d_ctr, h->n_ctr * sizeof(int)));
     CU(cudaMallocHost(&h->h_ctr, h->n_ctr * sizeof(int)));
-    const size_t need = qp_smem_bytes(cfg->horizon);
-    if (need <= h->smem_optin) {
-        CU(cudaFuncSetAttribute(k_qp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-        CU(cudaFuncSetAttribute(k_condense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-    }
     h->n_ev = 3 * cfg->max_sqp_iter + 2;
     h->ev = new cudaEvent_t[2 * h->n_ev];
     h->ev_class = new int[h->n_ev];
@@ -408,6 +403,8 @@ int ftmpc_step(ftmpc_handle h, int batch, const double* state, const double* xre
     double* gscratch = use_global ? (double*)((char*)workspace + align_up(L.stride * sizeof(double) * (size_t)batch, 256)) : nullptr;
     const size_t sdoubles = align_up(smem, 256) / sizeof(double);
     const int K = h->cfg.max_sqp_iter;
+    // the attribute is per function, not per handle: handles with different horizons share k_qp
+    if (!use_global) CU(cudaFuncSetAttribute(k_qp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU(cudaMemsetAsync(h->d_ctr, 0, h->n_ctr * sizeof(int), stream));
     int* run_ctr = h->d_ctr;
     int* queue = h->d_ctr + (K + 2);
@@ -470,6 +467,7 @@ int ftmpc_condense(ftmpc_handle h, int batch, const double* jac, const double* h
     const size_t smem = qp_smem_bytes(h->cfg.horizon);
     if (smem > h->smem_optin) return FTMPC_ERR_UNSUPPORTED;
     const int grid = batch < h->num_sms ? batch : h->num_sms;
+    CU(cudaFuncSetAttribute(k_condense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_condense<<<grid, FTMPC_QP_THREADS, smem, (cudaStream_t)stream>>>(h->d_cfg, h->L, batch, jac, hess, x, u, xref,
                                                                          gradV, hessV, theta, H, g, nullptr, 0);
     CU(cudaGetLastError());

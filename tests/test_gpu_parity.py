@@ -21,8 +21,19 @@ def dev(a, dtype=F64):
     return torch.tensor(np.ascontiguousarray(a), dtype=dtype, device="cuda")
 
 
+_KEEP = []       # tensors whose device pointers were handed to the C ABI stay alive until the test module ends
+
+
 def ptr(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else None
+    """raw device pointer for the C ABI; the tensor is kept alive (a temporary passed as ptr(dev(x)) would be
+    returned to the caching allocator -- and reused by the next temporary -- before the kernel runs)"""
+    if t is None:
+        return None
+    _KEEP.append(t)
+    if len(_KEEP) > 4096:
+        torch.cuda.synchronize()
+        del _KEEP[:2048]
+    return C.c_void_p(t.data_ptr())
 
 
 @pytest.fixture(scope="module")

@@ -12,6 +12,7 @@ nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_rea
 SMI=$!
 timeout 900 python bench.py --steps 3 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"; cat $OUT/bench_$TAG.json
 kill $SMI
+[ "${SKIP_NCU:-0}" = "1" ] && exit 0
 SMALL="python bench.py --batch 592 --steps 1 --warmup 3 --no-latency --no-cpu-baseline"
 timeout 600 $SMALL > $OUT/plain_$TAG.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $OUT/launches_$TAG.csv $SMALL > $OUT/ncu_launches_$TAG.log 2>&1
