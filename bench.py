@@ -231,7 +231,6 @@ def main():
     sync_all()
     # ---- timed region: device-resident inputs
     L.check(eng.lib.ftmpc_profile_enable(eng.handle, 1))
-    ms_cls = np.zeros(4); n_cls = np.zeros(4, np.int64)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         sync_all()
@@ -243,10 +242,12 @@ def main():
         e1.record(stream)
         sync_all()
     ms_total = e0.elapsed_time(e1)
-    # per-kernel-class device time of the LAST timed step (events recorded on the launching stream by ftmpc_step)
-    msb = (C.c_double * 4)(); lb = (C.c_int32 * 4)()
-    L.check(eng.lib.ftmpc_profile_read(eng.handle, C.c_void_p(stream.cuda_stream), msb, lb, None, 0))
-    ms_cls[:] = list(msb); n_cls[:] = list(lb)
+    # device time of the two kernels of the LAST timed step (events recorded on the launching stream by ftmpc_step)
+    # and the solver kernel's own per-phase cycle profile
+    kms = (C.c_double * 2)(); cyc = (C.c_int64 * L.N_PHASES)()
+    L.check(eng.lib.ftmpc_profile_read(eng.handle, C.c_void_p(stream.cuda_stream), kms, cyc, L.N_PHASES))
+    kernel_ms = {"k_solve": float(kms[0]), "k_alloc": float(kms[1])}
+    cyc = np.array(list(cyc), dtype=float)
     L.check(eng.lib.ftmpc_profile_enable(eng.handle, 0))
     status = out["status"].cpu().numpy()
     iters = out["iters"].cpu().numpy()
@@ -301,16 +302,12 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (rank 0's shard, last timed step)
-    names = ["k_ls (merit line search + rollout)", "k_lin (RK4 Jacobians / costates / stage Hessians)",
-             "k_qp (condense + Cholesky + dual active-set QP)", "k_out (u0, active set, thrust allocation)"]
+    # ---- roofline of the dominant kernel, k_solve (rank 0's shard, last timed step)
     fl = algorithmic_flops(N, iters[:, 0], iters[:, 1])
     peak = C.c_double()
     L.check(eng.lib.ftmpc_fp64_peak(eng.handle, C.byref(peak), C.c_void_p(stream.cuda_stream)))
-    dom = int(np.argmax(ms_cls))
-    dom_flops = {0: 0.0, 1: fl["lin_kernel"], 2: fl["qp_kernel"], 3: 5000.0 * B}[dom] if n_cls.sum() > 1 else fl["total"]
-    dom_ms = ms_cls[dom] if ms_cls[dom] > 0 else ms_total / a.steps
-    achieved = dom_flops / (dom_ms * 1e-3) * 1e-12
+    solve_flops = fl["total"] - 5000.0 * B                      # everything but the allocation QP runs in k_solve
+    achieved = solve_flops / (kernel_ms["k_solve"] * 1e-3) * 1e-12
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_ach = algorithmic_bytes(N) * B / (ms_total / a.steps * 1e-3) * 1e-9
@@ -321,13 +318,13 @@ def main():
             traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "fp64", "kernel": names[dom].split(" ")[0], "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
+    roofline = {"bound": "fp64", "kernel": "k_solve", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved / peak.value if peak.value > 0 else None, "traffic": traffic,
                 "peak_source": "FP64 FMA probe run live on this device (ftmpc_fp64_peak); MEASURED_PEAKS.json has no fp64 figure",
                 "flops_model": "SURVEY.md 8d: K_sqp(F_lin+F_cond+F_chol)+K_qp F_iter+F_alloc with the kernel's own iteration counters",
-                "algorithmic_flops_per_step": fl["total"], "kernel_ms": {names[i].split(" ")[0]: float(ms_cls[i]) for i in range(4)},
-                "kernel_launches": {names[i].split(" ")[0]: int(n_cls[i]) for i in range(4)},
-                "whole_step_tflops": fl["total"] / (ms_total / a.steps * 1e-3) * 1e-12,
+                "algorithmic_flops_per_launch": solve_flops, "kernel_ms": kernel_ms,
+                "kernel_share_of_step": kernel_ms["k_solve"] / (ms_total / a.steps),
+                "phase_share": {n: float(c / cyc.sum()) for n, c in zip(L.PHASE_NAMES, cyc)} if cyc.sum() > 0 else None,
                 "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                         "algorithmic_bytes_per_solve": algorithmic_bytes(N),
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"}}
@@ -339,7 +336,7 @@ def main():
         from ft_mpc_b200.util import BrokenThruster
         m1 = SystemModel(0.1)
         m1.set_fault(BrokenThruster(10, 1.0)); m1.set_fault(BrokenThruster(11, 1.0))
-        c1 = SpiralingController(SpiralModel.from_system_model(m1), {"horizon": 15}, None, device=devs, poll_every=1)
+        c1 = SpiralingController(SpiralModel.from_system_model(m1), {"horizon": 15}, None, device=devs)
         c1.load_trajectory("hover", 30)
         from scipy.spatial.transform import Rotation
         x = np.concatenate([[1, 0, 1], [1, .5, 0], Rotation.from_euler("zyx", [50, 30, -10], degrees=True).as_quat(), [.3, .8, -.1]])

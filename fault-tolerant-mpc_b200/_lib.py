@@ -18,6 +18,8 @@ NX, NU, NE, NTHR, NH, NF = 13, 6, 9, 16, 26, 72
 HULL_STRIDE = NH * NU + NH
 MAX_POLY, MAX_ROOT = 32, 16
 
+N_PHASES = 9
+PHASE_NAMES = ['ls', 'lin', 'condense', 'cholesky', 'inverse', 'qp_setup', 'qp_active_set', 'qp_post', 'out']
 ST_OK, ST_MAXITER, ST_QPFAIL, ST_INFEASIBLE, ST_ALLOC = 0, 1, 2, 3, 4
 
 _PKG = Path(__file__).resolve().parent
@@ -129,7 +131,7 @@ def lib() -> C.CDLL:
     L.ftmpc_allocate.argtypes = [vp, C.c_int, dp, dp, dp, ip, vp]
     L.ftmpc_plant_step.argtypes = [vp, C.c_int, dp, dp, ip, dp, dp, C.c_int, dp, vp]
     L.ftmpc_profile_enable.argtypes = [vp, C.c_int]
-    L.ftmpc_profile_read.argtypes = [vp, vp, dp, ip, ip, C.c_int]
+    L.ftmpc_profile_read.argtypes = [vp, vp, dp, ip, C.c_int]
     L.ftmpc_last_launches.argtypes = [vp]
     L.ftmpc_fp64_peak.argtypes = [vp, C.POINTER(C.c_double), vp]
     L.ftmpc_fp64_peak.restype = C.c_int

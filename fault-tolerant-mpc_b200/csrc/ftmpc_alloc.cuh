@@ -92,26 +92,24 @@ FT_HD int clip_to_hull(const ftmpc_config& cfg, const double* hull, const double
     return tiny_qp<FTMPC_NU, FTMPC_NH>(cons, 1.0, v, 0, 1e-12, out);
 }
 
-// ---- phase_out ------------------------------------------------------------------------------------------
-FT_HD void phase_out(const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst) {
-    double* w = io.ws + (size_t)inst * L.stride;
+// ---- phase_out: write the per-instance results, then clip + allocate ---------------------------------
+// (a) phase_out_write -- block-cooperative: decision vector [u | x], u0, active set, status, counters, cost
+template <class Blk>
+FT_HD void phase_out_write(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst, int slot) {
+    const double* w = ws_slot(io, L, slot);
     const double* sc = w + L.oSc;
-    const int N = L.N;
-    int status = (int)sc[SC_STATUS];
-    if (status == FTMPC_ST_RUNNING) status = FTMPC_ST_MAXITER;
+    const int N = L.N, tid = blk.tid(), nt = blk.nthreads();
     const double* U = w + L.oU;
     const double* X = w + L.oX;
     const double* C = w + L.oC;
-    const double* uref = io.uref ? io.uref + (size_t)inst * (N + 1) * FTMPC_NU : nullptr;
-    const double* hull = io.hull_table + (size_t)io.hull_idx[inst] * FTMPC_HULL_STRIDE;
-    // optimal decision vector, reference layout [u | x]
+    // optimal decision vector, reference layout [u | x]   (spiraling_mpc.py:110-114)
     double* zw = io.z_warm + (size_t)inst * (L.n + (size_t)(N + 1) * FTMPC_NX);
-    for (int i = 0; i < L.n; ++i) zw[i] = U[i];
-    for (int i = 0; i < (N + 1) * FTMPC_NX; ++i) zw[L.n + i] = X[i];
-    for (int j = 0; j < FTMPC_NU; ++j) io.u0[(size_t)inst * FTMPC_NU + j] = U[j];
+    for (int i = tid; i < L.n; i += nt) zw[i] = U[i];
+    for (int i = tid; i < (N + 1) * FTMPC_NX; i += nt) zw[L.n + i] = X[i];
+    for (int j = tid; j < FTMPC_NU; j += nt) io.u0[(size_t)inst * FTMPC_NU + j] = U[j];
     // active set: row i active <=> b_i - g_i <= act_tol  <=>  c_i >= -act_tol
     const int nw = (L.mc + 31) / 32;
-    for (int wd = 0; wd < nw; ++wd) {
+    for (int wd = tid; wd < nw; wd += nt) {
         uint32_t bits = 0;
         for (int b = 0; b < 32; ++b) {
             const int i = wd * 32 + b;
@@ -119,6 +117,27 @@ FT_HD void phase_out(const ftmpc_config& cfg, const WsLayout& L, const StepIO& i
         }
         io.active_set[(size_t)inst * nw + wd] = bits;
     }
+    if (tid == 0) {
+        int status = (int)sc[SC_STATUS];
+        if (status == FTMPC_ST_RUNNING) status = FTMPC_ST_MAXITER;
+        io.status[inst] = status;
+        io.iters[2 * inst] = (int)sc[SC_ITER];
+        io.iters[2 * inst + 1] = (int)sc[SC_QPIT];
+        if (io.cost) io.cost[inst] = sc[SC_F];
+    }
+    blk.sync();
+    blk.mark(PH_OUT);
+}
+
+// (b) phase_alloc -- one thread per instance, from the written results: u_res, clip, thrust allocation
+FT_HD void phase_alloc(const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst) {
+    const int N = L.N;
+    int status = io.status[inst];
+    const double* zw = io.z_warm + (size_t)inst * (L.n + (size_t)(N + 1) * FTMPC_NX);
+    const double* U = zw;
+    const double* X = zw + L.n;
+    const double* uref = io.uref ? io.uref + (size_t)inst * (N + 1) * FTMPC_NU : nullptr;
+    const double* hull = io.hull_table + (size_t)io.hull_idx[inst] * FTMPC_HULL_STRIDE;
     // u_res = u*_0 + RotFullInv(q_0) ur_0 + u_comp                     spiraling_mpc.py:301-306
     const double* ff = io.fault_force + (size_t)inst * FTMPC_NTHR;
     double Df[FTMPC_NU], v[FTMPC_NU], vc[FTMPC_NU], ub[FTMPC_NTHR];
@@ -145,12 +164,8 @@ FT_HD void phase_out(const ftmpc_config& cfg, const WsLayout& L, const StepIO& i
         for (int j = 0; j < FTMPC_NTHR; ++j) a += cfg.D[i * FTMPC_NTHR + j] * th[j];
         res = fmax(res, fabs(a));
     }
-    if ((st_alloc != 0 || st_clip != 0 || !(res <= 1e-6)) && status == FTMPC_ST_OK) status = FTMPC_ST_ALLOC;
+    if ((st_alloc != 0 || st_clip != 0 || !(res <= 1e-6)) && status == FTMPC_ST_OK) io.status[inst] = FTMPC_ST_ALLOC;
     for (int j = 0; j < FTMPC_NTHR; ++j) io.thrust[(size_t)inst * FTMPC_NTHR + j] = th[j];
-    io.status[inst] = status;
-    io.iters[2 * inst] = (int)sc[SC_ITER];
-    io.iters[2 * inst + 1] = (int)sc[SC_QPIT];
-    if (io.cost) io.cost[inst] = sc[SC_F];
 }
 
 }  // namespace ftmpc

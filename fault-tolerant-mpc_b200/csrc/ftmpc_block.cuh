@@ -34,14 +34,30 @@ struct SerialBlock {
     // (value, index) pair with the smallest value; ties -> smallest index
     FT_HD void argmin(double& v, int& idx) { (void)v; (void)idx; }
     FT_HD int any(int pred) { return pred; }
+    FT_HD void mark(int) {}
 };
+
+// phase ids of the in-kernel cycle profile (ftmpc_profile_read)
+enum { PH_LS = 0, PH_LIN, PH_COND, PH_CHOL, PH_INV, PH_QPSETUP, PH_GI, PH_POST, PH_OUT, PH_COUNT };
 
 #if defined(__CUDACC__)
 // scratch: >= 2 * 32 * 2 doubles of shared memory (double-buffered so one barrier per reduction suffices)
 struct CudaBlock {
     double* scratch;
     int phase;
-    __device__ __forceinline__ explicit CudaBlock(double* s) : scratch(s), phase(0) {}
+    long long* prof;         // optional per-phase cycle accumulators (global memory), thread 0 only
+    long long t_last;
+    __device__ __forceinline__ explicit CudaBlock(double* s, long long* p = nullptr) : scratch(s), phase(0), prof(p), t_last(0) {
+        if (prof) t_last = clock64();
+    }
+    // attribute the cycles since the previous mark to phase `id` (call right after a block-wide barrier)
+    __device__ __forceinline__ void mark(int id) {
+        if (prof && threadIdx.x == 0) {
+            const long long t = clock64();
+            atomicAdd(reinterpret_cast<unsigned long long*>(prof + id), (unsigned long long)(t - t_last));
+            t_last = t;
+        }
+    }
     __device__ __forceinline__ int tid() const { return threadIdx.x; }
     __device__ __forceinline__ int nthreads() const { return blockDim.x; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }

@@ -1,12 +1,14 @@
 // ftmpc_kernels.cu -- CUDA kernels (sm_100a) and the C ABI of include/ftmpc.h.
 //
 // Kernel map:
-//   K1  k_lin / k_rk4_jac : RK4 rollout Jacobians + costates + exact stage Hessians, ONE WARP PER INSTANCE
-//   K4  k_ls              : SQP step acceptance (l1 merit) + forward rollout, one thread per instance
-//   K2+K3 k_qp            : condensing -> Cholesky -> dual active-set QP, ONE CTA PER INSTANCE, every
-//                           matrix resident in shared memory (223 KB at N=20), dynamic work queue
-//   K5  k_out             : u0, active set, thrust allocation QP, one thread per instance
-//   K6  k_plant           : plant step for closed-loop rollouts
+//   k_solve : ONE PERSISTENT CTA PER SM runs whole MPC solves back to back (dynamic instance queue):
+//               K4 step acceptance (all backtracking step lengths rolled out at once by the lanes of a warp)
+//               K1 RK4 Jacobians + costates + exact stage Hessians (one (stage, column) task per thread)
+//               K2 condensing  ->  K3 Cholesky, J = L^-T, dual active-set QP
+//             every matrix of the QP lives in shared memory (224 KB at N = 20); the per-CTA iterate (U, X,
+//             multipliers, stage Jacobians) sits in a per-CTA global slot that stays L1/L2 resident.
+//   k_alloc : K5 clip + thrust allocation QP, one thread per instance
+//   k_plant : K6 plant step for closed-loop rollouts
 // There is no CPU fallback in this translation unit: without a CUDA device ftmpc_create fails.
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -29,58 +31,50 @@ struct ftmpc_ctx {
     ftmpc_config cfg;          // host copy
     ftmpc_config* d_cfg;       // device copy
     double* d_hull;            // device hull table
-    int* d_ctr;                // device counters: [0..K) running instances after iteration k, [K..2K) work queue heads
-    int* h_ctr;                // pinned host mirror for polling
-    int n_ctr;
+    int* d_queue;              // device work-queue head
+    long long* d_prof;         // per-phase cycle accumulators (PH_COUNT) of the last profiled step
     int device, num_sms;
     size_t smem_optin;
     WsLayout L;
-    int profile, last_launches, n_ev, last_iters;
-    cudaEvent_t* ev;           // 2 events per launch slot
-    int* ev_class;             // kernel class of each slot
+    int profile, last_launches;
+    cudaEvent_t ev[3];         // before k_solve / between / after k_alloc (profile mode)
 };
 
 // -------------------------------------------------------------------------------------------------
 // kernels
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_ls(const ftmpc_config* __restrict__ cfg, WsLayout L, StepIO io, int first,
-                                           int* run_ctr) {
-    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
-    if (inst >= io.batch) return;
-    phase_ls(*cfg, L, io, inst, first);
-    if (io.ws[(size_t)inst * L.stride + L.oSc + SC_STATUS] == (double)FTMPC_ST_RUNNING) atomicAdd(run_ctr, 1);
-}
-
-__global__ void __launch_bounds__(128) k_lin(const ftmpc_config* __restrict__ cfg, WsLayout L, StepIO io) {
-    const int inst = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (inst >= io.batch) return;
-    WarpBlock wb;
-    phase_lin(wb, *cfg, L, io, inst);
-}
-
 #define FTMPC_QP_THREADS 256
 __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
-    k_qp(const ftmpc_config* __restrict__ cfg, WsLayout L, StepIO io, int* queue, double* gscratch, size_t sdoubles) {
+    k_solve(const ftmpc_config* __restrict__ cfg, WsLayout L, StepIO io, int* queue, double* gscratch, size_t sdoubles,
+            long long* prof) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double red[128];
     __shared__ int s_inst;
     double* scratch = gscratch ? gscratch + (size_t)blockIdx.x * sdoubles : smem;
-    CudaBlock blk(red);
+    CudaBlock blk(red, prof);
+    const int slot = blockIdx.x;
+    const double* sc = ws_slot(io, L, slot) + L.oSc;
     for (;;) {
         if (threadIdx.x == 0) s_inst = atomicAdd(queue, 1);
         __syncthreads();
         const int inst = s_inst;
         __syncthreads();
         if (inst >= io.batch) break;
-        phase_qp(blk, *cfg, L, io, inst, scratch);
-        __syncthreads();
+        phase_ls_block(blk, *cfg, L, io, inst, slot, 1, scratch);
+        for (int it = 0; it < cfg->max_sqp_iter; ++it) {
+            if (sc[SC_STATUS] != (double)FTMPC_ST_RUNNING) break;      // uniform: written before the last barrier
+            phase_lin(blk, *cfg, L, io, inst, slot);
+            phase_qp(blk, *cfg, L, io, inst, slot, scratch);
+            phase_ls_block(blk, *cfg, L, io, inst, slot, 0, scratch);
+        }
+        phase_out_write(blk, *cfg, L, io, inst, slot);
     }
 }
 
-__global__ void __launch_bounds__(64) k_out(const ftmpc_config* __restrict__ cfg, WsLayout L, StepIO io) {
+__global__ void __launch_bounds__(64) k_alloc(const ftmpc_config* __restrict__ cfg, WsLayout L, StepIO io) {
     const int inst = blockIdx.x * blockDim.x + threadIdx.x;
     if (inst >= io.batch) return;
-    phase_out(*cfg, L, io, inst);
+    phase_alloc(*cfg, L, io, inst);
 }
 
 // ---- stage kernels --------------------------------------------------------------------------------
@@ -277,10 +271,6 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 static size_t qp_smem_bytes(int N) { return qp_scratch_doubles(N) * sizeof(double); }
 
-static int qp_grid(const ftmpc_ctx* h, int batch, bool use_global) {
-    int g = h->num_sms * (use_global ? 2 : 1);
-    return batch < g ? batch : g;
-}
 
 extern "C" {
 
@@ -319,13 +309,10 @@ int ftmpc_create(ftmpc_handle* out, const ftmpc_config* cfg, const double* hull_
     const size_t hb = (size_t)cfg->n_hull_sets * FTMPC_HULL_STRIDE * sizeof(double);
     CU(cudaMalloc(&h->d_hull, hb));
     CU(cudaMemcpy(h->d_hull, hull_table, hb, cudaMemcpyHostToDevice));
-    h->n_ctr = 2 * (cfg->max_sqp_iter + 2);
-    CU(cudaMalloc(&h->d_ctr, h->n_ctr * sizeof(int)));
-    CU(cudaMallocHost(&h->h_ctr, h->n_ctr * sizeof(int)));
-    h->n_ev = 3 * cfg->max_sqp_iter + 2;
-    h->ev = new cudaEvent_t[2 * h->n_ev];
-    h->ev_class = new int[h->n_ev];
-    for (int i = 0; i < 2 * h->n_ev; ++i) CU(cudaEventCreate(&h->ev[i]));
+    CU(cudaMalloc(&h->d_queue, sizeof(int)));
+    CU(cudaMalloc(&h->d_prof, PH_COUNT * sizeof(long long)));
+    CU(cudaMemset(h->d_prof, 0, PH_COUNT * sizeof(long long)));
+    for (int i = 0; i < 3; ++i) CU(cudaEventCreate(&h->ev[i]));
     *out = h;
     return FTMPC_OK;
 }
@@ -338,48 +325,53 @@ int ftmpc_profile_enable(ftmpc_handle h, int enable) {
 
 int ftmpc_last_launches(ftmpc_handle h) { return h ? h->last_launches : FTMPC_ERR_ARG; }
 
-int ftmpc_profile_read(ftmpc_handle h, void* stream, double* ms, int32_t* launches, int32_t* running, int n_running) {
-    if (!h || !ms || !launches) return FTMPC_ERR_ARG;
+int ftmpc_profile_read(ftmpc_handle h, void* stream, double* kernel_ms, int64_t* phase_cycles, int n_phase) {
+    if (!h || !kernel_ms) return FTMPC_ERR_ARG;
     CU(cudaStreamSynchronize((cudaStream_t)stream));
-    for (int c = 0; c < 4; ++c) { ms[c] = 0.0; launches[c] = 0; }
+    kernel_ms[0] = kernel_ms[1] = 0.0;
     if (h->profile) {
-        for (int i = 0; i < h->last_launches && i < h->n_ev; ++i) {
-            float t = 0.f;
-            CU(cudaEventElapsedTime(&t, h->ev[2 * i], h->ev[2 * i + 1]));
-            ms[h->ev_class[i]] += t;
-            launches[h->ev_class[i]] += 1;
-        }
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, h->ev[0], h->ev[1]));
+        kernel_ms[0] = t;
+        CU(cudaEventElapsedTime(&t, h->ev[1], h->ev[2]));
+        kernel_ms[1] = t;
     }
-    if (running && n_running > 0) {
-        const int K = h->cfg.max_sqp_iter;
-        CU(cudaMemcpy(h->h_ctr, h->d_ctr, (K + 1) * sizeof(int), cudaMemcpyDeviceToHost));
-        for (int k = 0; k < n_running; ++k) running[k] = (k <= h->last_iters && k <= K) ? h->h_ctr[k] : -1;
+    if (phase_cycles && n_phase > 0) {
+        long long tmp[PH_COUNT];
+        CU(cudaMemcpy(tmp, h->d_prof, sizeof(tmp), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n_phase; ++i) phase_cycles[i] = i < PH_COUNT ? (int64_t)tmp[i] : 0;
     }
     return FTMPC_OK;
 }
 
 void ftmpc_destroy(ftmpc_handle h) {
     if (!h) return;
-    if (h->ev) {
-        for (int i = 0; i < 2 * h->n_ev; ++i) cudaEventDestroy(h->ev[i]);
-        delete[] h->ev;
-        delete[] h->ev_class;
-    }
+    for (int i = 0; i < 3; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     cudaFree(h->d_cfg);
     cudaFree(h->d_hull);
-    cudaFree(h->d_ctr);
-    cudaFreeHost(h->h_ctr);
+    cudaFree(h->d_queue);
+    cudaFree(h->d_prof);
     delete h;
 }
 
 int ftmpc_num_var(ftmpc_handle h) { return h ? h->L.n + (h->L.N + 1) * FTMPC_NX : FTMPC_ERR_ARG; }
 int ftmpc_num_ineq(ftmpc_handle h) { return h ? h->L.mc : FTMPC_ERR_ARG; }
 
+// shared-memory scratch of one CTA: the QP matrices, or the line-search rollouts (they alternate)
+static size_t solve_smem_bytes(int N) {
+    size_t a = qp_scratch_doubles(N), b = ls_scratch_doubles(N);
+    return (a > b ? a : b) * sizeof(double);
+}
+
+static int solve_grid(const ftmpc_ctx* h, int batch) { return batch < h->num_sms ? batch : h->num_sms; }
+
 int ftmpc_workspace_bytes(ftmpc_handle h, int batch, size_t* out) {
     if (!h || !out || batch < 1) return FTMPC_ERR_ARG;
-    size_t b = align_up(h->L.stride * sizeof(double) * (size_t)batch, 256);
-    const size_t need = qp_smem_bytes(h->cfg.horizon);
-    if (need > h->smem_optin) b += align_up(need, 256) * (size_t)qp_grid(h, batch, true);
+    // one iterate slot per resident CTA (not per instance), plus the CTA scratch when it does not fit in shared memory
+    const int grid = solve_grid(h, batch);
+    size_t b = align_up(h->L.stride * sizeof(double) * (size_t)grid, 256);
+    const size_t need = solve_smem_bytes(h->cfg.horizon);
+    if (need > h->smem_optin) b += align_up(need, 256) * (size_t)grid;
     *out = b;
     return FTMPC_OK;
 }
@@ -398,42 +390,24 @@ int ftmpc_step(ftmpc_handle h, int batch, const double* state, const double* xre
     const WsLayout L = h->L;
     StepIO io{batch, state, xref, uref, fault_mask, fault_force, hull_idx, h->d_hull, warm, z_warm, thrust, u0,
               active_set, status, iters, cost, (double*)workspace};
-    const size_t smem = qp_smem_bytes(h->cfg.horizon);
+    const int grid = solve_grid(h, batch);
+    const size_t smem = solve_smem_bytes(h->cfg.horizon);
     const bool use_global = smem > h->smem_optin;
-    double* gscratch = use_global ? (double*)((char*)workspace + align_up(L.stride * sizeof(double) * (size_t)batch, 256)) : nullptr;
+    double* gscratch = use_global ? (double*)((char*)workspace + align_up(L.stride * sizeof(double) * (size_t)grid, 256)) : nullptr;
     const size_t sdoubles = align_up(smem, 256) / sizeof(double);
-    const int K = h->cfg.max_sqp_iter;
-    // the attribute is per function, not per handle: handles with different horizons share k_qp
-    if (!use_global) CU(cudaFuncSetAttribute(k_qp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaMemsetAsync(h->d_ctr, 0, h->n_ctr * sizeof(int), stream));
-    int* run_ctr = h->d_ctr;
-    int* queue = h->d_ctr + (K + 2);
-    const int g128 = (batch + 127) / 128;
-    int slot = 0;
-#define FT_LAUNCH(cls, ...)                                                     \
-    do {                                                                        \
-        if (h->profile && slot < h->n_ev) cudaEventRecord(h->ev[2 * slot], stream); \
-        __VA_ARGS__;                                                            \
-        if (h->profile && slot < h->n_ev) { cudaEventRecord(h->ev[2 * slot + 1], stream); h->ev_class[slot] = cls; } \
-        ++slot;                                                                 \
-    } while (0)
-    FT_LAUNCH(0, (k_ls<<<g128, 128, 0, stream>>>(h->d_cfg, L, io, 1, run_ctr + 0)));
-    const int gq = qp_grid(h, batch, use_global);
-    int it = 0;
-    for (; it < K; ++it) {
-        FT_LAUNCH(1, (k_lin<<<(batch + 3) / 4, 128, 0, stream>>>(h->d_cfg, L, io)));
-        FT_LAUNCH(2, (k_qp<<<gq, FTMPC_QP_THREADS, use_global ? 0 : smem, stream>>>(h->d_cfg, L, io, queue + it, gscratch, sdoubles)));
-        FT_LAUNCH(0, (k_ls<<<g128, 128, 0, stream>>>(h->d_cfg, L, io, 0, run_ctr + it + 1)));
-        if (h->cfg.poll_every > 0 && (it + 1) % h->cfg.poll_every == 0 && it + 1 < K) {
-            CU(cudaMemcpyAsync(h->h_ctr, run_ctr + it + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
-            CU(cudaStreamSynchronize(stream));
-            if (h->h_ctr[0] == 0) { ++it; break; }
-        }
+    // the attribute is per function, not per handle: handles with different horizons share k_solve
+    if (!use_global) CU(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaMemsetAsync(h->d_queue, 0, sizeof(int), stream));
+    if (h->profile) {
+        CU(cudaMemsetAsync(h->d_prof, 0, PH_COUNT * sizeof(long long), stream));
+        CU(cudaEventRecord(h->ev[0], stream));
     }
-    h->last_iters = it;
-    FT_LAUNCH(3, (k_out<<<(batch + 63) / 64, 64, 0, stream>>>(h->d_cfg, L, io)));
-#undef FT_LAUNCH
-    h->last_launches = slot;
+    k_solve<<<grid, FTMPC_QP_THREADS, use_global ? 0 : smem, stream>>>(h->d_cfg, L, io, h->d_queue, gscratch, sdoubles,
+                                                                        h->profile ? h->d_prof : nullptr);
+    if (h->profile) CU(cudaEventRecord(h->ev[1], stream));
+    k_alloc<<<(batch + 63) / 64, 64, 0, stream>>>(h->d_cfg, L, io);
+    if (h->profile) CU(cudaEventRecord(h->ev[2], stream));
+    h->last_launches = 2;
     CU(cudaGetLastError());
     return FTMPC_OK;
 }

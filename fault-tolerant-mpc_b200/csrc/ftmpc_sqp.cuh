@@ -67,8 +67,10 @@ struct StepIO {
     int32_t* status;            // [B]
     int32_t* iters;             // [B,2]
     double* cost;               // [B]
-    double* ws;                 // workspace
+    double* ws;                 // workspace: one slot of L.stride doubles per instance (CPU port) or per CTA (k_solve)
 };
+
+FT_HD double* ws_slot(const StepIO& io, const WsLayout& L, int slot) { return io.ws + (size_t)slot * L.stride; }
 
 FT_HD DynConsts dyn_consts(const ftmpc_config& c) {
     DynConsts k;
@@ -130,8 +132,8 @@ FT_HD void rollout_eval(const ftmpc_config& cfg, const WsLayout& L, const double
 }
 
 // ---- phase_ls: initialise (first != 0) or accept the QP step, then re-evaluate -----------------------
-FT_HD void phase_ls(const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst, int first) {
-    double* w = io.ws + (size_t)inst * L.stride;
+FT_HD void phase_ls(const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst, int slot, int first) {
+    double* w = ws_slot(io, L, slot);
     double* sc = w + L.oSc;
     const int N = L.N;
     const double* xref = io.xref + (size_t)inst * (N + 1) * FTMPC_NE;
@@ -188,10 +190,209 @@ FT_HD void phase_ls(const ftmpc_config& cfg, const WsLayout& L, const StepIO& io
     terminal_eval(cfg, e, w + L.oGV, w + L.oHV);
 }
 
+#if defined(__CUDACC__)
+// ---- block-cooperative step acceptance (device only) ------------------------------------------------
+// Same merit test as phase_ls, organised for one CTA:
+//   A. the lanes of warp 0 roll the dynamics out for ALL backtracking step lengths at once
+//      (lane i <-> alpha = 2^-i, i < 28: the serial loop of phase_ls stops at alpha < 1e-8 = lane 27),
+//      states / stage wrenches go to shared scratch, the cost stays in a register;
+//   B. constraint rows are evaluated row-parallel: first for alpha = 1 by the whole block (the common
+//      case ends here), otherwise for the remaining step lengths warp-per-alpha;
+//   C. the first step length passing the Armijo test is committed.
+#define FTMPC_LS_NALPHA 28
+struct LsScratch {
+    double *Xs, *Ws, *fa, *csa, *cma, *hull;
+    int xs_stride, ws_stride;
+};
+__device__ __forceinline__ LsScratch ls_carve(double* buf, int N) {
+    LsScratch s;
+    s.xs_stride = (N + 1) * FTMPC_NX + 1;          // odd strides: lanes of warp 0 hit different banks
+    s.ws_stride = N * FTMPC_NU + 1;
+    double* p = buf;
+    s.Xs = p; p += (size_t)FTMPC_LS_NALPHA * s.xs_stride;
+    s.Ws = p; p += (size_t)FTMPC_LS_NALPHA * s.ws_stride;
+    s.fa = p; p += 32;
+    s.csa = p; p += 32;
+    s.cma = p; p += 32;
+    s.hull = p; p += FTMPC_HULL_STRIDE;
+    return s;
+}
+__host__ __device__ inline size_t ls_scratch_doubles(int N) {
+    return (size_t)FTMPC_LS_NALPHA * ((N + 1) * FTMPC_NX + 1 + N * FTMPC_NU + 1) + 96 + FTMPC_HULL_STRIDE;
+}
+
+// forward rollout at U + alpha d: states -> Xs, stage wrenches -> Ws, returns the objective
+__device__ __forceinline__ double rollout_states(const ftmpc_config& cfg, int N, const double* __restrict__ xref,
+                                                 const double* __restrict__ uref, const double* __restrict__ U,
+                                                 const double* __restrict__ d, double alpha, const double* x0,
+                                                 double* Xs, double* Ws) {
+    const DynConsts k = dyn_consts(cfg);
+    double x[FTMPC_NX], xn[FTMPC_NX], u[FTMPC_NU], Wr[FTMPC_NU];
+    for (int i = 0; i < FTMPC_NX; ++i) { x[i] = x0[i]; Xs[i] = x[i]; }
+    double f = 0.0;
+    for (int t = 0; t < N; ++t) {
+        for (int j = 0; j < FTMPC_NU; ++j) u[j] = U[t * FTMPC_NU + j] + alpha * d[t * FTMPC_NU + j];
+        stage_wrench(cfg, u, uref ? uref + t * FTMPC_NU : nullptr, x + 9, Wr);
+        for (int j = 0; j < FTMPC_NE; ++j) {
+            const double e = x[j] - xref[t * FTMPC_NE + j];
+            f += cfg.Q[j] * e * e;
+        }
+        for (int j = 0; j < FTMPC_NU; ++j) { f += cfg.R[j] * u[j] * u[j]; Ws[t * FTMPC_NU + j] = Wr[j]; }
+        rk4_step(k, x, Wr, xn);
+        for (int i = 0; i < FTMPC_NX; ++i) { x[i] = xn[i]; Xs[(t + 1) * FTMPC_NX + i] = xn[i]; }
+    }
+    double e[FTMPC_NE];
+    for (int j = 0; j < FTMPC_NE; ++j) e[j] = x[j] - xref[N * FTMPC_NE + j];
+    f += terminal_value(cfg, e);
+    return f;
+}
+
+// value of constraint row p (c <= 0 feasible) from stored stage wrenches / terminal state
+__device__ __forceinline__ double cons_value(const ftmpc_config& cfg, int N, const double* hull, const double* xrefN,
+                                             const double* Xs, const double* Ws, int p) {
+    if (p < FTMPC_NH * N) {
+        const int t = p / FTMPC_NH, i = p - t * FTMPC_NH;
+        double v = -hull[FTMPC_NH * FTMPC_NU + i];
+        for (int j = 0; j < FTMPC_NU; ++j) v += hull[i * FTMPC_NU + j] * Ws[t * FTMPC_NU + j];
+        return v;
+    }
+    const int i = p - FTMPC_NH * N;
+    double v = -cfg.bf[i];
+    for (int j = 0; j < FTMPC_NE; ++j) v += cfg.Af[i * FTMPC_NE + j] * (Xs[N * FTMPC_NX + j] - xrefN[j]);
+    return v;
+}
+
+__device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_config& cfg, const WsLayout& L,
+                                               const StepIO& io, int inst, int slot, int first, double* scratch) {
+    double* w = ws_slot(io, L, slot);
+    double* sc = w + L.oSc;
+    const int N = L.N, tid = blk.tid(), nt = blk.nthreads(), lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const double* xref = io.xref + (size_t)inst * (N + 1) * FTMPC_NE;
+    const double* uref = io.uref ? io.uref + (size_t)inst * (N + 1) * FTMPC_NU : nullptr;
+    const double* hull_g = io.hull_table + (size_t)io.hull_idx[inst] * FTMPC_HULL_STRIDE;
+    double* U = w + L.oU;
+    double* D = w + L.oD;
+    double* X = w + L.oX;
+    double* C = w + L.oC;
+    const LsScratch s = ls_carve(scratch, N);
+    double nu = 1.0, phi0 = 0.0, dphi = 0.0, dmax = 0.0, iter = 0.0;
+    if (first) {
+        if (tid == 0) robot_to_center(dyn_consts(cfg), io.state + (size_t)inst * FTMPC_NX, X);      // spiraling_mpc.py:290
+        const double* zw = io.z_warm + (size_t)inst * (L.n + (size_t)(N + 1) * FTMPC_NX);
+        for (int i = tid; i < L.n; i += nt) {                                                       // warm start shift, :324-331
+            const int t = i / FTMPC_NU;
+            U[i] = (io.warm && t + 1 < N) ? zw[i + FTMPC_NU] : 0.0;
+        }
+        for (int i = tid; i < L.nv; i += nt) D[i] = 0.0;
+        for (int i = tid; i < L.m; i += nt) w[L.oLam + i] = 0.0;
+    } else {
+        const double status = sc[SC_STATUS], qpst = sc[SC_QPST];
+        nu = fmax(sc[SC_NU], 1.1 * sc[SC_LAMMAX]);
+        phi0 = sc[SC_F] + nu * sc[SC_CSUM];
+        dphi = sc[SC_GD] - nu * sc[SC_CSUM];
+        dmax = sc[SC_DMAX];
+        iter = sc[SC_ITER] + 1.0;
+        blk.sync();                                   // everybody has read the scalars
+        if (status != FTMPC_ST_RUNNING) return;
+        if (qpst != 0.0) {
+            if (tid == 0) sc[SC_STATUS] = FTMPC_ST_QPFAIL;
+            blk.sync();
+            return;
+        }
+    }
+    for (int i = tid; i < FTMPC_HULL_STRIDE; i += nt) s.hull[i] = hull_g[i];
+    blk.sync();
+    // A. rollouts, one step length per lane
+    const int nalpha = first ? 1 : FTMPC_LS_NALPHA;
+    if (warp == 0 && lane < nalpha) {
+        const double alpha = first ? 0.0 : ldexp(1.0, -lane);
+        s.fa[lane] = rollout_states(cfg, N, xref, uref, U, D, alpha, X, s.Xs + (size_t)lane * s.xs_stride,
+                                    s.Ws + (size_t)lane * s.ws_stride);
+    }
+    blk.sync();
+    // B0. alpha index 0 by the whole block; the constraint values go straight to C
+    int win = -1;
+    {
+        double cs = 0.0, cm = 0.0;
+        for (int p = tid; p < L.mc; p += nt) {
+            const double v = cons_value(cfg, N, s.hull, xref + N * FTMPC_NE, s.Xs, s.Ws, p);
+            C[p] = v;
+            if (v > 0.0) { cs += v; cm = fmax(cm, v); }
+        }
+        cs = blk.sum(cs);
+        cm = blk.max(cm);
+        double f = s.fa[0];
+        if (!(f == f) || !(cs == cs)) { f = INFINITY; cs = INFINITY; }
+        if (tid == 0) { s.fa[0] = f; s.csa[0] = cs; s.cma[0] = cm; }
+        if (first || f + nu * cs <= phi0 + 1e-4 * dphi) win = 0;
+    }
+    blk.sync();
+    if (win < 0) {
+        // B1. the remaining step lengths, one warp per alpha
+        for (int a = 1 + warp; a < nalpha; a += nw) {
+            const double* Xa = s.Xs + (size_t)a * s.xs_stride;
+            const double* Wa = s.Ws + (size_t)a * s.ws_stride;
+            double cs = 0.0, cm = 0.0;
+            for (int p = lane; p < L.mc; p += 32) {
+                const double v = cons_value(cfg, N, s.hull, xref + N * FTMPC_NE, Xa, Wa, p);
+                if (v > 0.0) { cs += v; cm = fmax(cm, v); }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                cs += __shfl_xor_sync(0xffffffffu, cs, o);
+                cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+            }
+            if (lane == 0) {
+                double f = s.fa[a];
+                if (!(f == f) || !(cs == cs)) { f = INFINITY; cs = INFINITY; }
+                s.fa[a] = f; s.csa[a] = cs; s.cma[a] = cm;
+            }
+        }
+        blk.sync();
+        for (int a = 1; a < nalpha && win < 0; ++a) {
+            const double alpha = ldexp(1.0, -a);
+            if (s.fa[a] + nu * s.csa[a] <= phi0 + 1e-4 * alpha * dphi || alpha < 1e-8) win = a;
+        }
+        const double* Xa = s.Xs + (size_t)win * s.xs_stride;
+        const double* Wa = s.Ws + (size_t)win * s.ws_stride;
+        for (int p = tid; p < L.mc; p += nt) C[p] = cons_value(cfg, N, s.hull, xref + N * FTMPC_NE, Xa, Wa, p);
+    }
+    // C. commit
+    const double alpha = first ? 0.0 : ldexp(1.0, -win);
+    const double f = s.fa[win], csum = s.csa[win], cmax = s.cma[win];
+    const bool finite = f < INFINITY;
+    if (!first && finite) for (int i = tid; i < L.n; i += nt) U[i] += alpha * D[i];
+    const double* Xa = s.Xs + (size_t)win * s.xs_stride;
+    if (finite) for (int i = tid; i < (N + 1) * FTMPC_NX; i += nt) X[i] = Xa[i];
+    if (tid == 0) {
+        if (first) {
+            for (int i = 0; i < SC_COUNT; ++i) sc[i] = 0.0;
+            sc[SC_NU] = 1.0;
+            sc[SC_THETA] = -1.0;                   // first QP uses the Gauss-Newton model
+            sc[SC_STATUS] = finite ? FTMPC_ST_RUNNING : FTMPC_ST_QPFAIL;
+        } else {
+            sc[SC_ITER] = iter;
+            sc[SC_NU] = nu;
+            sc[SC_ALPHA] = alpha;
+            if (!finite) sc[SC_STATUS] = FTMPC_ST_QPFAIL;
+            else if (dmax <= cfg.sqp_tol) sc[SC_STATUS] = (cmax <= cfg.feas_tol) ? FTMPC_ST_OK : FTMPC_ST_INFEASIBLE;
+            else if (iter >= cfg.max_sqp_iter) sc[SC_STATUS] = FTMPC_ST_MAXITER;
+        }
+        if (finite || first) {
+            sc[SC_F] = f; sc[SC_CSUM] = csum; sc[SC_CMAX] = cmax;
+            double e[FTMPC_NE];
+            for (int j = 0; j < FTMPC_NE; ++j) e[j] = Xa[N * FTMPC_NX + j] - xref[N * FTMPC_NE + j];
+            terminal_eval(cfg, e, w + L.oGV, w + L.oHV);
+        }
+    }
+    blk.sync();
+    blk.mark(PH_LS);
+}
+#endif  // __CUDACC__
+
 // ---- phase_lin: Jacobians, costates, stage Hessians (lanes of one warp / a serial loop) -------------
 template <class Blk>
-FT_HD void phase_lin(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst) {
-    double* w = io.ws + (size_t)inst * L.stride;
+FT_HD void phase_lin(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst, int slot) {
+    double* w = ws_slot(io, L, slot);
     const double* sc = w + L.oSc;
     if (sc[SC_STATUS] != FTMPC_ST_RUNNING) return;
     const int N = L.N, tid = blk.tid(), nt = blk.nthreads();
@@ -248,6 +449,7 @@ FT_HD void phase_lin(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const
         for (int i = 0; i < 13; ++i) Wz[(size_t)it * 13 + i] = hc[i];
     }
     blk.sync();
+    blk.mark(PH_LIN);
 }
 
 // ---- the MPC QP seen by the active-set solver -----------------------------------------------------
@@ -487,8 +689,8 @@ FT_HD void condense(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
 
 // ---- phase_qp ------------------------------------------------------------------------------------------
 template <class Blk>
-FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst, double* scratch) {
-    double* w = io.ws + (size_t)inst * L.stride;
+FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst, int slot, double* scratch) {
+    double* w = ws_slot(io, L, slot);
     double* sc = w + L.oSc;
     if (sc[SC_STATUS] != FTMPC_ST_RUNNING) return;
     const int N = L.N, n = L.n, nv = L.nv, ne = nv + FTMPC_NE, ld = nv, tid = blk.tid(), nt = blk.nthreads();
@@ -516,10 +718,12 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     blk.sync();
     for (;;) {
         condense(blk, cfg, L, s, Jz, Wz, w + L.oX, w + L.oU, xref, w + L.oGV, w + L.oHV, theta, sigma, lam_prev);
+        blk.mark(PH_COND);
         double dmaxl = 0.0;
         for (int i = tid; i < n; i += nt) dmaxl = fmax(dmaxl, fabs(s.E[(size_t)i * ld + i]));
         const double dscale = blk.max(dmaxl);
         const int bad = chol_lower(blk, n, ld, s.E, 1e-10 * fmax(1.0, dscale));
+        blk.mark(PH_CHOL);
         if (!bad) break;
         ++fails;
         blk.sync();
@@ -530,6 +734,7 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         else theta = (theta > 0.125) ? 0.5 * theta : 0.0;
     }
     tri_inv_transpose(blk, n, ld, s.E, s.dg);
+    blk.mark(PH_INV);
     // slack variable column/row, extension rows  X J  (X = d x_N[0:9] / d U)
     for (int i = tid; i < nv; i += nt) {
         s.E[(size_t)i * ld + n] = 0.0;
@@ -556,9 +761,11 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     }
     blk.sync();
     MpcCons cons{N, n, nv, L.mc, s.hull, cfg.Af, s.cv};
+    blk.mark(PH_QPSETUP);
     int qit1 = 0;
     // the previous multipliers are still needed if this attempt is rejected: the QP writes to the spare copy
     st = gi_solve(blk, cons, s.gi, nv, ne, ld, L.m, 0, w + L.oLam + L.m, cfg.max_qp_iter, cfg.qp_tol, &qit1, &nact);
+    blk.mark(PH_GI);
     qit += qit1;
     if (sigma > 0.0 && st == GI_OK) {       // every predicted-active row must be active in the QP solution
         int viol = 0;
@@ -589,6 +796,7 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         sc[SC_QPST] = (st == GI_OK && dmx == dmx) ? 0.0 : (double)(st ? st : 4);
     }
     blk.sync();
+    blk.mark(PH_POST);
 }
 
 }  // namespace ftmpc

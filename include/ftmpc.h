@@ -10,8 +10,8 @@
  * ctypes binding a maintainer of the reference would add.
  *
  * Conventions: all tensors are contiguous row-major DEVICE buffers owned by the caller (PyTorch);
- * fp64 arithmetic; every call only enqueues work on `stream` (no hidden synchronisation, except
- * ftmpc_step's optional early-exit poll, see `poll_every`); return value 0 = ok, <0 = error
+ * fp64 arithmetic; every call only enqueues work on `stream` (no hidden synchronisation);
+ * return value 0 = ok, <0 = error
  * (ftmpc_strerror); per-instance outcomes are reported in status[B], never by exit()/exceptions.
  * One handle per device; a handle is not thread-safe.
  */
@@ -59,7 +59,7 @@ typedef struct ftmpc_config {
     int32_t dtype;             /* 0 = fp64 (only mode implemented)                                          */
     int32_t max_sqp_iter;      /* outer iteration cap (default 40)                                          */
     int32_t max_qp_iter;       /* active-set iteration cap per QP (default 20*(n+m))                        */
-    int32_t poll_every;        /* ftmpc_step polls the running-instance counter every k SQP iterations to stop early (0 = never: fully asynchronous) */
+    int32_t poll_every;        /* reserved (unused: ftmpc_step never synchronises; a persistent CTA stops iterating when its instance converges) */
     int32_t n_poly, n_root, n_hull_sets;
     double dt, mass, inertia[3], r[3], f_virt[3], max_thrust;   /* sys_model.py:52-61, spiral_parameters.py:33-39 */
     double Q[FTMPC_NE], R[FTMPC_NU];                            /* reactive.yaml:32-33                      */
@@ -107,12 +107,15 @@ int ftmpc_step(ftmpc_handle h, int batch, const double* state, const double* xre
                double* z_warm, double* thrust, double* u0, uint32_t* active_set, int32_t* status,
                int32_t* iters, double* cost, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Profiling hooks used by bench.py: when enabled, ftmpc_step brackets every kernel launch with CUDA
- * events on `stream`.  ftmpc_profile_read synchronises the stream and returns, for the LAST ftmpc_step:
- *   ms[0..3]   total device time of k_ls, k_lin, k_qp, k_out      launches[0..3] their launch counts
- *   running[k] instances still iterating after SQP iteration k (k < max_sqp_iter+1, -1 = not launched) */
+/* Profiling hooks used by bench.py.  When enabled, ftmpc_step brackets its kernels with CUDA events on `stream` and
+ * the solver kernel accumulates a per-phase cycle profile.  ftmpc_profile_read synchronises the stream and returns, for
+ * the LAST ftmpc_step:  kernel_ms[0] = k_solve, kernel_ms[1] = k_alloc (device time);
+ * phase_cycles[i] = SM cycles summed over all CTAs spent in phase i:
+ *   0 step acceptance + rollout, 1 linearisation (Jacobians, costates, stage Hessians), 2 condensing, 3 Cholesky,
+ *   4 J = L^-T, 5 QP set-up, 6 dual active-set iterations, 7 QP post-processing, 8 result write-out. */
+#define FTMPC_N_PHASES 9
 int ftmpc_profile_enable(ftmpc_handle h, int enable);
-int ftmpc_profile_read(ftmpc_handle h, void* stream, double* ms, int32_t* launches, int32_t* running, int n_running);
+int ftmpc_profile_read(ftmpc_handle h, void* stream, double* kernel_ms, int64_t* phase_cycles, int n_phase);
 /* number of kernels ftmpc_step launched on its last call */
 int ftmpc_last_launches(ftmpc_handle h);
 

@@ -47,12 +47,12 @@ int ftmpc_cpu_step(const ftmpc_config* cfg, const double* hull_table, int batch,
         SerialBlock blk;
 #pragma omp for schedule(dynamic, 1)
         for (int inst = 0; inst < batch; ++inst) {
-            phase_ls(*cfg, L, io, inst, 1);
+            phase_ls(*cfg, L, io, inst, inst, 1);
             for (int it = 0; it < cfg->max_sqp_iter; ++it) {
                 if (ws[(size_t)inst * L.stride + L.oSc + SC_STATUS] != FTMPC_ST_RUNNING) break;
-                phase_lin(blk, *cfg, L, io, inst);
-                phase_qp(blk, *cfg, L, io, inst, scratch.data());
-                phase_ls(*cfg, L, io, inst, 0);
+                phase_lin(blk, *cfg, L, io, inst, inst);
+                phase_qp(blk, *cfg, L, io, inst, inst, scratch.data());
+                phase_ls(*cfg, L, io, inst, inst, 0);
                 if (trace) {
                     const double* sc = ws + (size_t)inst * L.stride + L.oSc;
                     std::printf("inst %d it %2d f %.9f csum %.3e cmax %.3e nu %.3g theta %.3g dmax %.3e delta %.3e lammax %.3g alpha %.3g qpit %g nact %g cholfail %g qpst %g st %g\n",
@@ -60,7 +60,8 @@ int ftmpc_cpu_step(const ftmpc_config* cfg, const double* hull_table, int batch,
                                 sc[SC_LAMMAX], sc[SC_ALPHA], sc[SC_QPIT], sc[SC_NACT], sc[SC_CHOLFAIL], sc[SC_QPST], sc[SC_STATUS]);
                 }
             }
-            phase_out(*cfg, L, io, inst);
+            phase_out_write(blk, *cfg, L, io, inst, inst);
+            phase_alloc(*cfg, L, io, inst);
         }
     }
     return 0;

@@ -3,7 +3,7 @@
 # Usage (from the repo root, under gpurun): bash tools/gpu_round.sh <tag> [kernel-regex]
 set -u
 TAG=${1:-r01}
-KRE=${2:-k_qp}
+KRE=${2:-k_solve}
 OUT=gpurun_out
 mkdir -p $OUT
 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > $OUT/smoke_$TAG.log 2>&1; echo "smoke rc=$?"
@@ -15,9 +15,9 @@ kill $SMI
 [ "${SKIP_NCU:-0}" = "1" ] && exit 0
 SMALL="python bench.py --batch 592 --steps 1 --warmup 3 --no-latency --no-cpu-baseline"
 timeout 600 $SMALL > $OUT/plain_$TAG.log 2>&1 &&
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $OUT/launches_$TAG.csv $SMALL > $OUT/ncu_launches_$TAG.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches_$TAG.csv $SMALL > $OUT/ncu_launches_$TAG.log 2>&1
 echo "launch list rc=$?"
 timeout 600 $SMALL > $OUT/plain2_$TAG.log 2>&1 &&
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:$KRE -s 4 -c 3 -f -o $OUT/prof_$TAG $SMALL > $OUT/ncu_full_$TAG.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:$KRE -s 3 -c 1 -f -o $OUT/prof_$TAG $SMALL > $OUT/ncu_full_$TAG.log 2>&1
 echo "ncu full rc=$?"
 ls -la $OUT
