@@ -31,6 +31,7 @@ struct DenseCons16 {      // rows: 6 equalities D u = u_des, then u_i >= 0, then
             r.nnz = 1; r.idx[0] = j; r.val[0] = -1.0; r.beta = -ub[j];
         }
     }
+    FT_HD double slack(int p, const double* v, double sb) const { return cons_slack_generic(*this, p, v, sb); }
 };
 
 struct HullCons6 {        // -A_h v >= -b_h
@@ -44,6 +45,7 @@ struct HullCons6 {        // -A_h v >= -b_h
         }
         r.nnz = k; r.beta = -bh[p];
     }
+    FT_HD double slack(int p, const double* v, double sb) const { return cons_slack_generic(*this, p, v, sb); }
 };
 
 // generic tiny QP  min 1/2 h |x - x0|^2  (G = h I)  with the rows of `cons`; NV <= 16, M <= 38

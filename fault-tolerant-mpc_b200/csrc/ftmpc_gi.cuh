@@ -31,6 +31,16 @@ struct SparseRow {
 
 enum { GI_OK = 0, GI_MAXIT = 1, GI_INFEASIBLE = 2 };
 
+// n_p . v - beta_p through the generic row() interface (constraint types with structure override `slack`)
+template <class Cons>
+FT_HD double cons_slack_generic(const Cons& cons, int p, const double* v, double scale_beta) {
+    SparseRow row;
+    cons.row(p, row);
+    double a = -scale_beta * row.beta;
+    for (int k = 0; k < row.nnz; ++k) a += row.val[k] * v[row.idx[k]];
+    return a;
+}
+
 struct GiWork {
     double* E;      // ne x ld
     double* Ui;     // packed upper triangular, capacity nv*(nv+1)/2
@@ -129,11 +139,7 @@ FT_HD int gi_solve(Blk& blk, const Cons& cons, const GiWork& w, int nv, int ne, 
     int q = 0, iters = 0, status = GI_OK;
     // slack of every constraint at the unconstrained minimiser
     for (int i = tid; i < m; i += nt) {
-        SparseRow row;
-        cons.row(i, row);
-        double v = -row.beta;
-        for (int k = 0; k < row.nnz; ++k) v += row.val[k] * w.xe[row.idx[k]];
-        w.s[i] = v;
+        w.s[i] = cons.slack(i, w.xe, 1.0);
         w.pos[i] = -1;
     }
     blk.sync();
@@ -235,13 +241,7 @@ FT_HD int gi_solve(Blk& blk, const Cons& cons, const GiWork& w, int nv, int ne, 
             // primal + dual step
             for (int i = tid; i < ne; i += nt) w.xe[i] += t * w.ze[i];
             for (int j = tid; j <= q; j += nt) w.u[j] += t * ((j < q) ? -w.r[j] : 1.0);
-            for (int i = tid; i < m; i += nt) {
-                SparseRow row;
-                cons.row(i, row);
-                double v = 0.0;
-                for (int k = 0; k < row.nnz; ++k) v += row.val[k] * w.ze[row.idx[k]];
-                w.s[i] += t * v;
-            }
+            for (int i = tid; i < m; i += nt) w.s[i] += t * cons.slack(i, w.ze, 0.0);
             sp += t * d2n;
             blk.sync();
             if (t == t2) {
@@ -285,5 +285,177 @@ FT_HD int gi_solve(Blk& blk, const Cons& cons, const GiWork& w, int nv, int ne, 
     *nact_out = q;
     return status;
 }
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------------------------------------
+// CUDA-block specialisation of gi_solve: identical pivoting rules, five barriers per "add" iteration.
+//   * |d|^2 and |d2|^2 are reduced with warp shuffles while d is produced (no extra block reduction);
+//   * z = E[:, q:] d[q:] runs thread-per-row with four independent accumulators (the dependent-FMA chain of the
+//     straightforward loop is what bounds a 121-long dot product), r = R^-1 d[:q] runs on the threads at the other
+//     end of the block at the same time, and the dual step length falls out of the same barrier (argmin);
+//   * constraint slacks use Cons::slack (no sparse-row materialisation in the sweeps over all m rows).
+// ---------------------------------------------------------------------------------------------------------
+template <class Cons>
+__device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const GiWork& w, int nv, int ne, int ld, int m,
+                                        int meq, double* lam, int maxit, double tol, int* iters_out, int* nact_out) {
+    const int tid = blk.tid(), nt = blk.nthreads(), lane = tid & 31, warp = tid >> 5, nw = (nt + 31) >> 5;
+    double* gsc = blk.scratch + 128;              // 64 doubles of block scratch reserved for this routine
+    int q = 0, iters = 0, status = GI_OK;
+    for (int i = tid; i < m; i += nt) {
+        w.s[i] = cons.slack(i, w.xe, 1.0);
+        w.pos[i] = -1;
+    }
+    blk.sync();
+    int eq_next = 0;
+    for (;;) {
+        // ---- choose the constraint to add: pending equalities first, then the most violated row
+        int p = -1;
+        double sp = 0.0;
+        bool is_eq = false;
+        if (eq_next < meq) {
+            p = eq_next++;
+            sp = w.s[p];
+            is_eq = true;
+        } else {
+            double best = 0.0;
+            int bi = 0x7fffffff;
+            for (int i = meq + tid; i < m; i += nt) {
+                if (w.pos[i] < 0) {
+                    const double v = w.s[i];
+                    if (v < best || (v == best && i < bi)) { best = v; bi = i; }
+                }
+            }
+            blk.argmin(best, bi);
+            if (bi == 0x7fffffff || best >= -tol) break;      // primal feasible -> optimal
+            p = bi;
+            sp = best;
+        }
+        SparseRow np;
+        cons.row(p, np);
+        if (is_eq) {
+            const bool rev = sp > 0.0;
+            if (rev) {
+#pragma unroll
+                for (int k = 0; k < FTMPC_GI_MAXNNZ; ++k) np.val[k] = -np.val[k];
+                sp = -sp;
+            }
+            if (tid == 0) w.esign[p] = rev ? -1.0 : 1.0;
+        }
+        if (tid == 0) w.u[q] = 0.0;
+        bool added = false;
+        while (!added) {
+            ++iters;
+            if (iters > maxit) { status = GI_MAXIT; break; }
+            // d = J' n_p, with the two squared norms reduced on the fly
+            double pa = 0.0, p2 = 0.0;
+            for (int i = tid; i < nv; i += nt) {
+                double v = 0.0;
+#pragma unroll
+                for (int k = 0; k < FTMPC_GI_MAXNNZ; ++k)
+                    if (k < np.nnz) v += np.val[k] * w.E[(size_t)np.idx[k] * ld + i];
+                w.d[i] = v;
+                pa += v * v;
+                if (i >= q) p2 += v * v;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                pa += __shfl_xor_sync(0xffffffffu, pa, o);
+                p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+            }
+            if (lane == 0) { gsc[warp] = pa; gsc[32 + warp] = p2; }
+            blk.sync();
+            double dn = 0.0, d2n = 0.0;
+            for (int i = 0; i < nw; ++i) { dn += gsc[i]; d2n += gsc[32 + i]; }
+            // ze = E[:, q:] d[q:]  (threads from the front)   r = R^-1 d[:q]  (threads from the back)
+            for (int row = tid; row < ne; row += nt) {
+                const double* e = w.E + (size_t)row * ld;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                int k = q;
+                for (; k + 3 < nv; k += 4) {
+                    a0 += e[k] * w.d[k];
+                    a1 += e[k + 1] * w.d[k + 1];
+                    a2 += e[k + 2] * w.d[k + 2];
+                    a3 += e[k + 3] * w.d[k + 3];
+                }
+                for (; k < nv; ++k) a0 += e[k] * w.d[k];
+                w.ze[row] = (a0 + a1) + (a2 + a3);
+            }
+            double t1 = INFINITY;
+            int l = 0x7fffffff;
+            for (int j = nt - 1 - tid; j < q; j += nt) {
+                double a0 = 0.0, a1 = 0.0;
+                int k = j;
+                for (; k + 1 < q; k += 2) {
+                    a0 += w.Ui[gi_tri(k) + j] * w.d[k];
+                    a1 += w.Ui[gi_tri(k + 1) + j] * w.d[k + 1];
+                }
+                if (k < q) a0 += w.Ui[gi_tri(k) + j] * w.d[k];
+                const double rj = a0 + a1;
+                w.r[j] = rj;
+                if (w.act[j] >= meq && rj > 1e-13) {
+                    const double tj = w.u[j] / rj;
+                    if (tj < t1 || (tj == t1 && j < l)) { t1 = tj; l = j; }
+                }
+            }
+            blk.argmin(t1, l);                    // its barrier also publishes ze and r
+            const bool dep = (q >= nv) || (d2n <= 1e-22 * fmax(1.0, dn)) || (d2n <= 1e-28);
+            const double t2 = dep ? INFINITY : (-sp / d2n);
+            const double t = fmin(t1, t2);
+            if (t == INFINITY) {
+                if (is_eq && fabs(sp) <= 1e-9) break;
+                status = GI_INFEASIBLE;
+                break;
+            }
+            if (t2 == INFINITY) {
+                for (int j = tid; j <= q; j += nt) w.u[j] += t * ((j < q) ? -w.r[j] : 1.0);
+                blk.sync();
+                gi_drop(blk, w, nv, ne, ld, q, l);
+                continue;
+            }
+            for (int i = tid; i < ne; i += nt) w.xe[i] += t * w.ze[i];
+            for (int j = tid; j <= q; j += nt) w.u[j] += t * ((j < q) ? -w.r[j] : 1.0);
+            for (int i = tid; i < m; i += nt) w.s[i] += t * cons.slack(i, w.ze, 0.0);
+            sp += t * d2n;
+            blk.sync();
+            if (t == t2) {
+                const double alpha = sqrt(d2n);
+                const double d0 = w.d[q];
+                const double sg = (d0 >= 0.0) ? 1.0 : -1.0;
+                const double vv = 2.0 * alpha * (alpha + fabs(d0));
+                const double rho = -sg * alpha;
+                if (vv > 0.0) {
+                    const double f = 2.0 / vv;
+                    for (int row = tid; row < ne; row += nt) {
+                        double* e = w.E + (size_t)row * ld;
+                        const double wv = f * (w.ze[row] + sg * alpha * e[q]);
+                        e[q] -= wv * (d0 + sg * alpha);
+                        for (int k = q + 1; k < nv; ++k) e[k] -= wv * w.d[k];
+                    }
+                }
+                double* col = w.Ui + gi_tri(q);
+                for (int j = nt - 1 - tid; j < q; j += nt) col[j] = -w.r[j] / rho;
+                if (tid == nt - 1) {
+                    col[q] = 1.0 / rho;
+                    w.act[q] = p;
+                    w.pos[p] = q;
+                }
+                blk.sync();
+                q += 1;
+                added = true;
+            } else {
+                gi_drop(blk, w, nv, ne, ld, q, l);
+            }
+        }
+        if (status != GI_OK) break;
+    }
+    for (int i = tid; i < m; i += nt) lam[i] = 0.0;
+    blk.sync();
+    for (int j = tid; j < q; j += nt) lam[w.act[j]] = (w.act[j] < meq) ? w.esign[w.act[j]] * w.u[j] : w.u[j];
+    blk.sync();
+    *iters_out = iters;
+    *nact_out = q;
+    return status;
+}
+#endif  // __CUDACC__
 
 }  // namespace ftmpc

@@ -45,10 +45,10 @@ struct ftmpc_ctx {
 // -------------------------------------------------------------------------------------------------
 #define FTMPC_QP_THREADS 256
 __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
-    k_solve(const ftmpc_config* __restrict__ cfg, WsLayout L, StepIO io, int* queue, double* gscratch, size_t sdoubles,
+    k_solve(const __grid_constant__ ftmpc_config cfg, WsLayout L, StepIO io, int* queue, double* gscratch, size_t sdoubles,
             long long* prof) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ double red[128];
+    __shared__ double red[192];
     __shared__ int s_inst;
     double* scratch = gscratch ? gscratch + (size_t)blockIdx.x * sdoubles : smem;
     CudaBlock blk(red, prof);
@@ -60,21 +60,21 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
         const int inst = s_inst;
         __syncthreads();
         if (inst >= io.batch) break;
-        phase_ls_block(blk, *cfg, L, io, inst, slot, 1, scratch);
-        for (int it = 0; it < cfg->max_sqp_iter; ++it) {
+        phase_ls_block(blk, cfg, L, io, inst, slot, 1, scratch);
+        for (int it = 0; it < cfg.max_sqp_iter; ++it) {
             if (sc[SC_STATUS] != (double)FTMPC_ST_RUNNING) break;      // uniform: written before the last barrier
-            phase_lin(blk, *cfg, L, io, inst, slot);
-            phase_qp(blk, *cfg, L, io, inst, slot, scratch);
-            phase_ls_block(blk, *cfg, L, io, inst, slot, 0, scratch);
+            phase_lin(blk, cfg, L, io, inst, slot);
+            phase_qp(blk, cfg, L, io, inst, slot, scratch);
+            phase_ls_block(blk, cfg, L, io, inst, slot, 0, scratch);
         }
-        phase_out_write(blk, *cfg, L, io, inst, slot);
+        phase_out_write(blk, cfg, L, io, inst, slot);
     }
 }
 
-__global__ void __launch_bounds__(64) k_alloc(const ftmpc_config* __restrict__ cfg, WsLayout L, StepIO io) {
+__global__ void __launch_bounds__(64) k_alloc(const __grid_constant__ ftmpc_config cfg, WsLayout L, StepIO io) {
     const int inst = blockIdx.x * blockDim.x + threadIdx.x;
     if (inst >= io.batch) return;
-    phase_alloc(*cfg, L, io, inst);
+    phase_alloc(cfg, L, io, inst);
 }
 
 // ---- stage kernels --------------------------------------------------------------------------------
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
                const double* x, const double* u, const double* xref, const double* gradV, const double* hessV,
                double theta, double* H, double* g, double* gscratch, size_t sdoubles) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ double red[128];
+    __shared__ double red[192];
     double* scratch = gscratch ? gscratch + (size_t)blockIdx.x * sdoubles : smem;
     CudaBlock blk(red);
     const int N = L.N, n = L.n, ld = L.nv;
@@ -167,13 +167,14 @@ struct CsrCons {
         r.nnz = k;
         r.beta = -b[p];
     }
+    __device__ __forceinline__ double slack(int p, const double* v, double sb) const { return cons_slack_generic(*this, p, v, sb); }
 };
 
 __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
     k_qp_generic(int batch, int n, int m, const double* H, const double* g, const int32_t* ptr, const int32_t* idx,
                  const double* val, const double* b, double* x, double* lam, int32_t* status, int maxit, double tol) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ double red[128];
+    __shared__ double red[192];
     CudaBlock blk(red);
     const int ld = n | 1, tid = threadIdx.x, nt = blockDim.x;
     double* p = smem;
@@ -389,7 +390,7 @@ int ftmpc_step(ftmpc_handle h, int batch, const double* state, const double* xre
     cudaStream_t stream = (cudaStream_t)stream_;
     const WsLayout L = h->L;
     StepIO io{batch, state, xref, uref, fault_mask, fault_force, hull_idx, h->d_hull, warm, z_warm, thrust, u0,
-              active_set, status, iters, cost, (double*)workspace};
+              active_set, status, iters, cost, h->d_cfg, (double*)workspace};
     const int grid = solve_grid(h, batch);
     const size_t smem = solve_smem_bytes(h->cfg.horizon);
     const bool use_global = smem > h->smem_optin;
@@ -402,10 +403,10 @@ int ftmpc_step(ftmpc_handle h, int batch, const double* state, const double* xre
         CU(cudaMemsetAsync(h->d_prof, 0, PH_COUNT * sizeof(long long), stream));
         CU(cudaEventRecord(h->ev[0], stream));
     }
-    k_solve<<<grid, FTMPC_QP_THREADS, use_global ? 0 : smem, stream>>>(h->d_cfg, L, io, h->d_queue, gscratch, sdoubles,
+    k_solve<<<grid, FTMPC_QP_THREADS, use_global ? 0 : smem, stream>>>(h->cfg, L, io, h->d_queue, gscratch, sdoubles,
                                                                         h->profile ? h->d_prof : nullptr);
     if (h->profile) CU(cudaEventRecord(h->ev[1], stream));
-    k_alloc<<<(batch + 63) / 64, 64, 0, stream>>>(h->d_cfg, L, io);
+    k_alloc<<<(batch + 63) / 64, 64, 0, stream>>>(h->cfg, L, io);
     if (h->profile) CU(cudaEventRecord(h->ev[2], stream));
     h->last_launches = 2;
     CU(cudaGetLastError());

@@ -67,6 +67,8 @@ struct StepIO {
     int32_t* status;            // [B]
     int32_t* iters;             // [B,2]
     double* cost;               // [B]
+    const ftmpc_config* cfg_g;  // copy of the configuration in global memory (tables indexed per thread); the kernels
+                                // also receive it by value as a __grid_constant__ parameter for uniform accesses
     double* ws;                 // workspace: one slot of L.stride doubles per instance (CPU port) or per CTA (k_solve)
 };
 
@@ -248,7 +250,7 @@ __device__ __forceinline__ double rollout_states(const ftmpc_config& cfg, int N,
 }
 
 // value of constraint row p (c <= 0 feasible) from stored stage wrenches / terminal state
-__device__ __forceinline__ double cons_value(const ftmpc_config& cfg, int N, const double* hull, const double* xrefN,
+__device__ __forceinline__ double cons_value(const ftmpc_config& cfg /* global copy: per-thread rows */, int N, const double* hull, const double* xrefN,
                                              const double* Xs, const double* Ws, int p) {
     if (p < FTMPC_NH * N) {
         const int t = p / FTMPC_NH, i = p - t * FTMPC_NH;
@@ -315,7 +317,7 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
     {
         double cs = 0.0, cm = 0.0;
         for (int p = tid; p < L.mc; p += nt) {
-            const double v = cons_value(cfg, N, s.hull, xref + N * FTMPC_NE, s.Xs, s.Ws, p);
+            const double v = cons_value(*io.cfg_g, N, s.hull, xref + N * FTMPC_NE, s.Xs, s.Ws, p);
             C[p] = v;
             if (v > 0.0) { cs += v; cm = fmax(cm, v); }
         }
@@ -334,7 +336,7 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
             const double* Wa = s.Ws + (size_t)a * s.ws_stride;
             double cs = 0.0, cm = 0.0;
             for (int p = lane; p < L.mc; p += 32) {
-                const double v = cons_value(cfg, N, s.hull, xref + N * FTMPC_NE, Xa, Wa, p);
+                const double v = cons_value(*io.cfg_g, N, s.hull, xref + N * FTMPC_NE, Xa, Wa, p);
                 if (v > 0.0) { cs += v; cm = fmax(cm, v); }
             }
             for (int o = 16; o > 0; o >>= 1) {
@@ -354,7 +356,7 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
         }
         const double* Xa = s.Xs + (size_t)win * s.xs_stride;
         const double* Wa = s.Ws + (size_t)win * s.ws_stride;
-        for (int p = tid; p < L.mc; p += nt) C[p] = cons_value(cfg, N, s.hull, xref + N * FTMPC_NE, Xa, Wa, p);
+        for (int p = tid; p < L.mc; p += nt) C[p] = cons_value(*io.cfg_g, N, s.hull, xref + N * FTMPC_NE, Xa, Wa, p);
     }
     // C. commit
     const double alpha = first ? 0.0 : ldexp(1.0, -win);
@@ -460,31 +462,49 @@ struct MpcCons {
     const double* Ah;       // [26][6]
     const double* Af;       // [72][9]
     const double* cv;       // [mc] constraint values at the linearisation point
+    // fixed layout (zeros kept) so that the row stays in registers: hull rows 6 + 1 entries, terminal rows 9 + 1
     FT_HD void row(int p, SparseRow& r) const {
-        int k = 0;
         if (p < FTMPC_NH * N) {
-            const int t = p / FTMPC_NH, i = p % FTMPC_NH;
-            for (int j = 0; j < FTMPC_NU; ++j) {
-                const double a = Ah[i * FTMPC_NU + j];
-                if (a != 0.0) { r.idx[k] = t * FTMPC_NU + j; r.val[k] = -a; ++k; }
-            }
+            const int t = p / FTMPC_NH, i = p - t * FTMPC_NH;
+            for (int j = 0; j < FTMPC_NU; ++j) { r.idx[j] = t * FTMPC_NU + j; r.val[j] = -Ah[i * FTMPC_NU + j]; }
+            const double c = cv[p];
+            r.idx[FTMPC_NU] = n; r.val[FTMPC_NU] = (c > 0.0) ? c : 0.0;
+            r.nnz = FTMPC_NU + 1;
+            r.beta = c;
         } else if (p < mc) {
             const int i = p - FTMPC_NH * N;
-            for (int j = 0; j < FTMPC_NE; ++j) {
-                const double a = Af[i * FTMPC_NE + j];
-                if (a != 0.0) { r.idx[k] = nv + j; r.val[k] = -a; ++k; }
-            }
+            for (int j = 0; j < FTMPC_NE; ++j) { r.idx[j] = nv + j; r.val[j] = -Af[i * FTMPC_NE + j]; }
+            const double c = cv[p];
+            r.idx[FTMPC_NE] = n; r.val[FTMPC_NE] = (c > 0.0) ? c : 0.0;
+            r.nnz = FTMPC_NE + 1;
+            r.beta = c;
         } else if (p == mc) {          // delta >= 0
             r.idx[0] = n; r.val[0] = 1.0; r.nnz = 1; r.beta = 0.0;
-            return;
         } else {                       // delta <= 1
             r.idx[0] = n; r.val[0] = -1.0; r.nnz = 1; r.beta = -1.0;
-            return;
         }
-        const double c = cv[p];
-        if (c > 0.0) { r.idx[k] = n; r.val[k] = c; ++k; }
-        r.nnz = k;
-        r.beta = c;
+    }
+    // n_p . v - sb * beta_p without materialising the sparse row (v in extended coordinates [d ; delta ; dx_N])
+    FT_HD double slack(int p, const double* v, double sb) const {
+        if (p < FTMPC_NH * N) {
+            const int t = p / FTMPC_NH, i = p - t * FTMPC_NH;
+            const double* a = Ah + i * FTMPC_NU;
+            const double* x = v + t * FTMPC_NU;
+            const double c = cv[p];
+            double s = -sb * c;
+            for (int j = 0; j < FTMPC_NU; ++j) s -= a[j] * x[j];
+            if (c > 0.0) s += c * v[n];
+            return s;
+        }
+        if (p < mc) {
+            const double* a = Af + (p - FTMPC_NH * N) * FTMPC_NE;
+            const double c = cv[p];
+            double s = -sb * c;
+            for (int j = 0; j < FTMPC_NE; ++j) s -= a[j] * v[nv + j];
+            if (c > 0.0) s += c * v[n];
+            return s;
+        }
+        return (p == mc) ? v[n] : (sb - v[n]);
     }
 };
 
@@ -760,7 +780,7 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         s.gi.xe[row] = -v;
     }
     blk.sync();
-    MpcCons cons{N, n, nv, L.mc, s.hull, cfg.Af, s.cv};
+    MpcCons cons{N, n, nv, L.mc, s.hull, io.cfg_g->Af, s.cv};
     blk.mark(PH_QPSETUP);
     int qit1 = 0;
     // the previous multipliers are still needed if this attempt is rejected: the QP writes to the spare copy

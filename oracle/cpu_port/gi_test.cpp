@@ -12,6 +12,7 @@ struct CsrCons {
         for (int k = 0; k < r.nnz; ++k) { r.idx[k] = idx[ptr[p] + k]; r.val[k] = val[ptr[p] + k]; }
         r.beta = beta[p];
     }
+    inline double slack(int p, const double* v, double sb) const { return cons_slack_generic(*this, p, v, sb); }
 };
 
 // min 1/2 x'Gx + a'x  s.t. rows (CSR, <=12 nnz each): n_i'x >= beta_i ; first meq are equalities
