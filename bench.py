@@ -324,7 +324,8 @@ def main():
                 "flops_model": "SURVEY.md 8d: K_sqp(F_lin+F_cond+F_chol)+K_qp F_iter+F_alloc with the kernel's own iteration counters",
                 "algorithmic_flops_per_launch": solve_flops, "kernel_ms": kernel_ms,
                 "kernel_share_of_step": kernel_ms["k_solve"] / (ms_total / a.steps),
-                "phase_share": {n: float(c / cyc.sum()) for n, c in zip(L.PHASE_NAMES, cyc)} if cyc.sum() > 0 else None,
+                "phase_share": {n: round(float(c / cyc[:L.N_CYCLE_PHASES].sum()), 4) for n, c in zip(L.PHASE_NAMES[:L.N_CYCLE_PHASES], cyc)} if cyc.sum() > 0 else None,
+                "phase_counters": {n: int(c) for n, c in zip(L.PHASE_NAMES[L.N_CYCLE_PHASES:], cyc[L.N_CYCLE_PHASES:])},
                 "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                         "algorithmic_bytes_per_solve": algorithmic_bytes(N),
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"}}

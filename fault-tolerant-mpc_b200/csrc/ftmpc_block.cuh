@@ -35,10 +35,17 @@ struct SerialBlock {
     FT_HD void argmin(double& v, int& idx) { (void)v; (void)idx; }
     FT_HD int any(int pred) { return pred; }
     FT_HD void mark(int) {}
+    FT_HD void count(int, int = 1) {}
 };
 
 // phase ids of the in-kernel cycle profile (ftmpc_profile_read)
-enum { PH_LS = 0, PH_LIN, PH_COND, PH_CHOL, PH_INV, PH_QPSETUP, PH_GI, PH_POST, PH_OUT, PH_COUNT };
+enum { PH_LS = 0, PH_LIN, PH_COND, PH_CHOL, PH_INV, PH_QPSETUP, PH_GI, PH_POST, PH_OUT,
+       // finer attribution inside the phases above (the coarse ids then only receive the remainder)
+       PH_LS_ROLL, PH_LS_EVAL, PH_LS_TERM, PH_CHOL_PANEL, PH_CHOL_SYRK, PH_GI_SELECT, PH_GI_D, PH_GI_Z, PH_GI_STEP, PH_GI_UPD,
+       PH_GI_DROP, PH_LIN_JAC, PH_LIN_MU,
+       // event counters (not cycles)
+       CT_INST, CT_SQP, CT_CONDENSE, CT_CHOL_FAIL, CT_QP, CT_GI_ITER, CT_GI_DROP, CT_LS_BACKTRACK,
+       PH_COUNT };
 
 #if defined(__CUDACC__)
 // scratch: >= 2 * 32 * 2 doubles of shared memory (double-buffered so one barrier per reduction suffices)
@@ -57,6 +64,9 @@ struct CudaBlock {
             atomicAdd(reinterpret_cast<unsigned long long*>(prof + id), (unsigned long long)(t - t_last));
             t_last = t;
         }
+    }
+    __device__ __forceinline__ void count(int id, int n = 1) {
+        if (prof && threadIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(prof + id), (unsigned long long)n);
     }
     __device__ __forceinline__ int tid() const { return threadIdx.x; }
     __device__ __forceinline__ int nthreads() const { return blockDim.x; }

@@ -287,6 +287,36 @@ FT_HD int gi_solve(Blk& blk, const Cons& cons, const GiWork& w, int nv, int ne, 
 }
 
 #if defined(__CUDACC__)
+// Register-blocked row kernels.  A CTA runs 8 warps (2 per scheduler), so a dependent load -> FMA -> store chain
+// is bound by latency; these load eight operands of each stream before touching them.
+__device__ __forceinline__ double dot_ilp(const double* __restrict__ a, const double* __restrict__ b, int k0, int k1) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int k = k0;
+    for (; k + 7 < k1; k += 8) {
+        double x[8], y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { x[j] = a[k + j]; y[j] = b[k + j]; }
+        s0 += x[0] * y[0]; s1 += x[1] * y[1]; s2 += x[2] * y[2]; s3 += x[3] * y[3];
+        s0 += x[4] * y[4]; s1 += x[5] * y[5]; s2 += x[6] * y[6]; s3 += x[7] * y[7];
+    }
+    for (; k < k1; ++k) s0 += a[k] * b[k];
+    return (s0 + s1) + (s2 + s3);
+}
+// e[k] -= wv * d[k], k in [k0, k1)
+__device__ __forceinline__ void axpy_ilp(double* __restrict__ e, const double* __restrict__ d, double wv, int k0, int k1) {
+    int k = k0;
+    for (; k + 7 < k1; k += 8) {
+        double x[8], y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { x[j] = e[k + j]; y[j] = d[k + j]; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[k + j] = x[j] - wv * y[j];
+    }
+    for (; k < k1; ++k) e[k] -= wv * d[k];
+}
+#endif
+
+#if defined(__CUDACC__)
 // ---------------------------------------------------------------------------------------------------------
 // CUDA-block specialisation of gi_solve: identical pivoting rules, five barriers per "add" iteration.
 //   * |d|^2 and |d2|^2 are reduced with warp shuffles while d is produced (no extra block reduction);
@@ -330,6 +360,7 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
             p = bi;
             sp = best;
         }
+        blk.mark(PH_GI_SELECT);
         SparseRow np;
         cons.row(p, np);
         if (is_eq) {
@@ -364,21 +395,12 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
             }
             if (lane == 0) { gsc[warp] = pa; gsc[32 + warp] = p2; }
             blk.sync();
+            blk.mark(PH_GI_D);
             double dn = 0.0, d2n = 0.0;
             for (int i = 0; i < nw; ++i) { dn += gsc[i]; d2n += gsc[32 + i]; }
             // ze = E[:, q:] d[q:]  (threads from the front)   r = R^-1 d[:q]  (threads from the back)
             for (int row = tid; row < ne; row += nt) {
-                const double* e = w.E + (size_t)row * ld;
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                int k = q;
-                for (; k + 3 < nv; k += 4) {
-                    a0 += e[k] * w.d[k];
-                    a1 += e[k + 1] * w.d[k + 1];
-                    a2 += e[k + 2] * w.d[k + 2];
-                    a3 += e[k + 3] * w.d[k + 3];
-                }
-                for (; k < nv; ++k) a0 += e[k] * w.d[k];
-                w.ze[row] = (a0 + a1) + (a2 + a3);
+                w.ze[row] = dot_ilp(w.E + (size_t)row * ld, w.d, q, nv);
             }
             double t1 = INFINITY;
             int l = 0x7fffffff;
@@ -398,6 +420,7 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
                 }
             }
             blk.argmin(t1, l);                    // its barrier also publishes ze and r
+            blk.mark(PH_GI_Z);
             const bool dep = (q >= nv) || (d2n <= 1e-22 * fmax(1.0, dn)) || (d2n <= 1e-28);
             const double t2 = dep ? INFINITY : (-sp / d2n);
             const double t = fmin(t1, t2);
@@ -410,6 +433,8 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
                 for (int j = tid; j <= q; j += nt) w.u[j] += t * ((j < q) ? -w.r[j] : 1.0);
                 blk.sync();
                 gi_drop(blk, w, nv, ne, ld, q, l);
+                blk.mark(PH_GI_DROP);
+                blk.count(CT_GI_DROP);
                 continue;
             }
             for (int i = tid; i < ne; i += nt) w.xe[i] += t * w.ze[i];
@@ -417,6 +442,7 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
             for (int i = tid; i < m; i += nt) w.s[i] += t * cons.slack(i, w.ze, 0.0);
             sp += t * d2n;
             blk.sync();
+            blk.mark(PH_GI_STEP);
             if (t == t2) {
                 const double alpha = sqrt(d2n);
                 const double d0 = w.d[q];
@@ -429,7 +455,7 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
                         double* e = w.E + (size_t)row * ld;
                         const double wv = f * (w.ze[row] + sg * alpha * e[q]);
                         e[q] -= wv * (d0 + sg * alpha);
-                        for (int k = q + 1; k < nv; ++k) e[k] -= wv * w.d[k];
+                        axpy_ilp(e, w.d, wv, q + 1, nv);
                     }
                 }
                 double* col = w.Ui + gi_tri(q);
@@ -440,10 +466,13 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
                     w.pos[p] = q;
                 }
                 blk.sync();
+                blk.mark(PH_GI_UPD);
                 q += 1;
                 added = true;
             } else {
                 gi_drop(blk, w, nv, ne, ld, q, l);
+                blk.mark(PH_GI_DROP);
+                blk.count(CT_GI_DROP);
             }
         }
         if (status != GI_OK) break;
@@ -452,6 +481,7 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
     blk.sync();
     for (int j = tid; j < q; j += nt) lam[w.act[j]] = (w.act[j] < meq) ? w.esign[w.act[j]] * w.u[j] : w.u[j];
     blk.sync();
+    blk.count(CT_GI_ITER, iters);
     *iters_out = iters;
     *nact_out = q;
     return status;

@@ -121,6 +121,7 @@ __device__ __forceinline__ int chol_lower(CudaBlock& blk, int n, int ld, double*
             }
         }
         blk.sync();
+        blk.mark(PH_CHOL_PANEL);
         // the factored diagonal block is stored only now: slower warps may still have been reading it above
         if (tid < nb) {
             double* ar = A + (size_t)(c0 + tid) * ld + c0;
@@ -178,6 +179,7 @@ __device__ __forceinline__ int chol_lower(CudaBlock& blk, int n, int ld, double*
             }
         }
         blk.sync();
+        blk.mark(PH_CHOL_SYRK);
     }
     return 0;
 }

@@ -203,9 +203,14 @@ FT_HD void phase_ls(const ftmpc_config& cfg, const WsLayout& L, const StepIO& io
 //   C. the first step length passing the Armijo test is committed.
 #define FTMPC_LS_NALPHA 28
 struct LsScratch {
-    double *Xs, *Ws, *fa, *csa, *cma, *hull;
+    double *Xs, *Ws, *fa, *csa, *cma, *hull, *U, *D, *xref, *uref, *rec, *out;
     int xs_stride, ws_stride;
 };
+__host__ __device__ inline size_t ls_scratch_doubles(int N) {
+    return (size_t)FTMPC_LS_NALPHA * ((N + 1) * FTMPC_NX + 1 + N * FTMPC_NU + 1) + 96 + FTMPC_HULL_STRIDE +
+           2 * (size_t)(FTMPC_NU * N + 1) + (size_t)(N + 1) * (FTMPC_NE + FTMPC_NU) +
+           (size_t)(FTMPC_MAX_POLY + FTMPC_MAX_ROOT) * FTMPC_TERM_REC + FTMPC_TERM_REC + 8;
+}
 __device__ __forceinline__ LsScratch ls_carve(double* buf, int N) {
     LsScratch s;
     s.xs_stride = (N + 1) * FTMPC_NX + 1;          // odd strides: lanes of warp 0 hit different banks
@@ -217,50 +222,58 @@ __device__ __forceinline__ LsScratch ls_carve(double* buf, int N) {
     s.csa = p; p += 32;
     s.cma = p; p += 32;
     s.hull = p; p += FTMPC_HULL_STRIDE;
+    s.U = p; p += FTMPC_NU * N + 1;
+    s.D = p; p += FTMPC_NU * N + 1;
+    s.xref = p; p += (size_t)(N + 1) * FTMPC_NE;
+    s.uref = p; p += (size_t)(N + 1) * FTMPC_NU;
+    s.rec = p; p += (size_t)(FTMPC_MAX_POLY + FTMPC_MAX_ROOT) * FTMPC_TERM_REC;
+    s.out = p; p += FTMPC_TERM_REC;
     return s;
 }
-__host__ __device__ inline size_t ls_scratch_doubles(int N) {
-    return (size_t)FTMPC_LS_NALPHA * ((N + 1) * FTMPC_NX + 1 + N * FTMPC_NU + 1) + 96 + FTMPC_HULL_STRIDE;
-}
 
-// forward rollout at U + alpha d: states -> Xs, stage wrenches -> Ws, returns the objective
-__device__ __forceinline__ double rollout_states(const ftmpc_config& cfg, int N, const double* __restrict__ xref,
-                                                 const double* __restrict__ uref, const double* __restrict__ U,
-                                                 const double* __restrict__ d, double alpha, const double* x0,
-                                                 double* Xs, double* Ws) {
+// forward rollout at U + alpha d (all operands in shared memory): states -> Xs, stage wrenches -> Ws,
+// returns the running cost (the terminal cost is added term-parallel afterwards)
+__device__ __noinline__ double rollout_states(const ftmpc_config& cfg, int N, const double* xref, const double* uref,
+                                              const double* U, const double* d, double alpha, const double* x0,
+                                              double* Xs, double* Ws) {
     const DynConsts k = dyn_consts(cfg);
     double x[FTMPC_NX], xn[FTMPC_NX], u[FTMPC_NU], Wr[FTMPC_NU];
+#pragma unroll
     for (int i = 0; i < FTMPC_NX; ++i) { x[i] = x0[i]; Xs[i] = x[i]; }
     double f = 0.0;
     for (int t = 0; t < N; ++t) {
+#pragma unroll
         for (int j = 0; j < FTMPC_NU; ++j) u[j] = U[t * FTMPC_NU + j] + alpha * d[t * FTMPC_NU + j];
         stage_wrench(cfg, u, uref ? uref + t * FTMPC_NU : nullptr, x + 9, Wr);
+#pragma unroll
         for (int j = 0; j < FTMPC_NE; ++j) {
             const double e = x[j] - xref[t * FTMPC_NE + j];
             f += cfg.Q[j] * e * e;
         }
+#pragma unroll
         for (int j = 0; j < FTMPC_NU; ++j) { f += cfg.R[j] * u[j] * u[j]; Ws[t * FTMPC_NU + j] = Wr[j]; }
         rk4_step(k, x, Wr, xn);
+#pragma unroll
         for (int i = 0; i < FTMPC_NX; ++i) { x[i] = xn[i]; Xs[(t + 1) * FTMPC_NX + i] = xn[i]; }
     }
-    double e[FTMPC_NE];
-    for (int j = 0; j < FTMPC_NE; ++j) e[j] = x[j] - xref[N * FTMPC_NE + j];
-    f += terminal_value(cfg, e);
     return f;
 }
 
 // value of constraint row p (c <= 0 feasible) from stored stage wrenches / terminal state
-__device__ __forceinline__ double cons_value(const ftmpc_config& cfg /* global copy: per-thread rows */, int N, const double* hull, const double* xrefN,
-                                             const double* Xs, const double* Ws, int p) {
+__device__ __forceinline__ double cons_value(const ftmpc_config& cg /* global copy: per-thread rows */, int N,
+                                             const double* hull, const double* xrefN, const double* Xs,
+                                             const double* Ws, int p) {
     if (p < FTMPC_NH * N) {
         const int t = p / FTMPC_NH, i = p - t * FTMPC_NH;
         double v = -hull[FTMPC_NH * FTMPC_NU + i];
+#pragma unroll
         for (int j = 0; j < FTMPC_NU; ++j) v += hull[i * FTMPC_NU + j] * Ws[t * FTMPC_NU + j];
         return v;
     }
     const int i = p - FTMPC_NH * N;
-    double v = -cfg.bf[i];
-    for (int j = 0; j < FTMPC_NE; ++j) v += cfg.Af[i * FTMPC_NE + j] * (Xs[N * FTMPC_NX + j] - xrefN[j]);
+    double v = -cg.bf[i];
+#pragma unroll
+    for (int j = 0; j < FTMPC_NE; ++j) v += cg.Af[i * FTMPC_NE + j] * (Xs[N * FTMPC_NX + j] - xrefN[j]);
     return v;
 }
 
@@ -269,21 +282,24 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
     double* w = ws_slot(io, L, slot);
     double* sc = w + L.oSc;
     const int N = L.N, tid = blk.tid(), nt = blk.nthreads(), lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-    const double* xref = io.xref + (size_t)inst * (N + 1) * FTMPC_NE;
-    const double* uref = io.uref ? io.uref + (size_t)inst * (N + 1) * FTMPC_NU : nullptr;
+    const double* xref_g = io.xref + (size_t)inst * (N + 1) * FTMPC_NE;
+    const double* uref_g = io.uref ? io.uref + (size_t)inst * (N + 1) * FTMPC_NU : nullptr;
     const double* hull_g = io.hull_table + (size_t)io.hull_idx[inst] * FTMPC_HULL_STRIDE;
+    const ftmpc_config& cg = *io.cfg_g;
     double* U = w + L.oU;
     double* D = w + L.oD;
     double* X = w + L.oX;
     double* C = w + L.oC;
     const LsScratch s = ls_carve(scratch, N);
+    const int nterm = cfg.n_poly + cfg.n_root;
     double nu = 1.0, phi0 = 0.0, dphi = 0.0, dmax = 0.0, iter = 0.0;
     if (first) {
         if (tid == 0) robot_to_center(dyn_consts(cfg), io.state + (size_t)inst * FTMPC_NX, X);      // spiraling_mpc.py:290
         const double* zw = io.z_warm + (size_t)inst * (L.n + (size_t)(N + 1) * FTMPC_NX);
         for (int i = tid; i < L.n; i += nt) {                                                       // warm start shift, :324-331
             const int t = i / FTMPC_NU;
-            U[i] = (io.warm && t + 1 < N) ? zw[i + FTMPC_NU] : 0.0;
+            const double v = (io.warm && t + 1 < N) ? zw[i + FTMPC_NU] : 0.0;
+            U[i] = v; s.U[i] = v; s.D[i] = 0.0;
         }
         for (int i = tid; i < L.nv; i += nt) D[i] = 0.0;
         for (int i = tid; i < L.m; i += nt) w[L.oLam + i] = 0.0;
@@ -301,70 +317,126 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
             blk.sync();
             return;
         }
+        for (int i = tid; i < L.n; i += nt) { s.U[i] = U[i]; s.D[i] = D[i]; }
     }
     for (int i = tid; i < FTMPC_HULL_STRIDE; i += nt) s.hull[i] = hull_g[i];
+    for (int i = tid; i < (N + 1) * FTMPC_NE; i += nt) s.xref[i] = xref_g[i];
+    if (uref_g) for (int i = tid; i < (N + 1) * FTMPC_NU; i += nt) s.uref[i] = uref_g[i];
     blk.sync();
+    const double* xrefN = s.xref + N * FTMPC_NE;
     // A. rollouts, one step length per lane
     const int nalpha = first ? 1 : FTMPC_LS_NALPHA;
     if (warp == 0 && lane < nalpha) {
         const double alpha = first ? 0.0 : ldexp(1.0, -lane);
-        s.fa[lane] = rollout_states(cfg, N, xref, uref, U, D, alpha, X, s.Xs + (size_t)lane * s.xs_stride,
-                                    s.Ws + (size_t)lane * s.ws_stride);
+        s.fa[lane] = rollout_states(cfg, N, s.xref, uref_g ? s.uref : nullptr, s.U, s.D, alpha, X,
+                                    s.Xs + (size_t)lane * s.xs_stride, s.Ws + (size_t)lane * s.ws_stride);
     }
     blk.sync();
-    // B0. alpha index 0 by the whole block; the constraint values go straight to C
+    blk.mark(PH_LS_ROLL);
+    // B0. alpha index 0: constraint rows by the whole block (straight into C), terminal cost with its
+    //     gradient / Hessian records one term per thread (alpha = 1 is accepted most of the time)
     int win = -1;
     {
+        if (tid < nterm) {
+            double e[FTMPC_NE];
+#pragma unroll
+            for (int j = 0; j < FTMPC_NE; ++j) e[j] = s.Xs[N * FTMPC_NX + j] - xrefN[j];
+            double* rec = s.rec + (size_t)tid * FTMPC_TERM_REC;
+            for (int i = 0; i < FTMPC_TERM_REC; ++i) rec[i] = 0.0;
+            term_eval(term_desc(cg, tid), e, rec);
+        }
         double cs = 0.0, cm = 0.0;
         for (int p = tid; p < L.mc; p += nt) {
-            const double v = cons_value(*io.cfg_g, N, s.hull, xref + N * FTMPC_NE, s.Xs, s.Ws, p);
+            const double v = cons_value(cg, N, s.hull, xrefN, s.Xs, s.Ws, p);
             C[p] = v;
             if (v > 0.0) { cs += v; cm = fmax(cm, v); }
         }
-        cs = blk.sum(cs);
+        cs = blk.sum(cs);                             // barrier: the term records are complete
         cm = blk.max(cm);
-        double f = s.fa[0];
+        if (tid < FTMPC_TERM_REC) {
+            double v = 0.0;
+            for (int k = 0; k < nterm; ++k) v += s.rec[(size_t)k * FTMPC_TERM_REC + tid];
+            s.out[tid] = v;
+        }
+        blk.sync();
+        double f = s.fa[0] + cfg.term_const + s.out[0];
         if (!(f == f) || !(cs == cs)) { f = INFINITY; cs = INFINITY; }
+        blk.sync();                                   // everybody has read fa[0] before it is overwritten
         if (tid == 0) { s.fa[0] = f; s.csa[0] = cs; s.cma[0] = cm; }
         if (first || f + nu * cs <= phi0 + 1e-4 * dphi) win = 0;
     }
     blk.sync();
     if (win < 0) {
-        // B1. the remaining step lengths, one warp per alpha
+        // B1. the remaining step lengths: rows one warp per alpha, terminal cost one thread per (alpha, term)
+        for (int idx = tid; idx < (nalpha - 1) * nterm; idx += nt) {
+            const int a = 1 + idx / nterm, k = idx - (a - 1) * nterm;
+            const double* Xa = s.Xs + (size_t)a * s.xs_stride;
+            double e[FTMPC_NE];
+#pragma unroll
+            for (int j = 0; j < FTMPC_NE; ++j) e[j] = Xa[N * FTMPC_NX + j] - xrefN[j];
+            s.rec[(size_t)a * (FTMPC_MAX_POLY + FTMPC_MAX_ROOT) + k] = term_eval(term_desc(cg, k), e, nullptr);
+        }
         for (int a = 1 + warp; a < nalpha; a += nw) {
             const double* Xa = s.Xs + (size_t)a * s.xs_stride;
             const double* Wa = s.Ws + (size_t)a * s.ws_stride;
             double cs = 0.0, cm = 0.0;
             for (int p = lane; p < L.mc; p += 32) {
-                const double v = cons_value(*io.cfg_g, N, s.hull, xref + N * FTMPC_NE, Xa, Wa, p);
+                const double v = cons_value(cg, N, s.hull, xrefN, Xa, Wa, p);
                 if (v > 0.0) { cs += v; cm = fmax(cm, v); }
             }
             for (int o = 16; o > 0; o >>= 1) {
                 cs += __shfl_xor_sync(0xffffffffu, cs, o);
                 cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, o));
             }
-            if (lane == 0) {
-                double f = s.fa[a];
-                if (!(f == f) || !(cs == cs)) { f = INFINITY; cs = INFINITY; }
-                s.fa[a] = f; s.csa[a] = cs; s.cma[a] = cm;
-            }
+            if (lane == 0) { s.csa[a] = cs; s.cma[a] = cm; }
+        }
+        blk.sync();
+        if (tid >= 1 && tid < nalpha) {
+            double v = 0.0;
+            for (int k = 0; k < nterm; ++k) v += s.rec[(size_t)tid * (FTMPC_MAX_POLY + FTMPC_MAX_ROOT) + k];
+            double f = s.fa[tid] + cfg.term_const + v, cs = s.csa[tid];
+            if (!(f == f) || !(cs == cs)) { f = INFINITY; cs = INFINITY; }
+            s.fa[tid] = f; s.csa[tid] = cs;
         }
         blk.sync();
         for (int a = 1; a < nalpha && win < 0; ++a) {
             const double alpha = ldexp(1.0, -a);
             if (s.fa[a] + nu * s.csa[a] <= phi0 + 1e-4 * alpha * dphi || alpha < 1e-8) win = a;
         }
+        // constraint values and terminal records of the accepted step
         const double* Xa = s.Xs + (size_t)win * s.xs_stride;
         const double* Wa = s.Ws + (size_t)win * s.ws_stride;
-        for (int p = tid; p < L.mc; p += nt) C[p] = cons_value(*io.cfg_g, N, s.hull, xref + N * FTMPC_NE, Xa, Wa, p);
+        blk.sync();                                   // the per-alpha term values have been consumed
+        for (int p = tid; p < L.mc; p += nt) C[p] = cons_value(cg, N, s.hull, xrefN, Xa, Wa, p);
+        if (tid < nterm) {
+            double e[FTMPC_NE];
+#pragma unroll
+            for (int j = 0; j < FTMPC_NE; ++j) e[j] = Xa[N * FTMPC_NX + j] - xrefN[j];
+            double* rec = s.rec + (size_t)tid * FTMPC_TERM_REC;
+            for (int i = 0; i < FTMPC_TERM_REC; ++i) rec[i] = 0.0;
+            term_eval(term_desc(cg, tid), e, rec);
+        }
+        blk.sync();
+        if (tid < FTMPC_TERM_REC) {
+            double v = 0.0;
+            for (int k = 0; k < nterm; ++k) v += s.rec[(size_t)k * FTMPC_TERM_REC + tid];
+            s.out[tid] = v;
+        }
+        blk.sync();
     }
+    blk.mark(PH_LS_EVAL);
+    if (win > 0) blk.count(CT_LS_BACKTRACK);
     // C. commit
     const double alpha = first ? 0.0 : ldexp(1.0, -win);
     const double f = s.fa[win], csum = s.csa[win], cmax = s.cma[win];
     const bool finite = f < INFINITY;
-    if (!first && finite) for (int i = tid; i < L.n; i += nt) U[i] += alpha * D[i];
+    if (!first && finite) for (int i = tid; i < L.n; i += nt) U[i] = s.U[i] + alpha * s.D[i];
     const double* Xa = s.Xs + (size_t)win * s.xs_stride;
     if (finite) for (int i = tid; i < (N + 1) * FTMPC_NX; i += nt) X[i] = Xa[i];
+    if (finite || first) {                            // terminal gradient / Hessian at the accepted point
+        for (int i = tid; i < FTMPC_NE; i += nt) w[L.oGV + i] = s.out[1 + i];
+        for (int i = tid; i < FTMPC_NE * FTMPC_NE; i += nt) w[L.oHV + i] = s.out[10 + i];
+    }
     if (tid == 0) {
         if (first) {
             for (int i = 0; i < SC_COUNT; ++i) sc[i] = 0.0;
@@ -379,17 +451,28 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
             else if (dmax <= cfg.sqp_tol) sc[SC_STATUS] = (cmax <= cfg.feas_tol) ? FTMPC_ST_OK : FTMPC_ST_INFEASIBLE;
             else if (iter >= cfg.max_sqp_iter) sc[SC_STATUS] = FTMPC_ST_MAXITER;
         }
-        if (finite || first) {
-            sc[SC_F] = f; sc[SC_CSUM] = csum; sc[SC_CMAX] = cmax;
-            double e[FTMPC_NE];
-            for (int j = 0; j < FTMPC_NE; ++j) e[j] = Xa[N * FTMPC_NX + j] - xref[N * FTMPC_NE + j];
-            terminal_eval(cfg, e, w + L.oGV, w + L.oHV);
-        }
+        if (finite || first) { sc[SC_F] = f; sc[SC_CSUM] = csum; sc[SC_CMAX] = cmax; }
     }
     blk.sync();
-    blk.mark(PH_LS);
+    blk.mark(PH_LS_TERM);
+    blk.count(first ? CT_INST : CT_SQP);
 }
 #endif  // __CUDACC__
+
+// On the device the (stage, column) sweep is kept out of line: inside the persistent kernel it would otherwise
+// inherit the register pressure of everything around it and spill (local memory is L2-latency here, the
+// shared-memory carve-out leaves almost no L1).
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ void rk4_column_call(const DynConsts& k, const double* x, const double* Wr, int col, const double* lam,
+                                             double* jac_col, double* hess_col) {
+    rk4_column(k, x, Wr, col, lam, jac_col, hess_col);
+}
+#else
+FT_HD void rk4_column_call(const DynConsts& k, const double* x, const double* Wr, int col, const double* lam,
+                           double* jac_col, double* hess_col) {
+    rk4_column(k, x, Wr, col, lam, jac_col, hess_col);
+}
+#endif
 
 // ---- phase_lin: Jacobians, costates, stage Hessians (lanes of one warp / a serial loop) -------------
 template <class Blk>
@@ -413,10 +496,11 @@ FT_HD void phase_lin(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const
         double Wr[FTMPC_NU];
         stage_wrench(cfg, U + t * FTMPC_NU, uref ? uref + t * FTMPC_NU : nullptr, X + t * FTMPC_NX + 9, Wr);
         double jc[13];
-        rk4_column(k, X + t * FTMPC_NX, Wr, col, nullptr, jc, nullptr);
+        rk4_column_call(k, X + t * FTMPC_NX, Wr, col, nullptr, jc, nullptr);
         for (int i = 0; i < 13; ++i) Jz[(size_t)it * 13 + i] = jc[i];
     }
     blk.sync();
+    blk.mark(PH_LIN_JAC);
     // costates  mu_N = [grad V_f + A_f' lam_term ; 0],  mu_t = [2Q e_t ; 0] + A_t' mu_{t+1}
     for (int i = tid; i < FTMPC_NX; i += nt) {
         double v = 0.0;
@@ -441,13 +525,14 @@ FT_HD void phase_lin(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const
         }
         blk.sync();
     }
+    blk.mark(PH_LIN_MU);
     // second-order columns: Hessian of mu_{t+1}' RK4(x_t, W_t) in z-space
     for (int it = tid; it < N * 13; it += nt) {
         const int t = it / 13, col = it % 13;
         double Wr[FTMPC_NU];
         stage_wrench(cfg, U + t * FTMPC_NU, uref ? uref + t * FTMPC_NU : nullptr, X + t * FTMPC_NX + 9, Wr);
         double jc[13], hc[13];
-        rk4_column(k, X + t * FTMPC_NX, Wr, col, Mu + (t + 1) * FTMPC_NX, jc, hc);
+        rk4_column_call(k, X + t * FTMPC_NX, Wr, col, Mu + (t + 1) * FTMPC_NX, jc, hc);
         for (int i = 0; i < 13; ++i) Wz[(size_t)it * 13 + i] = hc[i];
     }
     blk.sync();
@@ -739,12 +824,14 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     for (;;) {
         condense(blk, cfg, L, s, Jz, Wz, w + L.oX, w + L.oU, xref, w + L.oGV, w + L.oHV, theta, sigma, lam_prev);
         blk.mark(PH_COND);
+        blk.count(CT_CONDENSE);
         double dmaxl = 0.0;
         for (int i = tid; i < n; i += nt) dmaxl = fmax(dmaxl, fabs(s.E[(size_t)i * ld + i]));
         const double dscale = blk.max(dmaxl);
         const int bad = chol_lower(blk, n, ld, s.E, 1e-10 * fmax(1.0, dscale));
         blk.mark(PH_CHOL);
         if (!bad) break;
+        blk.count(CT_CHOL_FAIL);
         ++fails;
         blk.sync();
         if (sigma == 0.0 && theta == 1.0 && aug_allowed) { sig0 = 10.0 * dscale; sigma = sig0; }
@@ -761,27 +848,39 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         s.E[(size_t)n * ld + i] = (i == n) ? 1.0 / sqrt(cfg.rho_slack) : 0.0;
     }
     blk.sync();
-    for (int idx = tid; idx < FTMPC_NE * nv; idx += nt) {
-        const int kk = idx / nv, i = idx % nv;
-        double v = 0.0;
-        if (i < n) for (int r = 0; r <= i; ++r) v += s.G[kk * ld + r] * s.E[(size_t)r * ld + i];
-        s.E[(size_t)(nv + kk) * ld + i] = v;
-    }
-    // unconstrained minimiser  x = -J J' ga
+    // column i of [X J ; ga' J]: ten accumulators share one sweep down column i of J (J is upper triangular)
     for (int i = tid; i < nv; i += nt) {
-        double v = 0.0;
-        if (i < n) for (int r = 0; r <= i; ++r) v += s.E[(size_t)r * ld + i] * s.ga[r];
-        s.gi.d[i] = v;
+        double acc[FTMPC_NE + 1];
+        for (int kk = 0; kk <= FTMPC_NE; ++kk) acc[kk] = 0.0;
+        if (i < n) {
+            for (int r = 0; r <= i; ++r) {
+                const double e = s.E[(size_t)r * ld + i];
+                for (int kk = 0; kk < FTMPC_NE; ++kk) acc[kk] += s.G[kk * ld + r] * e;
+                acc[FTMPC_NE] += s.ga[r] * e;
+            }
+        }
+        for (int kk = 0; kk < FTMPC_NE; ++kk) s.E[(size_t)(nv + kk) * ld + i] = acc[kk];
+        s.gi.d[i] = acc[FTMPC_NE];
     }
     blk.sync();
+    // unconstrained minimiser  x = -J J' ga  (extended coordinates)
     for (int row = tid; row < ne; row += nt) {
-        double v = 0.0;
-        for (int kk = 0; kk < nv; ++kk) v += s.E[(size_t)row * ld + kk] * s.gi.d[kk];
-        s.gi.xe[row] = -v;
+        const double* e = s.E + (size_t)row * ld;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int kk = 0;
+        for (; kk + 3 < nv; kk += 4) {
+            a0 += e[kk] * s.gi.d[kk];
+            a1 += e[kk + 1] * s.gi.d[kk + 1];
+            a2 += e[kk + 2] * s.gi.d[kk + 2];
+            a3 += e[kk + 3] * s.gi.d[kk + 3];
+        }
+        for (; kk < nv; ++kk) a0 += e[kk] * s.gi.d[kk];
+        s.gi.xe[row] = -((a0 + a1) + (a2 + a3));
     }
     blk.sync();
     MpcCons cons{N, n, nv, L.mc, s.hull, io.cfg_g->Af, s.cv};
     blk.mark(PH_QPSETUP);
+    blk.count(CT_QP);
     int qit1 = 0;
     // the previous multipliers are still needed if this attempt is rejected: the QP writes to the spare copy
     st = gi_solve(blk, cons, s.gi, nv, ne, ld, L.m, 0, w + L.oLam + L.m, cfg.max_qp_iter, cfg.qp_tol, &qit1, &nact);
