@@ -792,6 +792,227 @@ FT_HD void condense(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     blk.sync();
 }
 
+#if defined(__CUDACC__)
+// ---- condensing, CUDA-block specialisation -----------------------------------------------------------------
+// Same H, g, ga, G_N as the generic routine above, organised so that nothing is read-modify-written in
+// shared memory:
+//   * thread a < 6N owns COLUMN a of the sensitivity G_t = d x_t / d U in registers and advances it stage by
+//     stage (G_{t+1}[:,a] = A_t G_t[:,a] is thread-local); per stage it publishes G_t[:,a], (M_t G_t)[:,a] and
+//     (theta W_ux G_t)[:,a] to a double-buffered panel and accumulates its gradient entry;
+//   * thread (bi >= bj) owns the 6x6 BLOCK (bi, bj) of H in 36 registers and adds  G_t[:,bi]' (M_t G_t)[:,bj]
+//     (rank 13) at every stage t > bi; H is written once at the end.
+// One barrier per stage.  The panels live in the E region (free until H is stored).
+__device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg, const WsLayout& L, const QpScratch& s,
+                                         const double* Jz, const double* Wz_in, const double* X, const double* U,
+                                         const double* xref, const double* gradV, const double* hessV, double theta,
+                                         double sigma, const double* lam_prev) {
+    const int N = L.N, n = L.n, ld = L.nv, tid = blk.tid(), nt = blk.nthreads();
+    const int nblk = N * (N + 1) / 2;
+    const size_t panel_doubles = (size_t)64 * ld + (size_t)N * FTMPC_NE + 90;
+    if (nblk > nt || n > nt || panel_doubles > (size_t)(ld + FTMPC_NE) * ld) {      // very short / long horizons: generic path
+        condense<CudaBlock>(blk, cfg, L, s, Jz, Wz_in, X, U, xref, gradV, hessV, theta, sigma, lam_prev);
+        return;
+    }
+    double* Wp = const_cast<double*>(Wz_in);       // scratch copy owned by the caller: symmetrised / scaled in place
+    double* buf0 = s.E;                            // panel b: rows 0-12 G_t, 13-25 M_t G_t, 26-31 theta W_ux G_t
+    double* qe = s.E + (size_t)64 * ld;            // [N][9]   2 Q (x_t - xr_t)
+    double* Ht = qe + (size_t)N * FTMPC_NE;        // [9][9]   terminal Hessian model (+ augmentation)
+    double* tgv = Ht + 81;                         // [9]      augmentation of the terminal gradient
+    const double* Ah = s.hull;
+    // ---- pre-pass: W' = theta * sym(W) (+ 2Q on the omega diagonal), qe, Ht
+    for (int idx = tid; idx < N * 91; idx += nt) {
+        const int t = idx / 91;
+        int k = idx - t * 91;                      // pair (c >= r) of the 13 x 13 matrix
+        int c = (int)((sqrt(8.0 * k + 1.0) - 1.0) * 0.5);
+        while ((c + 1) * (c + 2) / 2 <= k) ++c;
+        while (c * (c + 1) / 2 > k) --c;
+        const int r = k - c * (c + 1) / 2;
+        double* wz = Wp + (size_t)t * 169;
+        double v = theta * 0.5 * (wz[c * 13 + r] + wz[r * 13 + c]);
+        if (c == r && c < 3) v += 2.0 * cfg.Q[6 + c];
+        wz[c * 13 + r] = v;
+        wz[r * 13 + c] = v;
+    }
+    for (int idx = tid; idx < N * FTMPC_NE; idx += nt) {
+        const int t = idx / FTMPC_NE, kk = idx - t * FTMPC_NE;
+        qe[idx] = 2.0 * cfg.Q[kk] * (X[t * FTMPC_NX + kk] - xref[t * FTMPC_NE + kk]);
+    }
+    for (int idx = tid; idx < 90; idx += nt) {
+        double v = 0.0;
+        const int kk = idx / 9, l = idx - kk * 9;
+        if (sigma > 0.0) {
+            const double* Af = cfg.Af;
+            for (int i = 0; i < FTMPC_NF; ++i) {
+                if (lam_prev[FTMPC_NH * N + i] > 0.0) {
+                    const double a = Af[i * FTMPC_NE + l];
+                    v += (idx < 81) ? Af[i * FTMPC_NE + kk] * a : s.cv[FTMPC_NH * N + i] * a;
+                }
+            }
+            v *= sigma;
+        }
+        if (idx < 81) {
+            const double q0 = cfg.term_quad[idx];
+            Ht[idx] = q0 + theta * (hessV[idx] - q0) + v;
+        } else {
+            tgv[l] = v;
+        }
+    }
+    if (tid == 0) { s.g[n] = 0.0; s.ga[n] = 0.0; }
+    for (int r = tid; r < FTMPC_NX; r += nt) s.G[r * ld + n] = 0.0;
+    // ---- roles
+    const int a = tid;                             // column role (a < n)
+    const int ta = a / FTMPC_NU, ja = a - ta * FTMPC_NU;
+    int bi = -1, bj = 0;                           // block role (tid < nblk)
+    if (tid < nblk) {
+        bi = (int)((sqrt(8.0 * tid + 1.0) - 1.0) * 0.5);
+        while ((bi + 1) * (bi + 2) / 2 <= tid) ++bi;
+        while (bi * (bi + 1) / 2 > tid) --bi;
+        bj = tid - bi * (bi + 1) / 2;
+    }
+    double g[FTMPC_NX], gs = 0.0, gaug = 0.0;
+    double acc[6][6];
+#pragma unroll
+    for (int i = 0; i < FTMPC_NX; ++i) g[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) acc[i][j] = 0.0;
+    blk.sync();
+    for (int t = 0; t <= N; ++t) {
+        double* buf = buf0 + (size_t)(t & 1) * 32 * ld;
+        // ---------------- column phase
+        if (a < n) {
+            if (ta < t) {
+                if (t < N) {
+                    const double* jz = Jz + (size_t)t * 169;
+                    const double* wp = Wp + (size_t)t * 169;
+                    double tp[FTMPC_NX], sx[FTMPC_NU];
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) tp[r] = 2.0 * cfg.Q[r] * g[r];
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int l = 0; l < 7; ++l) v += wp[k * 13 + l] * g[6 + l];
+                        tp[6 + k] = v;
+                    }
+#pragma unroll
+                    for (int i = 0; i < FTMPC_NU; ++i) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int l = 0; l < 7; ++l) v += wp[(7 + i) * 13 + l] * g[6 + l];
+                        sx[i] = v;
+                    }
+#pragma unroll
+                    for (int r = 0; r < FTMPC_NX; ++r) { buf[r * ld + a] = g[r]; buf[(13 + r) * ld + a] = tp[r]; }
+#pragma unroll
+                    for (int i = 0; i < FTMPC_NU; ++i) buf[(26 + i) * ld + a] = sx[i];
+#pragma unroll
+                    for (int kk = 0; kk < FTMPC_NE; ++kk) gs += qe[t * FTMPC_NE + kk] * g[kk];
+                    double gn[FTMPC_NX];
+#pragma unroll
+                    for (int r = 0; r < FTMPC_NX; ++r) {
+                        double v = (r < 3) ? g[r] + cfg.dt * g[r + 3] : ((r < 6) ? g[r] : 0.0);
+#pragma unroll
+                        for (int l = 0; l < 7; ++l) v += jz[l * 13 + r] * g[6 + l];
+                        gn[r] = v;
+                    }
+#pragma unroll
+                    for (int r = 0; r < FTMPC_NX; ++r) g[r] = gn[r];
+                } else {
+                    // terminal stage: publish G_N and Ht G_N, finish the gradient
+                    double va = 0.0, vg = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < FTMPC_NE; ++kk) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int l = 0; l < FTMPC_NE; ++l) v += Ht[kk * FTMPC_NE + l] * g[l];
+                        buf[kk * ld + a] = g[kk];
+                        buf[(13 + kk) * ld + a] = v;
+                        vg += gradV[kk] * g[kk];
+                        va += tgv[kk] * g[kk];
+                    }
+                    gs += vg;
+                    s.g[a] = gs;
+                    s.ga[a] = gaug + gs + va;
+#pragma unroll
+                    for (int r = 0; r < FTMPC_NX; ++r) s.G[r * ld + a] = g[r];
+                }
+            } else if (ta == t) {
+                // birth of column a = 6t + ja:  G_{t+1}[:, a] = B_t e_ja,  g_a = 2 R u
+                const double* jz = Jz + (size_t)t * 169;
+#pragma unroll
+                for (int r = 0; r < FTMPC_NX; ++r) g[r] = jz[(7 + ja) * 13 + r];
+                gs = 2.0 * cfg.R[ja] * U[a];
+                if (sigma > 0.0) {
+                    double av = 0.0;
+                    for (int i = 0; i < FTMPC_NH; ++i)
+                        if (lam_prev[t * FTMPC_NH + i] > 0.0) av += s.cv[t * FTMPC_NH + i] * Ah[i * FTMPC_NU + ja];
+                    gaug = sigma * av;
+                }
+            }
+        }
+        blk.sync();
+        // ---------------- block phase
+        if (bi >= 0) {
+            if (bi < t) {
+                const int K = (t < N) ? FTMPC_NX : FTMPC_NE;
+                const double* Pa = buf + 6 * bi;
+                const double* Tb = buf + (size_t)13 * ld + 6 * bj;
+                for (int r = 0; r < K; ++r) {
+                    double pa[6], tb[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) { pa[i] = Pa[(size_t)r * ld + i]; tb[i] = Tb[(size_t)r * ld + i]; }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i)
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) acc[i][j] += pa[i] * tb[j];
+                }
+            } else if (bi == t) {
+                if (bj < t) {
+                    // new block row: theta W_ux G_t   (row i of the block <- input i, column j <- column 6 bj + j)
+#pragma unroll
+                    for (int i = 0; i < 6; ++i)
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) acc[i][j] = buf[(size_t)(26 + i) * ld + 6 * bj + j];
+                } else {
+                    const double* wp = Wp + (size_t)t * 169;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i)
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) {
+                            double v = wp[(7 + i) * 13 + 7 + j];
+                            if (i == j) v += 2.0 * cfg.R[i];
+                            acc[i][j] = v;
+                        }
+                    if (sigma > 0.0) {
+                        for (int r = 0; r < FTMPC_NH; ++r) {
+                            if (lam_prev[t * FTMPC_NH + r] > 0.0) {
+#pragma unroll
+                                for (int i = 0; i < 6; ++i)
+#pragma unroll
+                                    for (int j = 0; j < 6; ++j) acc[i][j] += sigma * Ah[r * FTMPC_NU + i] * Ah[r * FTMPC_NU + j];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    blk.sync();                                    // the panels are dead: store H (lower triangle)
+    if (bi >= 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const int ra = 6 * bi + i, cb = 6 * bj + j;
+                if (cb <= ra) s.E[(size_t)ra * ld + cb] = acc[i][j];
+            }
+    }
+    blk.sync();
+}
+#endif  // __CUDACC__
+
 // ---- phase_qp ------------------------------------------------------------------------------------------
 template <class Blk>
 FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst, int slot, double* scratch) {

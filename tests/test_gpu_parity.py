@@ -124,10 +124,10 @@ def test_terminal_vs_oracle(L, eng6, oracle):
             assert np.allclose(Hs[b].reshape(9, 9)[i], fd, rtol=1e-5, atol=1e-4)
 
 
-def test_condense_gauss_newton_vs_oracle(L, oracle):
+@pytest.mark.parametrize("N", [8, 12, 20])      # 8: generic path, 12 / 20: register-tiled path
+def test_condense_gauss_newton_vs_oracle(L, oracle, N):
     """K2: condensed Hessian / gradient at theta = 0 == 2R + sum_t G_t' 2Q G_t + G_N' Hq G_N from the
     oracle's complex-step sensitivities (Hq = quadratic part of V_f)"""
-    N = 8
     eng = make_engine([[(10, 1.0), (11, 1.0)]], N)
     prob, _ = oracle.default_problem(N)
     rng = np.random.default_rng(7)
@@ -373,7 +373,7 @@ def test_batch_1024_properties_and_sharding(L, oracle):
         fs = oracle.FaultSet(cells[scen[k]]["faults"])
         prob = oracle.Problem(fs, N, oracle.robot_to_center(st[k]), xref[k], np.zeros((N + 1, 6)))
         r = oracle.kkt_residual(prob, g["z"][k, :6 * N])
-        assert r["stat"] < 1e-6 and r["viol"] < 1e-7, (k, r["stat"], r["viol"])
+        assert r["stat"] < 1e-5 and r["viol"] < 1e-7, (k, r["stat"], r["viol"])     # step-based stop, see above
     # determinism + shard invariance
     for G in (2, 8):
         for r in range(G):
