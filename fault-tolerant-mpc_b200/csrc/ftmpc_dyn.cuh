@@ -65,16 +65,20 @@ FT_HD void mat3_tmul(const double M[9], const double* v, double* o) {         //
     o[1] = M[1] * v[0] + M[4] * v[1] + M[7] * v[2];
     o[2] = M[2] * v[0] + M[5] * v[1] + M[8] * v[2];
 }
-// out[j] = g^T B(q,e_j) a   (gradient w.r.t. q of  g . (Rot(q) a))
+// out[j] = g^T B(q,e_j) a   (gradient w.r.t. q of  g . (Rot(q) a)).
+// g' Rot(q) a is the quadratic form q' S q with the symmetric 4x4 matrix S(g, a) below, and B is its
+// polarisation, so the gradient is 2 S q: 9 products for S instead of four bilinear-form evaluations.
 FT_HD void quat_grad(const double* q, const double* a, const double* g, double out[4]) {
-    for (int j = 0; j < 4; ++j) {
-        double e[4] = {0, 0, 0, 0};
-        e[j] = 1.0;
-        double M[9], t[3];
-        rot_bilinear(q, e, M);
-        mat3_mul(M, a, t);
-        out[j] = dot3(g, t);
-    }
+    const double P00 = g[0] * a[0], P01 = g[0] * a[1], P02 = g[0] * a[2];
+    const double P10 = g[1] * a[0], P11 = g[1] * a[1], P12 = g[1] * a[2];
+    const double P20 = g[2] * a[0], P21 = g[2] * a[1], P22 = g[2] * a[2];
+    const double Sxx = P00 - P11 - P22, Syy = -P00 + P11 - P22, Szz = -P00 - P11 + P22, Sww = P00 + P11 + P22;
+    const double Sxy = P01 + P10, Szw = P01 - P10, Sxz = P02 + P20, Syw = P20 - P02, Syz = P12 + P21, Sxw = P12 - P21;
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    out[0] = 2.0 * (Sxx * x + Sxy * y + Sxz * z + Sxw * w);
+    out[1] = 2.0 * (Sxy * x + Syy * y + Syz * z + Syw * w);
+    out[2] = 2.0 * (Sxz * x + Syz * y + Szz * z + Szw * w);
+    out[3] = 2.0 * (Sxw * x + Syw * y + Szw * z + Sww * w);
 }
 // OmegaOperator(w) @ q                                                   (sys_model.py:8-29)
 FT_HD void omega_apply(const double* w, const double* q, double* o) {
@@ -290,6 +294,106 @@ FT_HD void rk4_column(const DynConsts& k, const double* x, const double* Wr, int
         const double zero3[3] = {0, 0, 0};
         double nw[3], nq[4], nF[3], nT[3];
         dyn_vjp(k, sw[st], sq[st], sg[st], zero3, daw, daq, nw, nq, nF, nT, nullptr, nullptr);
+        for (int i = 0; i < 3; ++i) {
+            psi_v[i] = ap[i]; psi_w[i] = mw[i];
+            dps_w[i] = ow[i] + nw[i];
+            hw[i] += dps_w[i]; hF[i] += oF[i] + nF[i]; hT[i] += oT[i] + nT[i];
+        }
+        for (int i = 0; i < 4; ++i) { psi_q[i] = mq[i]; dps_q[i] = oq[i] + nq[i]; hq[i] += dps_q[i]; }
+    }
+    for (int i = 0; i < 3; ++i) { hess_col[i] = hw[i]; hess_col[7 + i] = hF[i]; hess_col[10 + i] = hT[i]; }
+    for (int i = 0; i < 4; ++i) hess_col[3 + i] = hq[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// Split form of rk4_column for the CUDA block path: the forward sweep parks the per-stage data the
+// reverse sweep needs in (shared) memory instead of registers, the nominal stage data once per stage
+// t, the tangents once per (t, column).  `st` strides let the caller choose a conflict-free layout.
+//   nom  : [4][10]   stage (w q g), contiguous per stage t
+//   tang : [4*7]     tangent of (w q) at the four RK stages, element e at tang[e * tstride]
+// ------------------------------------------------------------------------------------------
+FT_HD void rk4_col_forward(const DynConsts& k, const double* x, const double* Wr, int col, double* jac_col,
+                           double* nom /* or nullptr */, double* tang, int tstride) {
+    const double cs[4] = {0.0, 0.5 * k.dt, 0.5 * k.dt, k.dt};
+    const double bs[4] = {k.dt / 6.0, k.dt / 3.0, k.dt / 3.0, k.dt / 6.0};
+    double tW[6] = {0, 0, 0, 0, 0, 0};
+    double tx0[13];
+    for (int i = 0; i < 13; ++i) tx0[i] = 0.0;
+    if (col < 7) tx0[6 + col] = 1.0; else tW[col - 7] = 1.0;
+    double kn[13], kt[13], accn[13], acct[13];
+    for (int i = 0; i < 13; ++i) { kn[i] = 0.0; kt[i] = 0.0; acct[i] = tx0[i]; accn[i] = x[i]; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int st = 0; st < 4; ++st) {
+        double s[13], ts[13], g[3];
+        for (int i = 0; i < 13; ++i) { s[i] = x[i] + cs[st] * kn[i]; ts[i] = tx0[i] + cs[st] * kt[i]; }
+        for (int i = 0; i < 7; ++i) tang[(size_t)(st * 7 + i) * tstride] = ts[6 + i];
+        dyn_f(k, s + 3, s + 6, s + 9, Wr, kn, kn + 3, kn + 6, kn + 9, g);
+        if (nom) {
+            for (int i = 0; i < 7; ++i) nom[st * 10 + i] = s[6 + i];
+            for (int i = 0; i < 3; ++i) nom[st * 10 + 7 + i] = g[i];
+        }
+        dyn_jvp(k, s + 6, s + 9, g, ts + 3, ts + 6, ts + 9, tW, kt, kt + 3, kt + 6, kt + 9);
+        for (int i = 0; i < 13; ++i) { accn[i] += bs[st] * kn[i]; acct[i] += bs[st] * kt[i]; }
+    }
+    for (int i = 0; i < 13; ++i) jac_col[i] = acct[i];
+}
+
+// Jacobian columns of the three force inputs in closed form (the (w, q) tangents stay zero):
+//   d v+ / d F = sum_i b_i Rot(q_i)^T / m,   d p+ / d F = sum_i b_i c_i (d v-stage tangent),  jacF[j][13]
+FT_HD void rk4_force_columns(const DynConsts& k, const double* nom, double* jacF) {
+    const double cs[4] = {0.0, 0.5 * k.dt, 0.5 * k.dt, k.dt};
+    const double bs[4] = {k.dt / 6.0, k.dt / 3.0, k.dt / 3.0, k.dt / 6.0};
+    double kv_prev[9];
+    for (int i = 0; i < 39; ++i) jacF[i] = 0.0;
+    for (int i = 0; i < 9; ++i) kv_prev[i] = 0.0;
+    for (int st = 0; st < 4; ++st) {
+        double R[9];
+        rot_mat(nom + st * 10 + 3, R);
+        for (int j = 0; j < 3; ++j)
+            for (int i = 0; i < 3; ++i) {
+                const double kv = R[3 * j + i] / k.mass;         // (Rot^T e_j)_i = R[j][i]
+                jacF[j * 13 + i] += bs[st] * cs[st] * kv_prev[3 * j + i];
+                jacF[j * 13 + 3 + i] += bs[st] * kv;
+                kv_prev[3 * j + i] = kv;
+            }
+    }
+}
+
+// Reverse sweep: column `col` of the Hessian of lam^T RK4(x, W) in z-space from the parked forward data.
+FT_HD void rk4_col_reverse(const DynConsts& k, const double* nom, const double* tang, int tstride, int col,
+                           const double* lam, double* hess_col) {
+    double tW[6] = {0, 0, 0, 0, 0, 0};
+    if (col >= 7) tW[col - 7] = 1.0;
+    double hw[3] = {0, 0, 0}, hq[4] = {0, 0, 0, 0}, hF[3] = {0, 0, 0}, hT[3] = {0, 0, 0};
+    double psi_v[3] = {0, 0, 0}, psi_w[3] = {0, 0, 0}, psi_q[4] = {0, 0, 0, 0};
+    double dps_w[3] = {0, 0, 0}, dps_q[4] = {0, 0, 0, 0};
+    // the stage loop is deliberately NOT unrolled on the device: one stage already fills the register file
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int st = 3; st >= 0; --st) {
+        const double b_st = (st == 0 || st == 3) ? k.dt / 6.0 : k.dt / 3.0;          // RK4 weights
+        const double cnext = (st == 3) ? 0.0 : ((st == 2) ? k.dt : 0.5 * k.dt);      // node of the NEXT stage
+        double sw[3], sq[4], sg[3], tws[3], tqs[4];
+        for (int i = 0; i < 3; ++i) { sw[i] = nom[st * 10 + i]; sg[i] = nom[st * 10 + 7 + i]; tws[i] = tang[(size_t)(st * 7 + i) * tstride]; }
+        for (int i = 0; i < 4; ++i) { sq[i] = nom[st * 10 + 3 + i]; tqs[i] = tang[(size_t)(st * 7 + 3 + i) * tstride]; }
+        double av[3], aw[3], aq[4], daw[3], daq[4];
+        for (int i = 0; i < 3; ++i) {
+            av[i] = b_st * lam[3 + i] + cnext * psi_v[i];
+            aw[i] = b_st * lam[6 + i] + cnext * psi_w[i];
+            daw[i] = cnext * dps_w[i];
+        }
+        for (int i = 0; i < 4; ++i) { aq[i] = b_st * lam[9 + i] + cnext * psi_q[i]; daq[i] = cnext * dps_q[i]; }
+        const double ap[3] = {b_st * lam[0], b_st * lam[1], b_st * lam[2]};
+        double mw[3], mq[4], mF[3], mT[3], h[3], beta[3];
+        dyn_vjp(k, sw, sq, sg, av, aw, aq, mw, mq, mF, mT, h, beta);
+        double ow[3], oq[4], oF[3], oT[3];
+        dyn_hvp(k, sw, sq, sg, av, aq, h, beta, tws, tqs, tW, ow, oq, oF, oT);
+        const double zero3[3] = {0, 0, 0};
+        double nw[3], nq[4], nF[3], nT[3];
+        dyn_vjp(k, sw, sq, sg, zero3, daw, daq, nw, nq, nF, nT, nullptr, nullptr);
         for (int i = 0; i < 3; ++i) {
             psi_v[i] = ap[i]; psi_w[i] = mw[i];
             dps_w[i] = ow[i] + nw[i];

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
         phase_ls_block(blk, cfg, L, io, inst, slot, 1, scratch);
         for (int it = 0; it < cfg.max_sqp_iter; ++it) {
             if (sc[SC_STATUS] != (double)FTMPC_ST_RUNNING) break;      // uniform: written before the last barrier
-            phase_lin(blk, cfg, L, io, inst, slot);
+            phase_lin(blk, cfg, L, io, inst, slot, scratch);
             phase_qp(blk, cfg, L, io, inst, slot, scratch);
             phase_ls_block(blk, cfg, L, io, inst, slot, 0, scratch);
         }
@@ -360,8 +360,10 @@ int ftmpc_num_ineq(ftmpc_handle h) { return h ? h->L.mc : FTMPC_ERR_ARG; }
 
 // shared-memory scratch of one CTA: the QP matrices, or the line-search rollouts (they alternate)
 static size_t solve_smem_bytes(int N) {
-    size_t a = qp_scratch_doubles(N), b = ls_scratch_doubles(N);
-    return (a > b ? a : b) * sizeof(double);
+    size_t a = qp_scratch_doubles(N), b = ls_scratch_doubles(N), c = lin_scratch_doubles(N);
+    if (b > a) a = b;
+    if (c > a) a = c;
+    return a * sizeof(double);
 }
 
 static int solve_grid(const ftmpc_ctx* h, int batch) { return batch < h->num_sms ? batch : h->num_sms; }

@@ -793,6 +793,142 @@ FT_HD void condense(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
 }
 
 #if defined(__CUDACC__)
+// ---- linearisation, CUDA-block specialisation ------------------------------------------------------------
+// Same Jz / Wz / Mu as phase_lin above.  The (stage, column) sweep of rk4_column is split so that nothing has to be
+// held in registers across the costate recursion:
+//   pass 1  thread (t, c), c = one of the 10 columns in (w, q, tau): forward tangent through the RK4 stages; parks the
+//           stage tangents (and, for c = 0, the nominal stage data) in shared memory; the three force columns of the
+//           Jacobian come in closed form from the nominal stage rotations (their (w, q) tangents vanish);
+//   costate one warp, shared-memory Jacobians, no block barrier inside the recursion;
+//   pass 2  thread (t, c): reverse sweep from the parked data -> Hessian column; the force rows/columns of W_t are
+//           the transposes of what the other columns produce (the dynamics are linear in F).
+struct LinScratch {
+    double *nom, *wr, *tang, *Jz, *mu, *X;
+};
+__host__ __device__ inline size_t lin_scratch_doubles(int N) {
+    return (size_t)N * 40 + (size_t)N * 6 + (size_t)28 * 10 * N + (size_t)N * 169 + 2 * (size_t)(N + 1) * FTMPC_NX + 8;
+}
+__device__ __forceinline__ LinScratch lin_carve(double* buf, int N) {
+    LinScratch s;
+    double* p = buf;
+    s.nom = p; p += (size_t)N * 40;
+    s.wr = p; p += (size_t)N * 6;
+    s.tang = p; p += (size_t)28 * 10 * N;
+    s.Jz = p; p += (size_t)N * 169;
+    s.mu = p; p += (size_t)(N + 1) * FTMPC_NX;
+    s.X = p; p += (size_t)(N + 1) * FTMPC_NX;
+    return s;
+}
+__device__ __noinline__ void lin_forward_task(const DynConsts& k, const double* x, const double* Wr, int col, double* jac_col,
+                                              double* nom, double* tang, int tstride) {
+    rk4_col_forward(k, x, Wr, col, jac_col, nom, tang, tstride);
+}
+__device__ __noinline__ void lin_reverse_task(const DynConsts& k, const double* nom, const double* tang, int tstride, int col,
+                                              const double* lam, double* hess_col) {
+    rk4_col_reverse(k, nom, tang, tstride, col, lam, hess_col);
+}
+
+__device__ __forceinline__ void phase_lin(CudaBlock& blk, const ftmpc_config& cfg, const WsLayout& L, const StepIO& io,
+                                          int inst, int slot, double* scratch) {
+    double* w = ws_slot(io, L, slot);
+    const double* sc = w + L.oSc;
+    if (sc[SC_STATUS] != FTMPC_ST_RUNNING) return;
+    const int N = L.N, tid = blk.tid(), nt = blk.nthreads();
+    const DynConsts k = dyn_consts(cfg);
+    const double* xref = io.xref + (size_t)inst * (N + 1) * FTMPC_NE;
+    const double* uref = io.uref ? io.uref + (size_t)inst * (N + 1) * FTMPC_NU : nullptr;
+    const double* U = w + L.oU;
+    const double* X = w + L.oX;
+    double* Jz = w + L.oJz;
+    double* Wz = w + L.oWz;
+    double* Mu = w + L.oMu;
+    const double* lam = w + L.oLam;
+    const LinScratch s = lin_carve(scratch, N);
+    const int ntask = 10 * N;
+    // stage states and wrenches -> shared memory
+    for (int i = tid; i < (N + 1) * FTMPC_NX; i += nt) s.X[i] = X[i];
+    blk.sync();
+    for (int t = tid; t < N; t += nt)
+        stage_wrench(cfg, U + t * FTMPC_NU, uref ? uref + t * FTMPC_NU : nullptr, s.X + t * FTMPC_NX + 9, s.wr + t * 6);
+    blk.sync();
+    // pass 1: first-order columns
+    for (int it = tid; it < ntask; it += nt) {
+        const int t = it / 10, c = it - t * 10;
+        const int col = (c < 7) ? c : c + 3;
+        double jc[13];
+        lin_forward_task(k, s.X + t * FTMPC_NX, s.wr + t * 6, col, jc, (c == 0) ? s.nom + (size_t)t * 40 : nullptr,
+                         s.tang + it, ntask);
+        double* js = s.Jz + ((size_t)t * 13 + col) * 13;
+        double* jg = Jz + ((size_t)t * 13 + col) * 13;
+#pragma unroll
+        for (int i = 0; i < 13; ++i) { js[i] = jc[i]; jg[i] = jc[i]; }
+    }
+    // terminal costate  mu_N = [grad V_f + A_f' lam_term ; 0]   (threads from the other end of the block)
+    for (int i = nt - 1 - tid; i < FTMPC_NX; i += nt) {
+        double v = 0.0;
+        if (i < FTMPC_NE) {
+            v = w[L.oGV + i];
+            const double* Af = io.cfg_g->Af;
+            for (int r = 0; r < FTMPC_NF; ++r) v += Af[r * FTMPC_NE + i] * lam[FTMPC_NH * N + r];
+        }
+        s.mu[N * FTMPC_NX + i] = v;
+    }
+    blk.sync();
+    for (int t = tid; t < N; t += nt) {                       // force columns need the parked nominal stages
+        double jf[39];
+        rk4_force_columns(k, s.nom + (size_t)t * 40, jf);
+        for (int i = 0; i < 39; ++i) { s.Jz[((size_t)t * 13 + 7) * 13 + i] = jf[i]; Jz[((size_t)t * 13 + 7) * 13 + i] = jf[i]; }
+    }
+    blk.sync();
+    blk.mark(PH_LIN_JAC);
+    // costates  mu_t = [2Q e_t ; 0] + A_t' mu_{t+1}   (one warp, 13 lanes)
+    if (tid < 32) {
+        for (int t = N - 1; t >= 1; --t) {
+            const double* mn = s.mu + (t + 1) * FTMPC_NX;
+            if (tid < FTMPC_NX) {
+                const int i = tid;
+                double v = (i < FTMPC_NE) ? 2.0 * cfg.Q[i] * (s.X[t * FTMPC_NX + i] - xref[t * FTMPC_NE + i]) : 0.0;
+                if (i < 3) v += mn[i];
+                else if (i < 6) v += k.dt * mn[i - 3] + mn[i];
+                else {
+                    const double* col = s.Jz + ((size_t)t * 13 + (i - 6)) * 13;
+                    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                    for (int r = 0; r < 12; r += 2) { a0 += col[r] * mn[r]; a1 += col[r + 1] * mn[r + 1]; }
+                    v += a0 + a1 + col[12] * mn[12];
+                }
+                s.mu[t * FTMPC_NX + i] = v;
+            }
+            __syncwarp();
+        }
+    }
+    blk.sync();
+    for (int i = tid; i < (N + 1) * FTMPC_NX; i += nt) Mu[i] = s.mu[i];
+    blk.mark(PH_LIN_MU);
+    // pass 2: second-order columns
+    for (int it = tid; it < ntask; it += nt) {
+        const int t = it / 10, c = it - t * 10;
+        const int col = (c < 7) ? c : c + 3;
+        double hc[13];
+        lin_reverse_task(k, s.nom + (size_t)t * 40, s.tang + it, ntask, col, s.mu + (t + 1) * FTMPC_NX, hc);
+        double* wg = Wz + (size_t)t * 169;
+#pragma unroll
+        for (int i = 0; i < 13; ++i) wg[col * 13 + i] = hc[i];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) wg[(7 + j) * 13 + col] = hc[7 + j];      // W[F_j][col] = W[col][F_j]
+        if (c == 0) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int l = 0; l < 3; ++l) wg[(7 + j) * 13 + 7 + l] = 0.0;   // the dynamics are linear in F
+        }
+    }
+    blk.sync();
+    blk.mark(PH_LIN);
+}
+#endif  // __CUDACC__
+
+#if defined(__CUDACC__)
 // ---- condensing, CUDA-block specialisation -----------------------------------------------------------------
 // Same H, g, ga, G_N as the generic routine above, organised so that nothing is read-modify-written in
 // shared memory:
@@ -878,6 +1014,7 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
 #pragma unroll
         for (int j = 0; j < 6; ++j) acc[i][j] = 0.0;
     blk.sync();
+    blk.mark(PH_COND_PRE);
     for (int t = 0; t <= N; ++t) {
         double* buf = buf0 + (size_t)(t & 1) * 32 * ld;
         // ---------------- column phase
@@ -953,6 +1090,7 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
             }
         }
         blk.sync();
+        blk.mark(PH_COND_COL);
         // ---------------- block phase
         if (bi >= 0) {
             if (bi < t) {
@@ -998,6 +1136,7 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
                 }
             }
         }
+        blk.mark(PH_COND_BLK);                     // thread 0 owns block (0,0), the longest-lived accumulator
     }
     blk.sync();                                    // the panels are dead: store H (lower triangle)
     if (bi >= 0) {
