@@ -27,6 +27,7 @@ namespace ftmpc {
 
 struct DynConsts {
     double dt, mass, Jd[3], r[3];
+    double im, iJ[3];        // reciprocals: an fp64 division costs ~10 multiplications on the GPU
 };
 
 FT_HD void cross3(const double* a, const double* b, double* o) {
@@ -122,9 +123,9 @@ FT_HD void dyn_f(const DynConsts& k, const double* v, const double* w, const dou
     double c[3], e[3], g[3], t[3];
     gyro_bilinear(k, w, w, c);
     centri_bilinear(k, w, w, e);
-    for (int i = 0; i < 3; ++i) dw[i] = (Wr[3 + i] - 0.5 * c[i]) / k.Jd[i];       // :63-67
+    for (int i = 0; i < 3; ++i) dw[i] = (Wr[3 + i] - 0.5 * c[i]) * k.iJ[i];       // :63-67
     cross3(dw, k.r, t);
-    for (int i = 0; i < 3; ++i) g[i] = Wr[i] / k.mass + t[i] + 0.5 * e[i];         // :70-72
+    for (int i = 0; i < 3; ++i) g[i] = Wr[i] * k.im + t[i] + 0.5 * e[i];         // :70-72
     double R[9];
     rot_mat(q, R);
     mat3_tmul(R, g, dv);                                                             // :69 RotCasadi(q).T @ (...)
@@ -156,10 +157,10 @@ FT_HD void dyn_jvp(const DynConsts& k, const double* w, const double* q, const d
                    double* op, double* ov, double* ow, double* oq) {
     double c[3], e[3], t[3], tg[3];
     gyro_bilinear(k, w, tw, c);
-    for (int i = 0; i < 3; ++i) ow[i] = (tW[3 + i] - c[i]) / k.Jd[i];
+    for (int i = 0; i < 3; ++i) ow[i] = (tW[3 + i] - c[i]) * k.iJ[i];
     centri_bilinear(k, w, tw, e);
     cross3(ow, k.r, t);
-    for (int i = 0; i < 3; ++i) tg[i] = tW[i] / k.mass + t[i] + e[i];
+    for (int i = 0; i < 3; ++i) tg[i] = tW[i] * k.im + t[i] + e[i];
     double R[9], Bm[9], a[3], b[3];
     rot_mat(q, R);
     rot_bilinear(q, tq, Bm);
@@ -183,8 +184,8 @@ FT_HD void dyn_vjp(const DynConsts& k, const double* w, const double* q, const d
     rot_mat(q, R);
     mat3_mul(R, av, h);
     cross3(k.r, h, rxh);
-    for (int i = 0; i < 3; ++i) beta[i] = (aw[i] + rxh[i]) / k.Jd[i];
-    for (int i = 0; i < 3; ++i) { mF[i] = h[i] / k.mass; mT[i] = beta[i]; }
+    for (int i = 0; i < 3; ++i) beta[i] = (aw[i] + rxh[i]) * k.iJ[i];
+    for (int i = 0; i < 3; ++i) { mF[i] = h[i] * k.im; mT[i] = beta[i]; }
     double ct[3], et[3];
     gyro_bilinear_T(k, w, beta, ct);
     centri_bilinear_T(k, w, h, et);
@@ -211,16 +212,16 @@ FT_HD void dyn_hvp(const DynConsts& k, const double* w, const double* q, const d
     // tangents of the intermediate quantities
     double c[3], e[3], t[3], twd[3], tg[3];
     gyro_bilinear(k, w, tw, c);
-    for (int i = 0; i < 3; ++i) twd[i] = (tW[3 + i] - c[i]) / k.Jd[i];
+    for (int i = 0; i < 3; ++i) twd[i] = (tW[3 + i] - c[i]) * k.iJ[i];
     centri_bilinear(k, w, tw, e);
     cross3(twd, k.r, t);
-    for (int i = 0; i < 3; ++i) tg[i] = tW[i] / k.mass + t[i] + e[i];
+    for (int i = 0; i < 3; ++i) tg[i] = tW[i] * k.im + t[i] + e[i];
     double Bm[9], th[3], rxth[3], tbeta[3];
     rot_bilinear(q, tq, Bm);
     mat3_mul(Bm, av, th);
     cross3(k.r, th, rxth);
-    for (int i = 0; i < 3; ++i) tbeta[i] = rxth[i] / k.Jd[i];
-    for (int i = 0; i < 3; ++i) { oF[i] = th[i] / k.mass; oT[i] = tbeta[i]; }
+    for (int i = 0; i < 3; ++i) tbeta[i] = rxth[i] * k.iJ[i];
+    for (int i = 0; i < 3; ++i) { oF[i] = th[i] * k.im; oT[i] = tbeta[i]; }
     double c1[3], c2[3], e1[3], e2[3];
     gyro_bilinear_T(k, w, tbeta, c1);
     gyro_bilinear_T(k, tw, beta, c2);
@@ -353,7 +354,7 @@ FT_HD void rk4_force_columns(const DynConsts& k, const double* nom, double* jacF
         rot_mat(nom + st * 10 + 3, R);
         for (int j = 0; j < 3; ++j)
             for (int i = 0; i < 3; ++i) {
-                const double kv = R[3 * j + i] / k.mass;         // (Rot^T e_j)_i = R[j][i]
+                const double kv = R[3 * j + i] * k.im;         // (Rot^T e_j)_i = R[j][i]
                 jacF[j * 13 + i] += bs[st] * cs[st] * kv_prev[3 * j + i];
                 jacF[j * 13 + 3 + i] += bs[st] * kv;
                 kv_prev[3 * j + i] = kv;

@@ -51,9 +51,24 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
     __shared__ double red[192];
     __shared__ int s_inst;
     double* scratch = gscratch ? gscratch + (size_t)blockIdx.x * sdoubles : smem;
+    __shared__ double s_tfv[2 * FTMPC_NF];
+    __shared__ int s_tfi[2 * FTMPC_NF];
     CudaBlock blk(red, prof);
     const int slot = blockIdx.x;
     const double* sc = ws_slot(io, L, slot) + L.oSc;
+    // compact rows of the terminal set (A_f has at most two non-zeros per row; checked by ftmpc_create)
+    for (int i = threadIdx.x; i < FTMPC_NF; i += blockDim.x) {
+        int k = 0;
+        s_tfv[2 * i] = s_tfv[2 * i + 1] = 0.0;
+        s_tfi[2 * i] = s_tfi[2 * i + 1] = 0;
+        for (int j = 0; j < FTMPC_NE; ++j) {
+            const double a = io.cfg_g->Af[i * FTMPC_NE + j];
+            if (a != 0.0 && k < 2) { s_tfv[2 * i + k] = a; s_tfi[2 * i + k] = j; ++k; }
+        }
+    }
+    io.tf_val = s_tfv;
+    io.tf_idx = s_tfi;
+    __syncthreads();
     for (;;) {
         if (threadIdx.x == 0) s_inst = atomicAdd(queue, 1);
         __syncthreads();
@@ -293,6 +308,17 @@ int ftmpc_create(ftmpc_handle* out, const ftmpc_config* cfg, const double* hull_
         cfg->n_root > FTMPC_MAX_ROOT || cfg->max_sqp_iter < 1)
         return FTMPC_ERR_ARG;
     if (cfg->dtype != 0) return FTMPC_ERR_UNSUPPORTED;
+    for (int i = 0; i < FTMPC_NF; ++i) {               // structure the kernels rely on (true for the reference's terminal.yaml)
+        int nz = 0;
+        for (int j = 0; j < FTMPC_NE; ++j) nz += cfg->Af[i * FTMPC_NE + j] != 0.0;
+        if (nz > 2) return FTMPC_ERR_UNSUPPORTED;
+    }
+    for (int k = 0; k < cfg->n_poly + cfg->n_root; ++k) {
+        const int8_t* p = k < cfg->n_poly ? cfg->poly_e[k] : cfg->root_e[k - cfg->n_poly];
+        int nvv = 0;
+        for (int j = 0; j < FTMPC_NE; ++j) nvv += p[j] > 0;
+        if (nvv > 3) return FTMPC_ERR_UNSUPPORTED;
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return FTMPC_ERR_NO_DEVICE;
     ftmpc_ctx* h = new (std::nothrow) ftmpc_ctx;
@@ -392,7 +418,7 @@ int ftmpc_step(ftmpc_handle h, int batch, const double* state, const double* xre
     cudaStream_t stream = (cudaStream_t)stream_;
     const WsLayout L = h->L;
     StepIO io{batch, state, xref, uref, fault_mask, fault_force, hull_idx, h->d_hull, warm, z_warm, thrust, u0,
-              active_set, status, iters, cost, h->d_cfg, (double*)workspace};
+              active_set, status, iters, cost, nullptr, nullptr, h->d_cfg, (double*)workspace};
     const int grid = solve_grid(h, batch);
     const size_t smem = solve_smem_bytes(h->cfg.horizon);
     const bool use_global = smem > h->smem_optin;

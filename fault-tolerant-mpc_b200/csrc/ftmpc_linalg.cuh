@@ -132,19 +132,21 @@ __device__ __forceinline__ int chol_lower(CudaBlock& blk, int n, int ld, double*
                     for (int j = 0; j < NB; ++j) if (j <= i) ar[j] = l[i][j];
                 }
         }
-        // (2) trailing update, 4x4 tiles of the lower triangle
+        // (2) trailing update A22 -= P P' with 4x4 register tiles.  A tile takes the INTERLEAVED row sets
+        //     I(ti) = {r0 + ti + T a}, I(tj) = {r0 + tj + T b}: neighbouring lanes (consecutive tj) then read
+        //     neighbouring rows (odd leading dimension -> no bank conflicts; contiguous 4-row tiles would put a
+        //     warp's loads on 4 of the 16 banks).  Pairs ti >= tj cover the lower triangle once: an entry with
+        //     i < j is stored at its mirror (j, i), which no other tile owns.
         const int r0 = c0 + nb;
         const int w = n - r0;
         if (w > 0) {
             const int T = (w + 3) >> 2;
             const int ntiles = T * (T + 1) / 2;
             for (int tile = tid; tile < ntiles; tile += nt) {
-                // tile -> (ti >= tj)
                 int ti = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
                 while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
                 while (ti * (ti + 1) / 2 > tile) --ti;
                 const int tj = tile - ti * (ti + 1) / 2;
-                const int i0 = r0 + 4 * ti, j0 = r0 + 4 * tj;
                 double acc[4][4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
@@ -154,8 +156,9 @@ __device__ __forceinline__ int chol_lower(CudaBlock& blk, int n, int ld, double*
                 const double* pj[4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
-                    pi[a] = A + (size_t)((i0 + a < n) ? i0 + a : n - 1) * ld + c0;
-                    pj[a] = A + (size_t)((j0 + a < n) ? j0 + a : n - 1) * ld + c0;
+                    const int ri = r0 + ti + T * a, rj = r0 + tj + T * a;
+                    pi[a] = A + (size_t)((ri < n) ? ri : n - 1) * ld + c0;
+                    pj[a] = A + (size_t)((rj < n) ? rj : n - 1) * ld + c0;
                 }
 #pragma unroll
                 for (int k = 0; k < NB; ++k) {
@@ -173,8 +176,11 @@ __device__ __forceinline__ int chol_lower(CudaBlock& blk, int n, int ld, double*
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
-                        const int i = i0 + a, j = j0 + b;
-                        if (i < n && j <= i) A[(size_t)i * ld + j] -= acc[a][b];
+                        const int i = r0 + ti + T * a, j = r0 + tj + T * b;
+                        if (i < n && j < n && (ti != tj || a >= b)) {
+                            if (j <= i) A[(size_t)i * ld + j] -= acc[a][b];
+                            else A[(size_t)j * ld + i] -= acc[a][b];
+                        }
                     }
             }
         }
@@ -209,7 +215,21 @@ __device__ __forceinline__ void tri_inv_transpose(CudaBlock& blk, int n, int ld,
             const double* lrow[8];
 #pragma unroll
             for (int a = 0; a < 8; ++a) lrow[a] = A + (size_t)((i0 + a < n) ? i0 + a : n - 1) * ld;
-            for (int k = k0; k < k1; ++k) {
+            int k = k0;
+            for (; k + 3 < k1; k += 4) {              // 36 loads in flight before the first FMA
+                double xk[4], lv[8][4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) xk[u] = xr[k + u];
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) lv[a][u] = lrow[a][k + u];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) acc[a] += lv[a][u] * xk[u];
+            }
+            for (; k < k1; ++k) {
                 const double xk = xr[k];
 #pragma unroll
                 for (int a = 0; a < 8; ++a) acc[a] += lrow[a][k] * xk;
@@ -234,10 +254,8 @@ __device__ __forceinline__ void tri_inv_transpose(CudaBlock& blk, int n, int ld,
         }
     }
     blk.sync();
-    for (int idx = tid; idx < n * n; idx += nt) {
-        const int i = idx / n, j = idx - i * n;
-        if (j < i) A[(size_t)i * ld + j] = 0.0;
-    }
+    for (int i = 1 + (tid >> 5); i < n; i += (nt >> 5))          // strict lower triangle <- 0, one warp per row
+        for (int j = tid & 31; j < i; j += 32) A[(size_t)i * ld + j] = 0.0;
     blk.sync();
 }
 }  // namespace ftmpc

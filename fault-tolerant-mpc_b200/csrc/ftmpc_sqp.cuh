@@ -67,6 +67,8 @@ struct StepIO {
     int32_t* status;            // [B]
     int32_t* iters;             // [B,2]
     double* cost;               // [B]
+    const double* tf_val;       // compact terminal-set rows (shared memory, built once per CTA) or nullptr
+    const int* tf_idx;
     const ftmpc_config* cfg_g;  // copy of the configuration in global memory (tables indexed per thread); the kernels
                                 // also receive it by value as a __grid_constant__ parameter for uniform accesses
     double* ws;                 // workspace: one slot of L.stride doubles per instance (CPU port) or per CTA (k_solve)
@@ -77,7 +79,8 @@ FT_HD double* ws_slot(const StepIO& io, const WsLayout& L, int slot) { return io
 FT_HD DynConsts dyn_consts(const ftmpc_config& c) {
     DynConsts k;
     k.dt = c.dt; k.mass = c.mass;
-    for (int i = 0; i < 3; ++i) { k.Jd[i] = c.inertia[i]; k.r[i] = c.r[i]; }
+    for (int i = 0; i < 3; ++i) { k.Jd[i] = c.inertia[i]; k.r[i] = c.r[i]; k.iJ[i] = 1.0 / c.inertia[i]; }
+    k.im = 1.0 / c.mass;
     return k;
 }
 
@@ -547,6 +550,8 @@ struct MpcCons {
     const double* Ah;       // [26][6]
     const double* Af;       // [72][9]
     const double* cv;       // [mc] constraint values at the linearisation point
+    const double* tf_val;   // optional compact terminal rows (<= 2 non-zeros per row of A_f): [72][2] values ...
+    const int* tf_idx;      // ... and column indices; nullptr -> dense rows of Af
     // fixed layout (zeros kept) so that the row stays in registers: hull rows 6 + 1 entries, terminal rows 9 + 1
     FT_HD void row(int p, SparseRow& r) const {
         if (p < FTMPC_NH * N) {
@@ -582,10 +587,16 @@ struct MpcCons {
             return s;
         }
         if (p < mc) {
-            const double* a = Af + (p - FTMPC_NH * N) * FTMPC_NE;
+            const int i = p - FTMPC_NH * N;
             const double c = cv[p];
             double s = -sb * c;
-            for (int j = 0; j < FTMPC_NE; ++j) s -= a[j] * v[nv + j];
+            if (tf_val) {                      // skipping exact zeros leaves the sum bit-identical
+                s -= tf_val[2 * i] * v[nv + tf_idx[2 * i]];
+                s -= tf_val[2 * i + 1] * v[nv + tf_idx[2 * i + 1]];
+            } else {
+                const double* a = Af + i * FTMPC_NE;
+                for (int j = 0; j < FTMPC_NE; ++j) s -= a[j] * v[nv + j];
+            }
             if (c > 0.0) s += c * v[n];
             return s;
         }
@@ -944,25 +955,24 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
                                          double sigma, const double* lam_prev) {
     const int N = L.N, n = L.n, ld = L.nv, tid = blk.tid(), nt = blk.nthreads();
     const int nblk = N * (N + 1) / 2;
-    const size_t panel_doubles = (size_t)64 * ld + (size_t)N * FTMPC_NE + 90;
+    const int ldp = 7 * N + 1;                     // panel row length: block column b starts at 7 b (6 + 1 pad -> lanes of
+                                                   // neighbouring blocks are an odd number of doubles apart: no bank conflicts)
+    const size_t panel_doubles = (size_t)64 * ldp + (size_t)N * FTMPC_NE + 90;
     if (nblk > nt || n > nt || panel_doubles > (size_t)(ld + FTMPC_NE) * ld) {      // very short / long horizons: generic path
         condense<CudaBlock>(blk, cfg, L, s, Jz, Wz_in, X, U, xref, gradV, hessV, theta, sigma, lam_prev);
         return;
     }
     double* Wp = const_cast<double*>(Wz_in);       // scratch copy owned by the caller: symmetrised / scaled in place
     double* buf0 = s.E;                            // panel b: rows 0-12 G_t, 13-25 M_t G_t, 26-31 theta W_ux G_t
-    double* qe = s.E + (size_t)64 * ld;            // [N][9]   2 Q (x_t - xr_t)
+    double* qe = s.E + (size_t)64 * ldp;           // [N][9]   2 Q (x_t - xr_t)
     double* Ht = qe + (size_t)N * FTMPC_NE;        // [9][9]   terminal Hessian model (+ augmentation)
     double* tgv = Ht + 81;                         // [9]      augmentation of the terminal gradient
     const double* Ah = s.hull;
     // ---- pre-pass: W' = theta * sym(W) (+ 2Q on the omega diagonal), qe, Ht
-    for (int idx = tid; idx < N * 91; idx += nt) {
-        const int t = idx / 91;
-        int k = idx - t * 91;                      // pair (c >= r) of the 13 x 13 matrix
-        int c = (int)((sqrt(8.0 * k + 1.0) - 1.0) * 0.5);
-        while ((c + 1) * (c + 2) / 2 <= k) ++c;
-        while (c * (c + 1) / 2 > k) --c;
-        const int r = k - c * (c + 1) / 2;
+    for (int idx = tid; idx < N * 169; idx += nt) {
+        const int t = idx / 169, e = idx - t * 169;
+        const int c = e / 13, r = e - c * 13;
+        if (c < r) continue;                       // the pair (c >= r) is written by one thread
         double* wz = Wp + (size_t)t * 169;
         double v = theta * 0.5 * (wz[c * 13 + r] + wz[r * 13 + c]);
         if (c == r && c < 3) v += 2.0 * cfg.Q[6 + c];
@@ -998,6 +1008,7 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
     // ---- roles
     const int a = tid;                             // column role (a < n)
     const int ta = a / FTMPC_NU, ja = a - ta * FTMPC_NU;
+    const int pa_ = 7 * ta + ja;                   // column a inside a panel
     int bi = -1, bj = 0;                           // block role (tid < nblk)
     if (tid < nblk) {
         bi = (int)((sqrt(8.0 * tid + 1.0) - 1.0) * 0.5);
@@ -1016,7 +1027,7 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
     blk.sync();
     blk.mark(PH_COND_PRE);
     for (int t = 0; t <= N; ++t) {
-        double* buf = buf0 + (size_t)(t & 1) * 32 * ld;
+        double* buf = buf0 + (size_t)(t & 1) * 32 * ldp;
         // ---------------- column phase
         if (a < n) {
             if (ta < t) {
@@ -1041,9 +1052,9 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
                         sx[i] = v;
                     }
 #pragma unroll
-                    for (int r = 0; r < FTMPC_NX; ++r) { buf[r * ld + a] = g[r]; buf[(13 + r) * ld + a] = tp[r]; }
+                    for (int r = 0; r < FTMPC_NX; ++r) { buf[r * ldp + pa_] = g[r]; buf[(13 + r) * ldp + pa_] = tp[r]; }
 #pragma unroll
-                    for (int i = 0; i < FTMPC_NU; ++i) buf[(26 + i) * ld + a] = sx[i];
+                    for (int i = 0; i < FTMPC_NU; ++i) buf[(26 + i) * ldp + pa_] = sx[i];
 #pragma unroll
                     for (int kk = 0; kk < FTMPC_NE; ++kk) gs += qe[t * FTMPC_NE + kk] * g[kk];
                     double gn[FTMPC_NX];
@@ -1064,8 +1075,8 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
                         double v = 0.0;
 #pragma unroll
                         for (int l = 0; l < FTMPC_NE; ++l) v += Ht[kk * FTMPC_NE + l] * g[l];
-                        buf[kk * ld + a] = g[kk];
-                        buf[(13 + kk) * ld + a] = v;
+                        buf[kk * ldp + pa_] = g[kk];
+                        buf[(13 + kk) * ldp + pa_] = v;
                         vg += gradV[kk] * g[kk];
                         va += tgv[kk] * g[kk];
                     }
@@ -1095,12 +1106,12 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
         if (bi >= 0) {
             if (bi < t) {
                 const int K = (t < N) ? FTMPC_NX : FTMPC_NE;
-                const double* Pa = buf + 6 * bi;
-                const double* Tb = buf + (size_t)13 * ld + 6 * bj;
+                const double* Pa = buf + 7 * bi;
+                const double* Tb = buf + (size_t)13 * ldp + 7 * bj;
                 for (int r = 0; r < K; ++r) {
                     double pa[6], tb[6];
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) { pa[i] = Pa[(size_t)r * ld + i]; tb[i] = Tb[(size_t)r * ld + i]; }
+                    for (int i = 0; i < 6; ++i) { pa[i] = Pa[(size_t)r * ldp + i]; tb[i] = Tb[(size_t)r * ldp + i]; }
 #pragma unroll
                     for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -1112,7 +1123,7 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
 #pragma unroll
                     for (int i = 0; i < 6; ++i)
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) acc[i][j] = buf[(size_t)(26 + i) * ld + 6 * bj + j];
+                        for (int j = 0; j < 6; ++j) acc[i][j] = buf[(size_t)(26 + i) * ldp + 7 * bj + j];
                 } else {
                     const double* wp = Wp + (size_t)t * 169;
 #pragma unroll
@@ -1238,7 +1249,7 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         s.gi.xe[row] = -((a0 + a1) + (a2 + a3));
     }
     blk.sync();
-    MpcCons cons{N, n, nv, L.mc, s.hull, io.cfg_g->Af, s.cv};
+    MpcCons cons{N, n, nv, L.mc, s.hull, io.cfg_g->Af, s.cv, io.tf_val, io.tf_idx};
     blk.mark(PH_QPSETUP);
     blk.count(CT_QP);
     int qit1 = 0;
