@@ -44,13 +44,18 @@ struct ftmpc_ctx {
 // kernels
 // -------------------------------------------------------------------------------------------------
 #define FTMPC_QP_THREADS 256
+// GS = false: the CTA scratch is the dynamic shared memory.  The choice is a TEMPLATE parameter on purpose: with a
+// run-time select the compiler cannot prove the address space and every scratch access becomes a generic LD/ST
+// (longer latency than LDS/STS, and it lands on the long scoreboard).  GS = true (horizons whose QP does not fit in
+// 227 KB) keeps the scratch in a per-CTA global slice.
+template <bool GS>
 __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
     k_solve(const __grid_constant__ ftmpc_config cfg, WsLayout L, StepIO io, int* queue, double* gscratch, size_t sdoubles,
             long long* prof) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double red[192];
     __shared__ int s_inst;
-    double* scratch = gscratch ? gscratch + (size_t)blockIdx.x * sdoubles : smem;
+    double* scratch = GS ? gscratch + (size_t)blockIdx.x * sdoubles : smem;
     __shared__ double s_tfv[2 * FTMPC_NF];
     __shared__ int s_tfi[2 * FTMPC_NF];
     CudaBlock blk(red, prof);
@@ -146,7 +151,8 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
                double theta, double* H, double* g, double* gscratch, size_t sdoubles) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double red[192];
-    double* scratch = gscratch ? gscratch + (size_t)blockIdx.x * sdoubles : smem;
+    double* scratch = smem;
+    (void)gscratch; (void)sdoubles;
     CudaBlock blk(red);
     const int N = L.N, n = L.n, ld = L.nv;
     for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
@@ -425,14 +431,18 @@ int ftmpc_step(ftmpc_handle h, int batch, const double* state, const double* xre
     double* gscratch = use_global ? (double*)((char*)workspace + align_up(L.stride * sizeof(double) * (size_t)grid, 256)) : nullptr;
     const size_t sdoubles = align_up(smem, 256) / sizeof(double);
     // the attribute is per function, not per handle: handles with different horizons share k_solve
-    if (!use_global) CU(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!use_global) CU(cudaFuncSetAttribute(k_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU(cudaMemsetAsync(h->d_queue, 0, sizeof(int), stream));
     if (h->profile) {
         CU(cudaMemsetAsync(h->d_prof, 0, PH_COUNT * sizeof(long long), stream));
         CU(cudaEventRecord(h->ev[0], stream));
     }
-    k_solve<<<grid, FTMPC_QP_THREADS, use_global ? 0 : smem, stream>>>(h->cfg, L, io, h->d_queue, gscratch, sdoubles,
-                                                                        h->profile ? h->d_prof : nullptr);
+    if (use_global)
+        k_solve<true><<<grid, FTMPC_QP_THREADS, 0, stream>>>(h->cfg, L, io, h->d_queue, gscratch, sdoubles,
+                                                             h->profile ? h->d_prof : nullptr);
+    else
+        k_solve<false><<<grid, FTMPC_QP_THREADS, smem, stream>>>(h->cfg, L, io, h->d_queue, nullptr, 0,
+                                                                 h->profile ? h->d_prof : nullptr);
     if (h->profile) CU(cudaEventRecord(h->ev[1], stream));
     k_alloc<<<(batch + 63) / 64, 64, 0, stream>>>(h->cfg, L, io);
     if (h->profile) CU(cudaEventRecord(h->ev[2], stream));
