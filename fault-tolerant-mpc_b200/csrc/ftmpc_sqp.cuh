@@ -949,16 +949,30 @@ __device__ __forceinline__ void phase_lin(CudaBlock& blk, const ftmpc_config& cf
 //   * thread (bi >= bj) owns the 6x6 BLOCK (bi, bj) of H in 36 registers and adds  G_t[:,bi]' (M_t G_t)[:,bj]
 //     (rank 13) at every stage t > bi; H is written once at the end.
 // One barrier per stage.  The panels live in the E region (free until H is stored).
+// When `hb` is given and the register-tiled path is taken, H is NOT stored: the 6x6 blocks stay in hb->acc (owner
+// thread (hb->bi, hb->bj)) for chol_inv_blocks, hb->fast = true.
+struct HBlocks {
+    double acc[6][6];
+    int bi, bj;
+    bool fast;
+};
+__device__ __forceinline__ bool condense_fast_path(const WsLayout& L, int nt) {
+    const int N = L.N, ld = L.nv;
+    const int ldp = 7 * N + 1;
+    const size_t panel_doubles = (size_t)64 * ldp + (size_t)N * FTMPC_NE + 90;
+    return !(N * (N + 1) / 2 > nt || L.n > nt || panel_doubles > (size_t)(ld + FTMPC_NE) * ld);
+}
 __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg, const WsLayout& L, const QpScratch& s,
                                          const double* Jz, const double* Wz_in, const double* X, const double* U,
                                          const double* xref, const double* gradV, const double* hessV, double theta,
-                                         double sigma, const double* lam_prev) {
+                                         double sigma, const double* lam_prev, HBlocks* hb = nullptr) {
     const int N = L.N, n = L.n, ld = L.nv, tid = blk.tid(), nt = blk.nthreads();
     const int nblk = N * (N + 1) / 2;
+    if (hb) hb->fast = false;
     const int ldp = 7 * N + 1;                     // panel row length: block column b starts at 7 b (6 + 1 pad -> lanes of
                                                    // neighbouring blocks are an odd number of doubles apart: no bank conflicts)
     const size_t panel_doubles = (size_t)64 * ldp + (size_t)N * FTMPC_NE + 90;
-    if (nblk > nt || n > nt || panel_doubles > (size_t)(ld + FTMPC_NE) * ld) {      // very short / long horizons: generic path
+    if (!condense_fast_path(L, nt)) {              // very short / long horizons: generic path
         condense<CudaBlock>(blk, cfg, L, s, Jz, Wz_in, X, U, xref, gradV, hessV, theta, sigma, lam_prev);
         return;
     }
@@ -1149,8 +1163,18 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
         }
         blk.mark(PH_COND_BLK);                     // thread 0 owns block (0,0), the longest-lived accumulator
     }
-    blk.sync();                                    // the panels are dead: store H (lower triangle)
-    if (bi >= 0) {
+    blk.sync();                                    // the panels are dead
+    if (hb) {                                      // hand the blocks over in registers
+        hb->fast = true;
+        hb->bi = bi;
+        hb->bj = bj;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) hb->acc[i][j] = acc[i][j];
+        return;
+    }
+    if (bi >= 0) {                                 // store H (lower triangle)
 #pragma unroll
         for (int i = 0; i < 6; ++i)
 #pragma unroll
@@ -1161,7 +1185,239 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
     }
     blk.sync();
 }
+
+// ---- register-resident block Cholesky + L^-T ------------------------------------------------------------
+// H arrives as 6x6 blocks in the registers of their owner threads (from `condense`), so the factorisation never
+// read-modify-writes shared memory: per block column k
+//   A  the owner of (k,k) factors its block, inverts it (6x6 lower) and publishes L_kk^-1;
+//   B  owners of (i,k), i > k:  L_ik = A_ik L_kk^-T  -> published to the lower triangle of E;
+//   C  owners of (i,j), i >= j > k:  A_ij -= L_ik L_jk'  (operands from E, accumulators in registers);
+// two barriers per block column.  Then X = L^-1 by block wavefronts (distance s = i - j): every owner adds
+// L_{i,j+s-1} X_{j+s-1,j} as soon as that X block exists and the owners at distance s finish
+// X_ij = -L_ii^-1 S_ij; X is stored TRANSPOSED in the upper triangle of E, i.e. directly as J = L^-T.
+// Returns 0, or 6k+1.. when a pivot of block column k is not safely positive (uniform over the block).
+__device__ __forceinline__ int chol_inv_blocks(CudaBlock& blk, int Nb, int ld, double* E, double* linv, HBlocks& hb,
+                                               double piv_tol) {
+    const int tid = blk.tid();
+    const int bi = hb.bi, bj = hb.bj;
+    double (&acc)[6][6] = hb.acc;
+    double* flag = linv + (size_t)Nb * 36;
+    if (tid == 0) *flag = 0.0;
+    blk.sync();
+    for (int k = 0; k < Nb; ++k) {
+        if (bi == k && bj == k) {
+            int bad = 0;
+            double inv[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                double d = acc[j][j];
+#pragma unroll
+                for (int m = 0; m < 6; ++m) if (m < j) d -= acc[j][m] * acc[j][m];
+                if (!(d > piv_tol)) bad = 1;
+                const double rs = rsqrt(d);
+                inv[j] = rs;
+                acc[j][j] = d * rs;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    if (i > j) {
+                        double v = acc[i][j];
+#pragma unroll
+                        for (int m = 0; m < 6; ++m) if (m < j) v -= acc[i][m] * acc[j][m];
+                        acc[i][j] = v * rs;
+                    }
+                }
+            }
+            // Y = L_kk^-1 (lower)
+            double Y[6][6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    if (i < j) Y[i][j] = 0.0;
+                    else if (i == j) Y[i][j] = inv[j];
+                    else {
+                        double v = 0.0;
+#pragma unroll
+                        for (int m = 0; m < 6; ++m) if (m >= j && m < i) v += acc[i][m] * Y[m][j];
+                        Y[i][j] = -v * inv[i];
+                    }
+                }
+            }
+            double* lk = linv + (size_t)k * 36;
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    lk[i * 6 + j] = Y[i][j];
+                    // diagonal block of E: X_kk^T in the upper triangle (incl. diagonal), zeros strictly below
+                    E[(size_t)(6 * k + j) * ld + 6 * k + i] = Y[i][j];      // (j,i) <- Y[i][j]; for i < j this writes the zeros
+                }
+            if (bad) *flag = (double)(6 * k + 1);
+        }
+        blk.sync();
+        if (*flag != 0.0) return (int)*flag;
+        if (bj == k && bi > k) {
+            const double* lk = linv + (size_t)k * 36;
+            double Y[6][6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int j = 0; j < 6; ++j) Y[i][j] = (j <= i) ? lk[i * 6 + j] : 0.0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                double x[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int m = 0; m < 6; ++m) if (m <= j) v += acc[i][m] * Y[j][m];
+                    x[j] = v;
+                }
+                double* er = E + (size_t)(6 * bi + i) * ld + 6 * k;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) { acc[i][j] = x[j]; er[j] = x[j]; }
+            }
+        }
+        blk.sync();
+        if (bi >= 0 && bj > k) {
+            double Lb[6][6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const double* er = E + (size_t)(6 * bj + j) * ld + 6 * k;
+#pragma unroll
+                for (int m = 0; m < 6; ++m) Lb[j][m] = er[m];
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const double* er = E + (size_t)(6 * bi + i) * ld + 6 * k;
+                double La[6];
+#pragma unroll
+                for (int m = 0; m < 6; ++m) La[m] = er[m];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    double v = acc[i][j];
+#pragma unroll
+                    for (int m = 0; m < 6; ++m) v -= La[m] * Lb[j][m];
+                    acc[i][j] = v;
+                }
+            }
+        }
+    }
+    blk.mark(PH_CHOL);
+    // ---- X = L^-1 by block wavefronts; S accumulates in the (now dead) H registers
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) acc[i][j] = 0.0;
+    for (int sdist = 1; sdist < Nb; ++sdist) {
+        if (bi >= 0 && bi - bj >= sdist) {
+            const int kb = bj + sdist - 1;
+            double Xb[6][6];                               // Xb[b][m] = X_{kb,bj}[m][b]
+#pragma unroll
+            for (int b = 0; b < 6; ++b) {
+                const double* er = E + (size_t)(6 * bj + b) * ld + 6 * kb;
+#pragma unroll
+                for (int m = 0; m < 6; ++m) Xb[b][m] = er[m];
+            }
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                const double* er = E + (size_t)(6 * bi + a) * ld + 6 * kb;
+                double La[6];
+#pragma unroll
+                for (int m = 0; m < 6; ++m) La[m] = er[m];
+#pragma unroll
+                for (int b = 0; b < 6; ++b) {
+                    double v = acc[a][b];
+#pragma unroll
+                    for (int m = 0; m < 6; ++m) v += La[m] * Xb[b][m];
+                    acc[a][b] = v;
+                }
+            }
+            if (bi - bj == sdist) {
+                const double* lk = linv + (size_t)bi * 36;
+#pragma unroll
+                for (int b = 0; b < 6; ++b) {
+                    double x[6];
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int m = 0; m < 6; ++m) if (m <= a) v += lk[a * 6 + m] * acc[m][b];
+                        x[a] = -v;
+                    }
+                    double* er = E + (size_t)(6 * bj + b) * ld + 6 * bi;
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) er[a] = x[a];
+                }
+            }
+        }
+        blk.sync();
+    }
+    // the strictly lower blocks (L) are dead: J is upper triangular
+    if (bi > bj) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double* er = E + (size_t)(6 * bi + i) * ld + 6 * bj;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) er[j] = 0.0;
+        }
+    }
+    blk.sync();
+    blk.mark(PH_INV);
+    return 0;
+}
 #endif  // __CUDACC__
+
+// ---- condensed Hessian -> J = L^-T (rows 0..n-1 of E); returns 0 or the failing pivot + 1 -------------------
+template <class Blk>
+FT_HD int factor_hessian(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const QpScratch& s, double* Jz, double* Wz,
+                         const double* Jz_src, const double* Wz_src, const double* X, const double* U, const double* xref,
+                         const double* gradV, const double* hessV, double theta, double sigma, const double* lam_prev,
+                         double* dscale_out) {
+    const int N = L.N, n = L.n, ld = L.nv, tid = blk.tid(), nt = blk.nthreads();
+    for (int i = tid; i < N * 169; i += nt) { Jz[i] = Jz_src[i]; Wz[i] = Wz_src[i]; }     // (the QP reuses this region)
+    blk.sync();
+    condense(blk, cfg, L, s, Jz, Wz, X, U, xref, gradV, hessV, theta, sigma, lam_prev);
+    blk.mark(PH_COND);
+    blk.count(CT_CONDENSE);
+    double dmaxl = 0.0;
+    for (int i = tid; i < n; i += nt) dmaxl = fmax(dmaxl, fabs(s.E[(size_t)i * ld + i]));
+    const double dscale = blk.max(dmaxl);
+    *dscale_out = dscale;
+    const int bad = chol_lower(blk, n, ld, s.E, 1e-10 * fmax(1.0, dscale));
+    blk.mark(PH_CHOL);
+    if (bad) return bad;
+    tri_inv_transpose(blk, n, ld, s.E, s.dg);
+    blk.mark(PH_INV);
+    return 0;
+}
+#if defined(__CUDACC__)
+__device__ __forceinline__ int factor_hessian(CudaBlock& blk, const ftmpc_config& cfg, const WsLayout& L, const QpScratch& s,
+                                              double* Jz, double* Wz, const double* Jz_src, const double* Wz_src,
+                                              const double* X, const double* U, const double* xref, const double* gradV,
+                                              const double* hessV, double theta, double sigma, const double* lam_prev,
+                                              double* dscale_out) {
+    const int N = L.N, n = L.n, ld = L.nv, tid = blk.tid(), nt = blk.nthreads();
+    if (!condense_fast_path(L, nt))
+        return factor_hessian<CudaBlock>(blk, cfg, L, s, Jz, Wz, Jz_src, Wz_src, X, U, xref, gradV, hessV, theta, sigma,
+                                         lam_prev, dscale_out);
+    for (int i = tid; i < N * 169; i += nt) { Jz[i] = Jz_src[i]; Wz[i] = Wz_src[i]; }     // Wz is scaled in place below
+    blk.sync();
+    HBlocks hb;
+    condense(blk, cfg, L, s, Jz, Wz, X, U, xref, gradV, hessV, theta, sigma, lam_prev, &hb);
+    blk.mark(PH_COND);
+    blk.count(CT_CONDENSE);
+    double dmaxl = 0.0;
+    if (hb.bi >= 0 && hb.bi == hb.bj) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) dmaxl = fmax(dmaxl, fabs(hb.acc[i][i]));
+    }
+    const double dscale = blk.max(dmaxl);
+    *dscale_out = dscale;
+    (void)n;
+    return chol_inv_blocks(blk, N, ld, s.E, s.T, hb, 1e-10 * fmax(1.0, dscale));
+}
+#endif
 
 // ---- phase_qp ------------------------------------------------------------------------------------------
 template <class Blk>
@@ -1190,17 +1446,10 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     int fails = 0, qit = 0, nact = 0, st = GI_OK;
     for (;;) {        // QP attempts (re-solved without augmentation if a predicted-active row came out inactive)
     double sig0 = 0.0;
-    for (int i = tid; i < N * 169; i += nt) { Jz[i] = w[L.oJz + i]; Wz[i] = w[L.oWz + i]; }    // (the QP reuses this region)
-    blk.sync();
     for (;;) {
-        condense(blk, cfg, L, s, Jz, Wz, w + L.oX, w + L.oU, xref, w + L.oGV, w + L.oHV, theta, sigma, lam_prev);
-        blk.mark(PH_COND);
-        blk.count(CT_CONDENSE);
-        double dmaxl = 0.0;
-        for (int i = tid; i < n; i += nt) dmaxl = fmax(dmaxl, fabs(s.E[(size_t)i * ld + i]));
-        const double dscale = blk.max(dmaxl);
-        const int bad = chol_lower(blk, n, ld, s.E, 1e-10 * fmax(1.0, dscale));
-        blk.mark(PH_CHOL);
+        double dscale = 0.0;
+        const int bad = factor_hessian(blk, cfg, L, s, Jz, Wz, w + L.oJz, w + L.oWz, w + L.oX, w + L.oU, xref, w + L.oGV,
+                                       w + L.oHV, theta, sigma, lam_prev, &dscale);
         if (!bad) break;
         blk.count(CT_CHOL_FAIL);
         ++fails;
@@ -1211,8 +1460,6 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         else if (theta <= 0.0) { if (tid == 0) { sc[SC_QPST] = 3.0; } return; }
         else theta = (theta > 0.125) ? 0.5 * theta : 0.0;
     }
-    tri_inv_transpose(blk, n, ld, s.E, s.dg);
-    blk.mark(PH_INV);
     // slack variable column/row, extension rows  X J  (X = d x_N[0:9] / d U)
     for (int i = tid; i < nv; i += nt) {
         s.E[(size_t)i * ld + n] = 0.0;
