@@ -138,7 +138,8 @@ def cpu_solve_rate(N: int, cells, states, scen, xref, sample: int, steps: int, w
             ffs[k, i] = a * model.max_thrust
     s = slice(0, sample)
     args = (cfg, table, states[s], xref[s], None, masks[scen[s]], ffs[scen[s]], scen[s])
-    cores = port.lib.ftmpc_cpu_num_threads()
+    cores = os.cpu_count() or port.lib.ftmpc_cpu_num_threads()       # torchrun exports OMP_NUM_THREADS=1: ask for all cores explicitly
+    args = args + (0, None, cores)
     for _ in range(warmup):
         port.step(*args)
     t0 = time.perf_counter()
@@ -206,6 +207,7 @@ def main():
     torch.cuda.set_device(local)
     devs = f"cuda:{local}"
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")                # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device(devs))
     B = a.batch
     Btot = B * world
