@@ -606,7 +606,6 @@ struct MpcCons {
 
 // per-CTA scratch carved out of one buffer of doubles (shared memory on the device)
 struct QpScratch {
-    const ftmpc_config* cg;      // configuration copy addressable per thread (global memory on the device)
     double *E, *RS, *G, *T, *g, *ga, *taug, *cv, *hull;
     GiWork gi;
     double* dg;
@@ -623,11 +622,10 @@ FT_HD size_t qp_scratch_doubles(int N) {
     size_t ints = ((nv + 1) + L.m + (nv + 1) + 1) / 2 + 1;
     return ne * nv + rs + (size_t)FTMPC_NX * nv + gi_vec + 2 * nv /*g, ga*/ + 90 /*taug*/ + L.mc /*cv*/ + FTMPC_HULL_STRIDE + ints + 8;
 }
-FT_HD QpScratch qp_carve(double* buf, int N, const ftmpc_config* cg = nullptr) {
+FT_HD QpScratch qp_carve(double* buf, int N) {
     const WsLayout L = ws_layout(N);
     const size_t nv = L.nv, ne = nv + FTMPC_NE, n = L.n;
     QpScratch s;
-    s.cg = cg;
     double* p = buf;
     s.E = p; p += ne * nv;
     size_t rs = nv * (nv + 1) / 2;
@@ -951,49 +949,40 @@ __device__ __forceinline__ void phase_lin(CudaBlock& blk, const ftmpc_config& cf
 //   * thread (bi >= bj) owns the 6x6 BLOCK (bi, bj) of H in 36 registers and adds  G_t[:,bi]' (M_t G_t)[:,bj]
 //     (rank 13) at every stage t > bi; H is written once at the end.
 // One barrier per stage.  The panels live in the E region (free until H is stored).
-// When `hb` is given and the register-tiled path is taken, the 6x6 blocks are also handed over in hb->acc (owner
+// When `hb` is given and the register-tiled path is taken, H is NOT stored: the 6x6 blocks stay in hb->acc (owner
 // thread (hb->bi, hb->bj)) for chol_inv_blocks, hb->fast = true.
 struct HBlocks {
     double acc[6][6];
     int bi, bj;
     bool fast;
 };
-__device__ __forceinline__ int condense_ntall(int N) {          // 12x6 blocks: pair p covers block rows 2p, 2p+1
-    int c = 0;
-    for (int p2 = 0; 2 * p2 < N; ++p2) c += (2 * p2 + 1 < N) ? 2 * p2 + 2 : 2 * p2 + 1;
-    return c;
-}
 __device__ __forceinline__ bool condense_fast_path(const WsLayout& L, int nt) {
     const int N = L.N, ld = L.nv;
     const int ldp = 7 * N + 1;
-    const size_t panel_doubles = (size_t)64 * ldp + (size_t)N * FTMPC_NE + 90 + (size_t)L.mc;
-    return nt >= 256 && L.n <= nt / 2 && condense_ntall(N) <= nt / 2 && N * (N + 1) / 2 <= nt &&
-           panel_doubles <= (size_t)(ld + FTMPC_NE) * ld;
+    const size_t panel_doubles = (size_t)64 * ldp + (size_t)N * FTMPC_NE + 90;
+    return !(N * (N + 1) / 2 > nt || L.n > nt || panel_doubles > (size_t)(ld + FTMPC_NE) * ld);
 }
-// Warp-specialised: the first half of the block owns 12x6 blocks of H (two block rows sharing the same M_t G_t
-// operand), the second half owns the columns of G.  While the block owners consume the panel of stage t, the column
-// owners already produce the panel of stage t+1 into the other buffer: a stage costs max(block, column) work
-// instead of their sum, with one barrier per stage.
 __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg, const WsLayout& L, const QpScratch& s,
                                          const double* Jz, const double* Wz_in, const double* X, const double* U,
                                          const double* xref, const double* gradV, const double* hessV, double theta,
-                                         double sigma, const double* lam_prev_g, HBlocks* hb = nullptr) {
+                                         double sigma, const double* lam_prev, HBlocks* hb = nullptr) {
     const int N = L.N, n = L.n, ld = L.nv, tid = blk.tid(), nt = blk.nthreads();
+    const int nblk = N * (N + 1) / 2;
     if (hb) hb->fast = false;
+    const int ldp = 7 * N + 1;                     // panel row length: block column b starts at 7 b (6 + 1 pad -> lanes of
+                                                   // neighbouring blocks are an odd number of doubles apart: no bank conflicts)
+    const size_t panel_doubles = (size_t)64 * ldp + (size_t)N * FTMPC_NE + 90;
     if (!condense_fast_path(L, nt)) {              // very short / long horizons: generic path
-        condense<CudaBlock>(blk, cfg, L, s, Jz, Wz_in, X, U, xref, gradV, hessV, theta, sigma, lam_prev_g);
+        condense<CudaBlock>(blk, cfg, L, s, Jz, Wz_in, X, U, xref, gradV, hessV, theta, sigma, lam_prev);
         return;
     }
-    const int ldp = 7 * N + 1;                     // panel row length: block column b starts at 7 b (6 + 1 pad: lanes of
-                                                   // neighbouring blocks are an odd number of doubles apart)
     double* Wp = const_cast<double*>(Wz_in);       // scratch copy owned by the caller: symmetrised / scaled in place
     double* buf0 = s.E;                            // panel b: rows 0-12 G_t, 13-25 M_t G_t, 26-31 theta W_ux G_t
     double* qe = s.E + (size_t)64 * ldp;           // [N][9]   2 Q (x_t - xr_t)
     double* Ht = qe + (size_t)N * FTMPC_NE;        // [9][9]   terminal Hessian model (+ augmentation)
     double* tgv = Ht + 81;                         // [9]      augmentation of the terminal gradient
-    double* lam_prev = tgv + 9;                    // [mc]     shared-memory copy of the previous multipliers
     const double* Ah = s.hull;
-    // ---- pre-pass: W' = theta * sym(W) (+ 2Q on the omega diagonal), qe, multipliers
+    // ---- pre-pass: W' = theta * sym(W) (+ 2Q on the omega diagonal), qe, Ht
     for (int idx = tid; idx < N * 169; idx += nt) {
         const int t = idx / 169, e = idx - t * 169;
         const int c = e / 13, r = e - c * 13;
@@ -1008,64 +997,53 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
         const int t = idx / FTMPC_NE, kk = idx - t * FTMPC_NE;
         qe[idx] = 2.0 * cfg.Q[kk] * (X[t * FTMPC_NX + kk] - xref[t * FTMPC_NE + kk]);
     }
-    if (sigma > 0.0) for (int i = tid; i < L.mc; i += nt) lam_prev[i] = lam_prev_g[i];
-    if (tid == 0) { s.g[n] = 0.0; s.ga[n] = 0.0; }
-    for (int r = tid; r < FTMPC_NX; r += nt) s.G[r * ld + n] = 0.0;
-    blk.sync();
-    // terminal model Ht = quad + theta (hessV - quad) + sigma sum_A a_i a_i'  (rows of A_f have <= 2 non-zeros)
     for (int idx = tid; idx < 90; idx += nt) {
         double v = 0.0;
         const int kk = idx / 9, l = idx - kk * 9;
         if (sigma > 0.0) {
-            const double* Af = s.cg->Af;
+            const double* Af = cfg.Af;
             for (int i = 0; i < FTMPC_NF; ++i) {
                 if (lam_prev[FTMPC_NH * N + i] > 0.0) {
-                    const double al = Af[i * FTMPC_NE + l];
-                    if (al != 0.0) v += (idx < 81) ? Af[i * FTMPC_NE + kk] * al : s.cv[FTMPC_NH * N + i] * al;
+                    const double a = Af[i * FTMPC_NE + l];
+                    v += (idx < 81) ? Af[i * FTMPC_NE + kk] * a : s.cv[FTMPC_NH * N + i] * a;
                 }
             }
             v *= sigma;
         }
         if (idx < 81) {
-            const double q0 = s.cg->term_quad[idx];
+            const double q0 = cfg.term_quad[idx];
             Ht[idx] = q0 + theta * (hessV[idx] - q0) + v;
         } else {
             tgv[l] = v;
         }
     }
+    if (tid == 0) { s.g[n] = 0.0; s.ga[n] = 0.0; }
+    for (int r = tid; r < FTMPC_NX; r += nt) s.G[r * ld + n] = 0.0;
     // ---- roles
-    const int half = nt >> 1;
-    const bool is_col = tid >= half && tid - half < n;
-    const int a = tid - half;                      // column role
-    const int ta = is_col ? a / FTMPC_NU : 0, ja = is_col ? a - ta * FTMPC_NU : 0;
+    const int a = tid;                             // column role (a < n)
+    const int ta = a / FTMPC_NU, ja = a - ta * FTMPC_NU;
     const int pa_ = 7 * ta + ja;                   // column a inside a panel
-    int bp = -1, bj = 0;                           // block role: pair bp (block rows 2bp, 2bp+1), block column bj
-    if (tid < condense_ntall(N)) {
-        bp = (int)((sqrtf(4.0f * tid + 1.0f) - 1.0f) * 0.5f);
-        while ((bp + 1) * (bp + 2) <= tid) ++bp;
-        while (bp * (bp + 1) > tid) --bp;
-        bj = tid - bp * (bp + 1);
+    int bi = -1, bj = 0;                           // block role (tid < nblk)
+    if (tid < nblk) {
+        bi = (int)((sqrt(8.0 * tid + 1.0) - 1.0) * 0.5);
+        while ((bi + 1) * (bi + 2) / 2 <= tid) ++bi;
+        while (bi * (bi + 1) / 2 > tid) --bi;
+        bj = tid - bi * (bi + 1) / 2;
     }
-    const int bt = 2 * bp, bb = 2 * bp + 1;        // top / bottom block rows (bb may be >= N)
-    blk.sync();
-    blk.mark(PH_COND_PRE);
-    // The two roles run as two separate loops that meet at a named barrier once per stage (bar.sync 1 counts
-    // arrivals, the arriving instruction need not be the same).  Keeping them apart lets the compiler allocate the
-    // registers of the larger role instead of the sum of both.
-    // Software pipeline: iteration `it` = column phase of stage it || block phase of stage it - 1.
-    double acc[12][6];
+    double g[FTMPC_NX], gs = 0.0, gaug = 0.0;
+    double acc[6][6];
 #pragma unroll
-    for (int i = 0; i < 12; ++i)
+    for (int i = 0; i < FTMPC_NX; ++i) g[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
 #pragma unroll
         for (int j = 0; j < 6; ++j) acc[i][j] = 0.0;
-    if (tid >= half) {
-        double g[FTMPC_NX], gs = 0.0, gaug = 0.0;
-#pragma unroll
-        for (int i = 0; i < FTMPC_NX; ++i) g[i] = 0.0;
-        for (int it = 0; it <= N + 1; ++it) {
-        if (is_col && it <= N) {
-            const int t = it;
-            double* buf = buf0 + (size_t)(t & 1) * 32 * ldp;
+    blk.sync();
+    blk.mark(PH_COND_PRE);
+    for (int t = 0; t <= N; ++t) {
+        double* buf = buf0 + (size_t)(t & 1) * 32 * ldp;
+        // ---------------- column phase
+        if (a < n) {
             if (ta < t) {
                 if (t < N) {
                     const double* jz = Jz + (size_t)t * 169;
@@ -1136,121 +1114,76 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
                 }
             }
         }
-            asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory");
-        }
-    } else {
-        for (int it = 0; it <= N + 1; ++it) {
-        if (bp >= 0 && it >= 1) {
-            const int t = it - 1;
-            const double* buf = buf0 + (size_t)(t & 1) * 32 * ldp;
-            const bool top_acc = bt < t && bj <= bt, bot_acc = bb < t && bb < N;
-            if (top_acc || bot_acc) {
+        blk.sync();
+        blk.mark(PH_COND_COL);
+        // ---------------- block phase
+        if (bi >= 0) {
+            if (bi < t) {
                 const int K = (t < N) ? FTMPC_NX : FTMPC_NE;
-                const double* Pt = buf + 7 * bt;
-                const double* Pb = buf + 7 * bb;
+                const double* Pa = buf + 7 * bi;
                 const double* Tb = buf + (size_t)13 * ldp + 7 * bj;
                 for (int r = 0; r < K; ++r) {
-                    double tb[6];
+                    double pa[6], tb[6];
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) tb[j] = Tb[(size_t)r * ldp + j];
-                    if (top_acc) {
-                        double pa[6];
+                    for (int i = 0; i < 6; ++i) { pa[i] = Pa[(size_t)r * ldp + i]; tb[i] = Tb[(size_t)r * ldp + i]; }
 #pragma unroll
-                        for (int i = 0; i < 6; ++i) pa[i] = Pt[(size_t)r * ldp + i];
+                    for (int i = 0; i < 6; ++i)
 #pragma unroll
-                        for (int i = 0; i < 6; ++i)
-#pragma unroll
-                            for (int j = 0; j < 6; ++j) acc[i][j] += pa[i] * tb[j];
-                    }
-                    if (bot_acc) {
-                        double pb[6];
-#pragma unroll
-                        for (int i = 0; i < 6; ++i) pb[i] = Pb[(size_t)r * ldp + i];
-#pragma unroll
-                        for (int i = 0; i < 6; ++i)
-#pragma unroll
-                            for (int j = 0; j < 6; ++j) acc[6 + i][j] += pb[i] * tb[j];
-                    }
+                        for (int j = 0; j < 6; ++j) acc[i][j] += pa[i] * tb[j];
                 }
-            }
-            // initialisation of the block row that becomes live at stage t (t < N)
+            } else if (bi == t) {
+                if (bj < t) {
+                    // new block row: theta W_ux G_t   (row i of the block <- input i, column j <- column 6 bj + j)
 #pragma unroll
-            for (int hseg = 0; hseg < 2; ++hseg) {
-                const int rb = hseg ? bb : bt;
-                if (rb == t && t < N && bj <= rb) {
-                    if (bj < t) {
-                        // new block row: theta W_ux G_t   (row i <- input i, column j <- column 6 bj + j)
+                    for (int i = 0; i < 6; ++i)
 #pragma unroll
-                        for (int i = 0; i < 6; ++i)
+                        for (int j = 0; j < 6; ++j) acc[i][j] = buf[(size_t)(26 + i) * ldp + 7 * bj + j];
+                } else {
+                    const double* wp = Wp + (size_t)t * 169;
 #pragma unroll
-                            for (int j = 0; j < 6; ++j) acc[6 * hseg + i][j] = buf[(size_t)(26 + i) * ldp + 7 * bj + j];
-                    } else {
-                        const double* wp = Wp + (size_t)t * 169;
+                    for (int i = 0; i < 6; ++i)
 #pragma unroll
-                        for (int i = 0; i < 6; ++i)
+                        for (int j = 0; j < 6; ++j) {
+                            double v = wp[(7 + i) * 13 + 7 + j];
+                            if (i == j) v += 2.0 * cfg.R[i];
+                            acc[i][j] = v;
+                        }
+                    if (sigma > 0.0) {
+                        for (int r = 0; r < FTMPC_NH; ++r) {
+                            if (lam_prev[t * FTMPC_NH + r] > 0.0) {
 #pragma unroll
-                            for (int j = 0; j < 6; ++j) {
-                                double v = wp[(7 + i) * 13 + 7 + j];
-                                if (i == j) v += 2.0 * cfg.R[i];
-                                acc[6 * hseg + i][j] = v;
-                            }
-                        if (sigma > 0.0) {
-                            for (int r = 0; r < FTMPC_NH; ++r) {
-                                if (lam_prev[t * FTMPC_NH + r] > 0.0) {
+                                for (int i = 0; i < 6; ++i)
 #pragma unroll
-                                    for (int i = 0; i < 6; ++i)
-#pragma unroll
-                                        for (int j = 0; j < 6; ++j)
-                                            acc[6 * hseg + i][j] += sigma * Ah[r * FTMPC_NU + i] * Ah[r * FTMPC_NU + j];
-                                }
+                                    for (int j = 0; j < 6; ++j) acc[i][j] += sigma * Ah[r * FTMPC_NU + i] * Ah[r * FTMPC_NU + j];
                             }
                         }
                     }
                 }
             }
         }
-            asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory");
-            blk.mark(PH_COND_BLK);
-        }
+        blk.mark(PH_COND_BLK);                     // thread 0 owns block (0,0), the longest-lived accumulator
     }
-    blk.sync();
-    // the panels are dead: store H (lower triangle)
-    if (bp >= 0) {
-#pragma unroll
-        for (int i = 0; i < 12; ++i) {
-            const int rb = (i < 6) ? bt : bb;
-            if (rb < N && bj <= rb) {
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    const int ra = 6 * bt + i, cb = 6 * bj + j;
-                    if (cb <= ra) s.E[(size_t)ra * ld + cb] = acc[i][j];
-                }
-            }
-        }
-    }
-    blk.sync();
-    if (hb) {                                      // 6x6 owners pick their blocks up in registers
+    blk.sync();                                    // the panels are dead
+    if (hb) {                                      // hand the blocks over in registers
         hb->fast = true;
-        int bi6 = -1, bj6 = 0;
-        if (tid < N * (N + 1) / 2) {
-            bi6 = (int)((sqrtf(8.0f * tid + 1.0f) - 1.0f) * 0.5f);
-            while ((bi6 + 1) * (bi6 + 2) / 2 <= tid) ++bi6;
-            while (bi6 * (bi6 + 1) / 2 > tid) --bi6;
-            bj6 = tid - bi6 * (bi6 + 1) / 2;
-        }
-        hb->bi = bi6;
-        hb->bj = bj6;
-        if (bi6 >= 0) {
+        hb->bi = bi;
+        hb->bj = bj;
 #pragma unroll
-            for (int i = 0; i < 6; ++i)
+        for (int i = 0; i < 6; ++i)
 #pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    const int ra = 6 * bi6 + i, cb = 6 * bj6 + j;
-                    hb->acc[i][j] = (cb <= ra) ? s.E[(size_t)ra * ld + cb] : 0.0;
-                }
-        }
-        blk.sync();                                // E is about to be overwritten by the factorisation
+            for (int j = 0; j < 6; ++j) hb->acc[i][j] = acc[i][j];
+        return;
     }
+    if (bi >= 0) {                                 // store H (lower triangle)
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const int ra = 6 * bi + i, cb = 6 * bj + j;
+                if (cb <= ra) s.E[(size_t)ra * ld + cb] = acc[i][j];
+            }
+    }
+    blk.sync();
 }
 
 // ---- register-resident block Cholesky + L^-T ------------------------------------------------------------
@@ -1347,30 +1280,25 @@ __device__ __forceinline__ int chol_inv_blocks(CudaBlock& blk, int Nb, int ld, d
         }
         blk.sync();
         if (bi >= 0 && bj > k) {
-            // two passes over the column halves keep the live set at acc + 18 + 6 doubles (a full 6x6 operand tile
-            // next to the accumulators spills inside the persistent kernel)
+            double Lb[6][6];
 #pragma unroll
-            for (int jh = 0; jh < 6; jh += 3) {
-                double Lb[3][6];
+            for (int j = 0; j < 6; ++j) {
+                const double* er = E + (size_t)(6 * bj + j) * ld + 6 * k;
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const double* er = E + (size_t)(6 * bj + jh + j) * ld + 6 * k;
+                for (int m = 0; m < 6; ++m) Lb[j][m] = er[m];
+            }
 #pragma unroll
-                    for (int m = 0; m < 6; ++m) Lb[j][m] = er[m];
-                }
+            for (int i = 0; i < 6; ++i) {
+                const double* er = E + (size_t)(6 * bi + i) * ld + 6 * k;
+                double La[6];
 #pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    const double* er = E + (size_t)(6 * bi + i) * ld + 6 * k;
-                    double La[6];
+                for (int m = 0; m < 6; ++m) La[m] = er[m];
 #pragma unroll
-                    for (int m = 0; m < 6; ++m) La[m] = er[m];
+                for (int j = 0; j < 6; ++j) {
+                    double v = acc[i][j];
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        double v = acc[i][jh + j];
-#pragma unroll
-                        for (int m = 0; m < 6; ++m) v -= La[m] * Lb[j][m];
-                        acc[i][jh + j] = v;
-                    }
+                    for (int m = 0; m < 6; ++m) v -= La[m] * Lb[j][m];
+                    acc[i][j] = v;
                 }
             }
         }
@@ -1384,28 +1312,25 @@ __device__ __forceinline__ int chol_inv_blocks(CudaBlock& blk, int Nb, int ld, d
     for (int sdist = 1; sdist < Nb; ++sdist) {
         if (bi >= 0 && bi - bj >= sdist) {
             const int kb = bj + sdist - 1;
+            double Xb[6][6];                               // Xb[b][m] = X_{kb,bj}[m][b]
 #pragma unroll
-            for (int bh = 0; bh < 6; bh += 3) {
-                double Xb[3][6];                           // Xb[b][m] = X_{kb,bj}[m][bh + b]
+            for (int b = 0; b < 6; ++b) {
+                const double* er = E + (size_t)(6 * bj + b) * ld + 6 * kb;
 #pragma unroll
-                for (int b = 0; b < 3; ++b) {
-                    const double* er = E + (size_t)(6 * bj + bh + b) * ld + 6 * kb;
+                for (int m = 0; m < 6; ++m) Xb[b][m] = er[m];
+            }
 #pragma unroll
-                    for (int m = 0; m < 6; ++m) Xb[b][m] = er[m];
-                }
+            for (int a = 0; a < 6; ++a) {
+                const double* er = E + (size_t)(6 * bi + a) * ld + 6 * kb;
+                double La[6];
 #pragma unroll
-                for (int a = 0; a < 6; ++a) {
-                    const double* er = E + (size_t)(6 * bi + a) * ld + 6 * kb;
-                    double La[6];
+                for (int m = 0; m < 6; ++m) La[m] = er[m];
 #pragma unroll
-                    for (int m = 0; m < 6; ++m) La[m] = er[m];
+                for (int b = 0; b < 6; ++b) {
+                    double v = acc[a][b];
 #pragma unroll
-                    for (int b = 0; b < 3; ++b) {
-                        double v = acc[a][bh + b];
-#pragma unroll
-                        for (int m = 0; m < 6; ++m) v += La[m] * Xb[b][m];
-                        acc[a][bh + b] = v;
-                    }
+                    for (int m = 0; m < 6; ++m) v += La[m] * Xb[b][m];
+                    acc[a][b] = v;
                 }
             }
             if (bi - bj == sdist) {
@@ -1501,7 +1426,7 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     double* sc = w + L.oSc;
     if (sc[SC_STATUS] != FTMPC_ST_RUNNING) return;
     const int N = L.N, n = L.n, nv = L.nv, ne = nv + FTMPC_NE, ld = nv, tid = blk.tid(), nt = blk.nthreads();
-    const QpScratch s = qp_carve(scratch, N, io.cfg_g);
+    const QpScratch s = qp_carve(scratch, N);
     const double* xref = io.xref + (size_t)inst * (N + 1) * FTMPC_NE;
     const double* hull_g = io.hull_table + (size_t)io.hull_idx[inst] * FTMPC_HULL_STRIDE;
     // stage data -> scratch (the R^-1 region is free until the active-set solve starts)
