@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
     CudaBlock blk(red);
     const int N = L.N, n = L.n, ld = L.nv;
     for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
-        const QpScratch s = qp_carve(scratch, N);
+        const QpScratch s = qp_carve(scratch, N, cfg);
         double* Jz = s.RS;
         double* Wz = s.RS + (size_t)N * 169;
         for (int i = threadIdx.x; i < N * 169; i += blockDim.x) {

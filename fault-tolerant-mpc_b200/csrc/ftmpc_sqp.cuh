@@ -28,7 +28,7 @@ struct WsLayout {
 };
 enum {      // scalar slots
     SC_F = 0, SC_CSUM, SC_NU, SC_GD, SC_THETA, SC_DMAX, SC_DELTA, SC_LAMMAX, SC_STATUS, SC_ITER, SC_QPIT,
-    SC_NACT, SC_CHOLFAIL, SC_QPST, SC_ALPHA, SC_CMAX, SC_SIGMA, SC_COUNT
+    SC_NACT, SC_CHOLFAIL, SC_QPST, SC_ALPHA, SC_CMAX, SC_SIGMA, SC_HFAIL, SC_COUNT
 };
 FT_HD WsLayout ws_layout(int N) {
     WsLayout L;
@@ -606,6 +606,7 @@ struct MpcCons {
 
 // per-CTA scratch carved out of one buffer of doubles (shared memory on the device)
 struct QpScratch {
+    const ftmpc_config* cg;      // configuration copy addressable per thread (global memory on the device)
     double *E, *RS, *G, *T, *g, *ga, *taug, *cv, *hull;
     GiWork gi;
     double* dg;
@@ -622,10 +623,11 @@ FT_HD size_t qp_scratch_doubles(int N) {
     size_t ints = ((nv + 1) + L.m + (nv + 1) + 1) / 2 + 1;
     return ne * nv + rs + (size_t)FTMPC_NX * nv + gi_vec + 2 * nv /*g, ga*/ + 90 /*taug*/ + L.mc /*cv*/ + FTMPC_HULL_STRIDE + ints + 8;
 }
-FT_HD QpScratch qp_carve(double* buf, int N) {
+FT_HD QpScratch qp_carve(double* buf, int N, const ftmpc_config* cg = nullptr) {
     const WsLayout L = ws_layout(N);
     const size_t nv = L.nv, ne = nv + FTMPC_NE, n = L.n;
     QpScratch s;
+    s.cg = cg;
     double* p = buf;
     s.E = p; p += ne * nv;
     size_t rs = nv * (nv + 1) / 2;
@@ -874,6 +876,11 @@ __device__ __forceinline__ void phase_lin(CudaBlock& blk, const ftmpc_config& cf
 #pragma unroll
         for (int i = 0; i < 13; ++i) { js[i] = jc[i]; jg[i] = jc[i]; }
     }
+    // running-cost gradient 2Q (x_t - xr_t) of every stage, parked in the (not yet used) costate slots
+    for (int i = tid; i < N * FTMPC_NX; i += nt) {
+        const int t = i / FTMPC_NX, r = i - t * FTMPC_NX;
+        s.mu[i] = (r < FTMPC_NE) ? 2.0 * cfg.Q[r] * (s.X[i] - xref[t * FTMPC_NE + r]) : 0.0;
+    }
     // terminal costate  mu_N = [grad V_f + A_f' lam_term ; 0]   (threads from the other end of the block)
     for (int i = nt - 1 - tid; i < FTMPC_NX; i += nt) {
         double v = 0.0;
@@ -898,7 +905,7 @@ __device__ __forceinline__ void phase_lin(CudaBlock& blk, const ftmpc_config& cf
             const double* mn = s.mu + (t + 1) * FTMPC_NX;
             if (tid < FTMPC_NX) {
                 const int i = tid;
-                double v = (i < FTMPC_NE) ? 2.0 * cfg.Q[i] * (s.X[t * FTMPC_NX + i] - xref[t * FTMPC_NE + i]) : 0.0;
+                double v = s.mu[t * FTMPC_NX + i];
                 if (i < 3) v += mn[i];
                 else if (i < 6) v += k.dt * mn[i - 3] + mn[i];
                 else {
@@ -1001,7 +1008,7 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
         double v = 0.0;
         const int kk = idx / 9, l = idx - kk * 9;
         if (sigma > 0.0) {
-            const double* Af = cfg.Af;
+            const double* Af = s.cg->Af;
             for (int i = 0; i < FTMPC_NF; ++i) {
                 if (lam_prev[FTMPC_NH * N + i] > 0.0) {
                     const double a = Af[i * FTMPC_NE + l];
@@ -1011,7 +1018,7 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
             v *= sigma;
         }
         if (idx < 81) {
-            const double q0 = cfg.term_quad[idx];
+            const double q0 = s.cg->term_quad[idx];
             Ht[idx] = q0 + theta * (hessV[idx] - q0) + v;
         } else {
             tgv[l] = v;
@@ -1426,7 +1433,7 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     double* sc = w + L.oSc;
     if (sc[SC_STATUS] != FTMPC_ST_RUNNING) return;
     const int N = L.N, n = L.n, nv = L.nv, ne = nv + FTMPC_NE, ld = nv, tid = blk.tid(), nt = blk.nthreads();
-    const QpScratch s = qp_carve(scratch, N);
+    const QpScratch s = qp_carve(scratch, N, io.cfg_g);
     const double* xref = io.xref + (size_t)inst * (N + 1) * FTMPC_NE;
     const double* hull_g = io.hull_table + (size_t)io.hull_idx[inst] * FTMPC_HULL_STRIDE;
     // stage data -> scratch (the R^-1 region is free until the active-set solve starts)
@@ -1440,8 +1447,13 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     const double* lam_prev = w + L.oLam;
     const bool can_aug = (sc[SC_ITER] > 0.0 || sc[SC_THETA] >= 0.0) && sc[SC_CSUM] <= 1e-6;
     double theta = sc[SC_THETA], sigma = 0.0;
-    theta = (theta < 0.0) ? 0.0 : ((theta == 0.0) ? 0.125 : fmin(1.0, 2.0 * theta));
+    theta = (theta < 0.0) ? 0.0 : ((theta == 0.0) ? cfg.theta_first : fmin(1.0, cfg.theta_growth * theta));
     if (can_aug && sc[SC_SIGMA] > 0.0) { theta = 1.0; sigma = sc[SC_SIGMA]; }
+    // while the iterate is still infeasible the exact Hessian is almost always indefinite and no convexification is
+    // allowed: once an attempt has fallen all the way back to Gauss-Newton, do not pay for the failing attempts again
+    // until feasibility is reached
+    const bool skip_exact = cfg.poll_every == 0 && sc[SC_HFAIL] != 0.0 && sc[SC_CSUM] > 1e-6;
+    if (skip_exact) theta = 0.0;
     bool aug_allowed = can_aug;
     int fails = 0, qit = 0, nact = 0, st = GI_OK;
     for (;;) {        // QP attempts (re-solved without augmentation if a predicted-active row came out inactive)
@@ -1529,6 +1541,7 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     if (tid == 0) {
         w[L.oD + n] = s.gi.xe[n];
         sc[SC_GD] = gd; sc[SC_DMAX] = dmx; sc[SC_LAMMAX] = lmx; sc[SC_DELTA] = s.gi.xe[n];
+        sc[SC_HFAIL] = (skip_exact || (fails > 0 && theta == 0.0)) ? 1.0 : 0.0;
         sc[SC_THETA] = theta; sc[SC_SIGMA] = sigma; sc[SC_QPIT] += qit; sc[SC_NACT] = nact; sc[SC_CHOLFAIL] += fails;
         sc[SC_QPST] = (st == GI_OK && dmx == dmx) ? 0.0 : (double)(st ? st : 4);
     }
