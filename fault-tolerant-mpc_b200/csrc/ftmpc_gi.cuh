@@ -330,6 +330,9 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
                                         int meq, double* lam, int maxit, double tol, int* iters_out, int* nact_out) {
     const int tid = blk.tid(), nt = blk.nthreads(), lane = tid & 31, warp = tid >> 5, nw = (nt + 31) >> 5;
     double* gsc = blk.scratch + 128;              // 64 doubles of block scratch reserved for this routine
+    // rows of E: the first `npair` rows are handled by lane pairs (each lane half of the columns), the rest by whole warps
+    const int npair = (ne < (nt >> 1)) ? ne : (nt >> 1);
+    const int prow = tid >> 1, phalf = tid & 1;
     int q = 0, iters = 0, status = GI_OK;
     for (int i = tid; i < m; i += nt) {
         w.s[i] = cons.slack(i, w.xe, 1.0);
@@ -337,6 +340,9 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
     }
     blk.sync();
     int eq_next = 0;
+    bool have_next = false;                       // most violated row already known from the previous full step
+    double next_best = 0.0;
+    int next_bi = 0x7fffffff;
     for (;;) {
         // ---- choose the constraint to add: pending equalities first, then the most violated row
         int p = -1;
@@ -347,19 +353,24 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
             sp = w.s[p];
             is_eq = true;
         } else {
-            double best = 0.0;
-            int bi = 0x7fffffff;
-            for (int i = meq + tid; i < m; i += nt) {
-                if (w.pos[i] < 0) {
-                    const double v = w.s[i];
-                    if (v < best || (v == best && i < bi)) { best = v; bi = i; }
+            double best = next_best;
+            int bi = next_bi;
+            if (!have_next) {
+                best = 0.0;
+                bi = 0x7fffffff;
+                for (int i = meq + tid; i < m; i += nt) {
+                    if (w.pos[i] < 0) {
+                        const double v = w.s[i];
+                        if (v < best || (v == best && i < bi)) { best = v; bi = i; }
+                    }
                 }
+                blk.argmin(best, bi);
             }
-            blk.argmin(best, bi);
             if (bi == 0x7fffffff || best >= -tol) break;      // primal feasible -> optimal
             p = bi;
             sp = best;
         }
+        have_next = false;
         blk.mark(PH_GI_SELECT);
         SparseRow np;
         cons.row(p, np);
@@ -398,10 +409,23 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
             blk.mark(PH_GI_D);
             double dn = 0.0, d2n = 0.0;
             for (int i = 0; i < nw; ++i) { dn += gsc[i]; d2n += gsc[32 + i]; }
-            // ze = E[:, q:] d[q:]  (threads from the front)   r = R^-1 d[:q]  (threads from the back)
-            for (int row = tid; row < ne; row += nt) {
-                w.ze[row] = dot_ilp(w.E + (size_t)row * ld, w.d, q, nv);
+            // ze = E[:, q:] d[q:]
+            const int mid = q + ((nv - q + 1) >> 1);
+            {
+                double v = 0.0;
+                if (prow < npair) v = dot_ilp(w.E + (size_t)prow * ld, w.d, phalf ? mid : q, phalf ? nv : mid);
+                v += __shfl_xor_sync(0xffffffffu, v, 1);       // every lane takes part (inactive pairs carry zeros)
+                if (prow < npair && !phalf) w.ze[prow] = v;
             }
+            for (int row = npair + warp; row < ne; row += nw) {
+                const double* e = w.E + (size_t)row * ld;
+                double v = 0.0;
+                for (int k = q + lane; k < nv; k += 32) v += e[k] * w.d[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) w.ze[row] = v;
+            }
+            // r = R^-1 d[:q] and the dual step length
             double t1 = INFINITY;
             int l = 0x7fffffff;
             for (int j = nt - 1 - tid; j < q; j += nt) {
@@ -437,13 +461,21 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
                 blk.count(CT_GI_DROP);
                 continue;
             }
+            const bool full = (t == t2);
             for (int i = tid; i < ne; i += nt) w.xe[i] += t * w.ze[i];
             for (int j = tid; j <= q; j += nt) w.u[j] += t * ((j < q) ? -w.r[j] : 1.0);
-            for (int i = tid; i < m; i += nt) w.s[i] += t * cons.slack(i, w.ze, 0.0);
+            // slack update; on a full step the same sweep finds the most violated remaining row for the next pass
+            double nb = 0.0;
+            int nbi = 0x7fffffff;
+            for (int i = tid; i < m; i += nt) {
+                const double v = w.s[i] + t * cons.slack(i, w.ze, 0.0);
+                w.s[i] = v;
+                if (i >= meq && i != p && w.pos[i] < 0 && (v < nb || (v == nb && i < nbi))) { nb = v; nbi = i; }
+            }
             sp += t * d2n;
             blk.sync();
             blk.mark(PH_GI_STEP);
-            if (t == t2) {
+            if (full) {
                 const double alpha = sqrt(d2n);
                 const double d0 = w.d[q];
                 const double sg = (d0 >= 0.0) ? 1.0 : -1.0;
@@ -451,11 +483,25 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
                 const double rho = -sg * alpha;
                 if (vv > 0.0) {
                     const double f = 2.0 / vv;
-                    for (int row = tid; row < ne; row += nt) {
+                    {
+                        double* e = w.E + (size_t)((prow < npair) ? prow : 0) * ld;
+                        const double wv = f * (w.ze[(prow < npair) ? prow : 0] + sg * alpha * e[q]);
+                        __syncwarp();                              // both lanes of a pair have read e[q]
+                        if (prow < npair) {
+                            if (!phalf) {
+                                e[q] -= wv * (d0 + sg * alpha);
+                                axpy_ilp(e, w.d, wv, q + 1, mid);
+                            } else {
+                                axpy_ilp(e, w.d, wv, (mid > q + 1) ? mid : q + 1, nv);
+                            }
+                        }
+                    }
+                    for (int row = npair + warp; row < ne; row += nw) {
                         double* e = w.E + (size_t)row * ld;
                         const double wv = f * (w.ze[row] + sg * alpha * e[q]);
-                        e[q] -= wv * (d0 + sg * alpha);
-                        axpy_ilp(e, w.d, wv, q + 1, nv);
+                        __syncwarp();
+                        if (lane == 0) e[q] -= wv * (d0 + sg * alpha);
+                        for (int k = q + 1 + lane; k < nv; k += 32) e[k] -= wv * w.d[k];
                     }
                 }
                 double* col = w.Ui + gi_tri(q);
@@ -465,7 +511,10 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
                     w.act[q] = p;
                     w.pos[p] = q;
                 }
-                blk.sync();
+                blk.argmin(nb, nbi);                               // barrier of the update + next selection in one
+                next_best = nb;
+                next_bi = nbi;
+                have_next = eq_next >= meq;
                 blk.mark(PH_GI_UPD);
                 q += 1;
                 added = true;

@@ -1470,7 +1470,7 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         else if (sigma > 0.0 && sig0 > 0.0 && sigma < 50.0 * sig0) sigma *= 10.0;
         else if (sigma > 0.0) { sigma = 0.0; theta = 0.5; aug_allowed = false; }
         else if (theta <= 0.0) { if (tid == 0) { sc[SC_QPST] = 3.0; } return; }
-        else theta = (theta > 0.125) ? 0.5 * theta : 0.0;
+        else theta = (theta > cfg.theta_first) ? 0.5 * theta : 0.0;      // below the first blend level: Gauss-Newton
     }
     // slack variable column/row, extension rows  X J  (X = d x_N[0:9] / d U)
     for (int i = tid; i < nv; i += nt) {

@@ -79,7 +79,7 @@ typedef struct ftmpc_config {
     double rho_slack;          /* weight of the QP elastic variable (default 1e4)                           */
     double clip_tol;           /* hull membership tolerance of clip_generalized_input (default 1e-9)        */
     double theta_first;        /* Hessian schedule: blend of exact second-order terms in SQP iteration 1 (iteration 0 is   */
-    double theta_growth;       /* Gauss-Newton), multiplied by theta_growth per iteration up to 1 (defaults 0.25, 2)       */
+    double theta_growth;       /* Gauss-Newton), multiplied by theta_growth per iteration up to 1 (defaults 0.5, 2)       */
 } ftmpc_config;
 
 typedef struct ftmpc_ctx* ftmpc_handle;
