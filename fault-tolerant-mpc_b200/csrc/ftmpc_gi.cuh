@@ -330,9 +330,6 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
                                         int meq, double* lam, int maxit, double tol, int* iters_out, int* nact_out) {
     const int tid = blk.tid(), nt = blk.nthreads(), lane = tid & 31, warp = tid >> 5, nw = (nt + 31) >> 5;
     double* gsc = blk.scratch + 128;              // 64 doubles of block scratch reserved for this routine
-    // rows of E: the first `npair` rows are handled by lane pairs (each lane half of the columns), the rest by whole warps
-    const int npair = (ne < (nt >> 1)) ? ne : (nt >> 1);
-    const int prow = tid >> 1, phalf = tid & 1;
     int q = 0, iters = 0, status = GI_OK;
     for (int i = tid; i < m; i += nt) {
         w.s[i] = cons.slack(i, w.xe, 1.0);
@@ -409,22 +406,9 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
             blk.mark(PH_GI_D);
             double dn = 0.0, d2n = 0.0;
             for (int i = 0; i < nw; ++i) { dn += gsc[i]; d2n += gsc[32 + i]; }
-            // ze = E[:, q:] d[q:]
-            const int mid = q + ((nv - q + 1) >> 1);
-            {
-                double v = 0.0;
-                if (prow < npair) v = dot_ilp(w.E + (size_t)prow * ld, w.d, phalf ? mid : q, phalf ? nv : mid);
-                v += __shfl_xor_sync(0xffffffffu, v, 1);       // every lane takes part (inactive pairs carry zeros)
-                if (prow < npair && !phalf) w.ze[prow] = v;
-            }
-            for (int row = npair + warp; row < ne; row += nw) {
-                const double* e = w.E + (size_t)row * ld;
-                double v = 0.0;
-                for (int k = q + lane; k < nv; k += 32) v += e[k] * w.d[k];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) w.ze[row] = v;
-            }
+            // ze = E[:, q:] d[q:]  (thread per row: a lane-pair split was measured slower -- the two halves of a row
+            // land on the same banks as their neighbours and double the shared-memory wavefronts)
+            for (int row = tid; row < ne; row += nt) w.ze[row] = dot_ilp(w.E + (size_t)row * ld, w.d, q, nv);
             // r = R^-1 d[:q] and the dual step length
             double t1 = INFINITY;
             int l = 0x7fffffff;
@@ -483,25 +467,11 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
                 const double rho = -sg * alpha;
                 if (vv > 0.0) {
                     const double f = 2.0 / vv;
-                    {
-                        double* e = w.E + (size_t)((prow < npair) ? prow : 0) * ld;
-                        const double wv = f * (w.ze[(prow < npair) ? prow : 0] + sg * alpha * e[q]);
-                        __syncwarp();                              // both lanes of a pair have read e[q]
-                        if (prow < npair) {
-                            if (!phalf) {
-                                e[q] -= wv * (d0 + sg * alpha);
-                                axpy_ilp(e, w.d, wv, q + 1, mid);
-                            } else {
-                                axpy_ilp(e, w.d, wv, (mid > q + 1) ? mid : q + 1, nv);
-                            }
-                        }
-                    }
-                    for (int row = npair + warp; row < ne; row += nw) {
+                    for (int row = tid; row < ne; row += nt) {
                         double* e = w.E + (size_t)row * ld;
                         const double wv = f * (w.ze[row] + sg * alpha * e[q]);
-                        __syncwarp();
-                        if (lane == 0) e[q] -= wv * (d0 + sg * alpha);
-                        for (int k = q + 1 + lane; k < nv; k += 32) e[k] -= wv * w.d[k];
+                        e[q] -= wv * (d0 + sg * alpha);
+                        axpy_ilp(e, w.d, wv, q + 1, nv);
                     }
                 }
                 double* col = w.Ui + gi_tri(q);

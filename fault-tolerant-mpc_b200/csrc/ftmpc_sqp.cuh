@@ -1455,7 +1455,7 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     const bool skip_exact = cfg.poll_every == 0 && sc[SC_HFAIL] != 0.0 && sc[SC_CSUM] > 1e-6;
     if (skip_exact) theta = 0.0;
     bool aug_allowed = can_aug;
-    int fails = 0, qit = 0, nact = 0, st = GI_OK;
+    int fails = 0, qit = 0, nact = 0, st = GI_OK, aug_retry = 0;
     for (;;) {        // QP attempts (re-solved without augmentation if a predicted-active row came out inactive)
     double sig0 = 0.0;
     for (;;) {
@@ -1520,7 +1520,21 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         int viol = 0;
         for (int i = tid; i < L.mc; i += nt)
             if (lam_prev[i] > 0.0 && s.gi.pos[i] < 0 && s.gi.s[i] > 1e-9) viol = 1;
-        if (blk.any(viol)) { sigma = 0.0; theta = 0.5; aug_allowed = false; ++fails; continue; }
+        if (blk.any(viol)) {
+            ++fails;
+            if (aug_retry < 2) {
+                // drop the rows that came out inactive from the predicted set and convexify again: the exact Hessian
+                // with the corrected set keeps the Newton-like rate, the theta = 1/2 fallback below does not
+                ++aug_retry;
+                double* lp = w + L.oLam;
+                for (int i = tid; i < L.mc; i += nt)
+                    if (lp[i] > 0.0 && s.gi.pos[i] < 0 && s.gi.s[i] > 1e-9) lp[i] = 0.0;
+                blk.sync();
+                continue;
+            }
+            sigma = 0.0; theta = 0.5; aug_allowed = false;
+            continue;
+        }
     }
     break;
     }
