@@ -1445,14 +1445,17 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     // Hessian schedule: exact second-order terms blended by theta; when the exact Hessian is indefinite,
     // first try the augmented-Lagrangian convexification (sigma > 0), then fall back to smaller theta.
     const double* lam_prev = w + L.oLam;
-    const bool can_aug = (sc[SC_ITER] > 0.0 || sc[SC_THETA] >= 0.0) && sc[SC_CSUM] <= 1e-6;
+    // the convexified QP equals the plain one whenever the predicted rows stay active, whatever the feasibility of the
+    // iterate; it is only kept away from the first, wildly infeasible iterations (elastic variable far from zero)
+    const double feas_aug = 1e-2;
+    const bool can_aug = (sc[SC_ITER] > 0.0 || sc[SC_THETA] >= 0.0) && sc[SC_CSUM] <= feas_aug;
     double theta = sc[SC_THETA], sigma = 0.0;
     theta = (theta < 0.0) ? 0.0 : ((theta == 0.0) ? cfg.theta_first : fmin(1.0, cfg.theta_growth * theta));
     if (can_aug && sc[SC_SIGMA] > 0.0) { theta = 1.0; sigma = sc[SC_SIGMA]; }
     // while the iterate is still infeasible the exact Hessian is almost always indefinite and no convexification is
     // allowed: once an attempt has fallen all the way back to Gauss-Newton, do not pay for the failing attempts again
     // until feasibility is reached
-    const bool skip_exact = cfg.poll_every == 0 && sc[SC_HFAIL] != 0.0 && sc[SC_CSUM] > 1e-6;
+    const bool skip_exact = cfg.poll_every == 0 && sc[SC_HFAIL] != 0.0 && sc[SC_CSUM] > feas_aug;
     if (skip_exact) theta = 0.0;
     bool aug_allowed = can_aug;
     int fails = 0, qit = 0, nact = 0, st = GI_OK, aug_retry = 0;

@@ -57,7 +57,7 @@ enum {
 typedef struct ftmpc_config {
     int32_t horizon;           /* N                                   reactive.yaml:26, spiraling_mpc.py:38 */
     int32_t dtype;             /* 0 = fp64 (only mode implemented)                                          */
-    int32_t max_sqp_iter;      /* outer iteration cap (default 40)                                          */
+    int32_t max_sqp_iter;      /* outer iteration cap (default 60)                                          */
     int32_t max_qp_iter;       /* active-set iteration cap per QP (default 20*(n+m))                        */
     int32_t poll_every;        /* reserved; non-zero disables the "skip exact-Hessian attempts while infeasible" heuristic (debugging) */
     int32_t n_poly, n_root, n_hull_sets;
