@@ -96,6 +96,13 @@ FT_HD void stage_wrench(const ftmpc_config& c, const double* u, const double* ur
     }
 }
 
+// SQP termination: the QP step is below sqp_tol, or it is within 100 sqp_tol AND the decrease it predicts is at the
+// rounding level of the objective (|g'd| <= 1e-13 max(1,|f|)): at that point the step is numerical noise of the
+// gradient divided by a small curvature and never shrinks further, although the iterate no longer moves.
+FT_HD bool sqp_step_converged(const ftmpc_config& cfg, double dmax, double gd, double f) {
+    return dmax <= cfg.sqp_tol || (dmax <= 100.0 * cfg.sqp_tol && fabs(gd) <= 1e-13 * fmax(1.0, fabs(f)));
+}
+
 // forward rollout at U + alpha*d: states, cost, constraint values (c <= 0 feasible).
 FT_HD void rollout_eval(const ftmpc_config& cfg, const WsLayout& L, const double* hull, const double* xref,
                         const double* uref, const double* U, const double* d, double alpha, double* X, double* C,
@@ -182,7 +189,7 @@ FT_HD void phase_ls(const ftmpc_config& cfg, const WsLayout& L, const StepIO& io
         sc[SC_ALPHA] = alpha;
         if (!(f < INFINITY)) { sc[SC_STATUS] = FTMPC_ST_QPFAIL; return; }
         for (int i = 0; i < L.n; ++i) U[i] += alpha * D[i];
-        if (sc[SC_DMAX] <= cfg.sqp_tol) {
+        if (sqp_step_converged(cfg, sc[SC_DMAX], sc[SC_GD], sc[SC_F])) {
             sc[SC_STATUS] = (cmax <= cfg.feas_tol) ? FTMPC_ST_OK : FTMPC_ST_INFEASIBLE;
         } else if (sc[SC_ITER] >= cfg.max_sqp_iter) {
             sc[SC_STATUS] = FTMPC_ST_MAXITER;
@@ -295,7 +302,7 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
     double* C = w + L.oC;
     const LsScratch s = ls_carve(scratch, N);
     const int nterm = cfg.n_poly + cfg.n_root;
-    double nu = 1.0, phi0 = 0.0, dphi = 0.0, dmax = 0.0, iter = 0.0;
+    double nu = 1.0, phi0 = 0.0, dphi = 0.0, dmax = 0.0, iter = 0.0, gd_prev = 0.0, f_prev = 0.0;
     if (first) {
         if (tid == 0) robot_to_center(dyn_consts(cfg), io.state + (size_t)inst * FTMPC_NX, X);      // spiraling_mpc.py:290
         const double* zw = io.z_warm + (size_t)inst * (L.n + (size_t)(N + 1) * FTMPC_NX);
@@ -312,6 +319,8 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
         phi0 = sc[SC_F] + nu * sc[SC_CSUM];
         dphi = sc[SC_GD] - nu * sc[SC_CSUM];
         dmax = sc[SC_DMAX];
+        gd_prev = sc[SC_GD];
+        f_prev = sc[SC_F];
         iter = sc[SC_ITER] + 1.0;
         blk.sync();                                   // everybody has read the scalars
         if (status != FTMPC_ST_RUNNING) return;
@@ -451,7 +460,7 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
             sc[SC_NU] = nu;
             sc[SC_ALPHA] = alpha;
             if (!finite) sc[SC_STATUS] = FTMPC_ST_QPFAIL;
-            else if (dmax <= cfg.sqp_tol) sc[SC_STATUS] = (cmax <= cfg.feas_tol) ? FTMPC_ST_OK : FTMPC_ST_INFEASIBLE;
+            else if (sqp_step_converged(cfg, dmax, gd_prev, f_prev)) sc[SC_STATUS] = (cmax <= cfg.feas_tol) ? FTMPC_ST_OK : FTMPC_ST_INFEASIBLE;
             else if (iter >= cfg.max_sqp_iter) sc[SC_STATUS] = FTMPC_ST_MAXITER;
         }
         if (finite || first) { sc[SC_F] = f; sc[SC_CSUM] = csum; sc[SC_CMAX] = cmax; }
