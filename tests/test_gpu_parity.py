@@ -337,7 +337,8 @@ def test_gpu_matches_cpu_port(L, built, golden):
     c = port.step(eng.cfg, eng.hull_table, st, xref, None, masks, ffs, scen)
     ok = (g["status"] == 0) & (c["status"] == 0)
     assert ok.sum() >= 0.9 * B
-    assert np.abs(g["u0"] - c["u0"])[ok].max() < 1e-7 and np.abs(g["thrust"] - c["thrust"])[ok].max() < 1e-7
+    # both stop within the SQP termination tolerance (step <= 1e-6 once the predicted decrease is rounding noise)
+    assert np.abs(g["u0"] - c["u0"])[ok].max() < 2e-6 and np.abs(g["thrust"] - c["thrust"])[ok].max() < 2e-6
     assert np.array_equal(g["active"].view(np.uint32)[ok], c["active"][ok])
 
 
