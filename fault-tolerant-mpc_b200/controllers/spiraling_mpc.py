@@ -231,7 +231,7 @@ class SpiralingController:
 
     # ---- reference trajectory ------------------------------------------------- spiraling_mpc.py:240-286
     def load_trajectory(self, cmd, duration):
-        self.assign_trajectory(load_trajectory(cmd, duration, self.dt))
+        self.assign_trajectory(load_trajectory(cmd, self.dt, duration))                  # spiraling_mpc.py:252
 
     def assign_trajectory(self, trajectory):
         N = self.Nt

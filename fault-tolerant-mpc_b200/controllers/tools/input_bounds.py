@@ -13,15 +13,14 @@ def hull_of_faults(D, max_thrust, faults):
         return _CACHE[key]
     from scipy.spatial import ConvexHull
     broken = {i: a * max_thrust for i, a in key}
-    # the 2^(#healthy) corner forces of :49-63 (itertools.product there), enumerated with bit patterns;
-    # np.unique below sorts the vertices, so the enumeration order is immaterial
-    healthy = [i for i in range(D.shape[1]) if i not in broken]
-    bits = (np.arange(2 ** len(healthy))[:, None] >> np.arange(len(healthy))[None, :]) & 1
-    corners = np.zeros((bits.shape[0], D.shape[1]))
-    corners[:, healthy] = bits * max_thrust
-    for i, f in broken.items():
-        corners[:, i] = f
-    verts = np.unique(corners @ D.T, axis=0)                                                              # :67
+    # the 2^(#healthy) corner forces of :49-63 in itertools.product order, and ONE matrix-vector product per corner as
+    # in the reference: a vectorised `corners @ D.T` differs in the last bit, which is enough to change the order in
+    # which np.unique sorts Qhull's facet equations, i.e. the numbering of the constraints
+    # (pinned by tests/golden/ref_fixtures.npz)
+    import itertools
+    min_max = [[broken[i], broken[i]] if i in broken else [0.0, max_thrust] for i in range(D.shape[1])]
+    corners = np.array(list(itertools.product(*min_max)))
+    verts = np.unique(np.array([np.matmul(D, c) for c in corners]), axis=0)                                   # :57-67
     hull = ConvexHull(verts)                                                                              # :68
     simplified = np.unique(hull.equations, axis=0)                                                        # :71
     A, b = simplified[:, :-1].copy(), -simplified[:, -1].copy()                                           # :72-73

@@ -3,11 +3,14 @@
 Restates the parts of ft_mpc/util/get_trajectory.py:71-184 the demo scenario needs: `hover`
 (point stabilising, optional `hover_<x>_<y>_<z>`), `generate_line` and `generate_circle`.
 Returns a 13 x T robot-state reference [p v q w] sampled at dt over 10*duration seconds.
+Signature as in the reference: load_trajectory(action, dt, duration=100, file_path=None)  (get_trajectory.py:6).
 """
 import numpy as np
 
 
-def load_trajectory(action: str, duration: float, dt: float) -> np.ndarray:
+def load_trajectory(action: str, dt: float, duration: float = 100, file_path=None) -> np.ndarray:
+    if action == "load":
+        raise NotImplementedError("trajectory files ('load') are host-side input preparation outside the hot path (SURVEY.md section 2 row 9)")
     t = np.arange(0, 10 * duration, dt).reshape(1, -1)
     one, zero = np.ones(t.shape), np.zeros(t.shape)
     ident_q = np.vstack((zero, zero, zero, one))                  # identity quaternion [x y z w]

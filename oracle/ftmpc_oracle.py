@@ -4,12 +4,17 @@ Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl
 import this module.  The product package (`fault-tolerant-mpc_b200/`, imported as `ft_mpc_b200`)
 never does; it fails loudly when its CUDA library is missing.
 
-PARITY UNPINNED: the reference (DISCOWER/fault-tolerant-mpc) ships no tests, golden vectors or
-known-answer values, and its solver stack (casadi 3.6.7 / IPOPT, cvxpy 1.6.4 / OSQP) is not
-installable here, so this restatement cannot be checked against reference outputs.  It is a
-line-by-line restatement of the reference's *problem definition* (numpy, fp64) solved by an
-independent solver (scipy SLSQP) to tight KKT tolerance; every function cites the reference
-file:line it follows (paths relative to /root/reference).
+PARITY: pinned for the problem definition, UNPINNED for the NLP solve.
+  * Pinned against the reference's own code: tools/gen_ref_fixtures.py executes ft_mpc.util.utils,
+    ft_mpc.models.sys_model / spiral_model, SpiralParameters, InputBounds and get_trajectory in the build
+    container (numeric stand-in for the few CasADi calls they make) and tests/test_reference_fixtures.py
+    checks every model function below against those outputs (tests/golden/ref_fixtures.npz) -- including the
+    ROW ORDER of the input-bound hull, i.e. the numbering of the constraints.  The stored terminal
+    ingredients (config/terminal.yaml) are pinned through sympy evaluation (tools/gen_terminal_data.py).
+  * Unpinned: the reference ships no tests or golden vectors for solve_mpc, and casadi 3.6.7 / IPOPT and
+    cvxpy 1.6.4 / OSQP are not installable here, so the optimiser outputs (KKT point, active set, thrust)
+    come from an independent solver on the restated NLP (scipy SLSQP + Newton polish to tight KKT
+    tolerance); every function cites the reference file:line it follows (paths relative to /root/reference).
 
 Derivatives in this file are obtained by complex-step differentiation (the prediction model is a
 polynomial map, so complex-step is exact to rounding) -- deliberately independent of the
@@ -230,9 +235,12 @@ def input_bounds(fs: FaultSet):
     min_max = []
     for i in range(NTHR):
         min_max.append([ff[i], ff[i]] if i in broken else [0.0, MAX_THRUST])     # :49-55
-    # same enumeration as itertools.product(*min_max) followed by D @ f (:57-63), vectorised
+    # itertools.product(*min_max), then ONE matrix-vector product per corner exactly as the reference does (:57-63).
+    # The per-corner np.matmul matters: a vectorised `corners @ D.T` rounds differently in the last bit, Qhull's facet
+    # normals inherit that noise, and np.unique (:71) then sorts the rows -- i.e. numbers the constraints --
+    # differently from the reference (checked against tests/golden/ref_fixtures.npz).
     corners = np.array(list(itertools.product(*min_max)))
-    verts = corners @ D_ALLOC.T
+    verts = np.array([np.matmul(D_ALLOC, c) for c in corners])
     verts = np.unique(verts, axis=0)                                              # :67
     hull = ConvexHull(verts)                                                      # :68
     simplified = np.unique(hull.equations, axis=0)                                # :71

@@ -134,5 +134,34 @@ def main():
     print("wrote", dst, "cases", len(cases))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1].startswith("--")):
     main()
+
+
+def refresh_active():
+    """Recompute only the active-set masks / facet counts from the stored KKT points (used after the constraint ROW ORDER of
+    the hull changed to the reference's: the minimisers themselves do not depend on the numbering)."""
+    dst = ROOT / "tests" / "golden" / "nlp_cases.npz"
+    g = dict(np.load(dst))
+    K = len(g["N"])
+    g["active"] = np.zeros_like(g["active"])
+    for k in range(K):
+        N = int(g["N"][k])
+        faults = [(int(i), float(a)) for i, a in zip(g["fault_idx"][k], g["fault_inten"][k]) if i >= 0]
+        prob = o.Problem(o.FaultSet(faults), N, o.robot_to_center(g["x0"][k]), g["xref"][k, :N + 1].copy(), g["uref"][k, :N + 1].copy())
+        r = o.kkt_residual(prob, g["U"][k, :N].ravel())
+        assert g["kkt_viol"][k] > 1e-8 or (r["stat"] < 1e-8 and r["viol"] < 1e-8), (g["name"][k], r["stat"], r["viol"])
+        g["n_h"][k] = prob.n_h
+        for row in r["active"]:
+            if row < prob.n_h * N:
+                t, i = divmod(int(row), prob.n_h)
+                bit = 26 * t + i
+            else:
+                bit = 26 * N + int(row) - prob.n_h * N
+            g["active"][k, bit // 32] |= np.uint32(1 << (bit % 32))
+        print(g["name"][k], "active rows", len(r["active"]), flush=True)
+    np.savez_compressed(dst, **g)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "--refresh-active":
+    refresh_active()
