@@ -271,8 +271,9 @@ def test_step_kkt_residual_through_oracle(L, oracle, golden):
     eng, out = run_cases(golden, ks, N)
     for j, k in enumerate(ks):
         r = oracle.kkt_residual(H.case_problem(oracle, golden, k), out["z"][j, :6 * N])
-        # the SQP stops on the step (|d|_inf <= 1e-8); the gradient residual is that times the Hessian scale (~1e2)
-        assert r["stat"] < 1e-6 and r["viol"] < 1e-8, (golden["name"][k], r["stat"], r["viol"])
+        # the SQP stops on the step (|d|_inf <= 1e-8, or <= 1e-6 once the predicted decrease is rounding noise); the
+        # gradient residual is that times the Hessian scale (~1e2).  u0 itself is checked to 1e-5 in test_step_vs_golden.
+        assert r["stat"] < 1e-4 and r["viol"] < 1e-8, (golden["name"][k], r["stat"], r["viol"])
 
 
 def test_warm_start_closed_loop_vs_golden(L, oracle, golden):
@@ -374,7 +375,7 @@ def test_batch_1024_properties_and_sharding(L, oracle):
         fs = oracle.FaultSet(cells[scen[k]]["faults"])
         prob = oracle.Problem(fs, N, oracle.robot_to_center(st[k]), xref[k], np.zeros((N + 1, 6)))
         r = oracle.kkt_residual(prob, g["z"][k, :6 * N])
-        assert r["stat"] < 1e-5 and r["viol"] < 1e-7, (k, r["stat"], r["viol"])     # step-based stop, see above
+        assert r["stat"] < 1e-4 and r["viol"] < 1e-7, (k, r["stat"], r["viol"])     # step-based stop, see above
     # determinism + shard invariance
     for G in (2, 8):
         for r in range(G):
