@@ -343,6 +343,29 @@ def test_gpu_matches_cpu_port(L, built, golden):
     assert np.array_equal(g["active"].view(np.uint32)[ok], c["active"][ok])
 
 
+def test_long_horizon_global_scratch_path(L, built):
+    """N = 30: the QP scratch (275 KB) no longer fits in shared memory -> k_solve<true> keeps it in a per-CTA global
+    slice and the generic condensing / factorisation routines run; results must agree with the CPU port"""
+    from ft_mpc_b200.util import scenarios
+    N, B = 30, 6
+    cells = scenarios.load_cells(kinds=("single",))[:3]
+    eng = make_engine(cells, N)
+    st = scenarios.random_states(B, 21)
+    scen = np.arange(B) % len(cells)
+    xref = scenarios.hover_reference(B, N)
+    out = eng.step(dev(st), dev(xref), scenario=dev(scen, torch.int64))
+    torch.cuda.synchronize()
+    g = {k: v.cpu().numpy() for k, v in out.items() if k != "ws"}
+    port = H.CpuPort()
+    masks = np.array([eng.mask_tab[s] for s in scen], np.uint16)
+    ffs = np.stack([eng.fault_force_tab[s] for s in scen])
+    c = port.step(eng.cfg, eng.hull_table, st, xref, None, masks, ffs, scen)
+    ok = (g["status"] == 0) & (c["status"] == 0)
+    assert ok.sum() >= B - 1, (g["status"], c["status"])
+    assert np.abs(g["u0"] - c["u0"])[ok].max() < 2e-6 and np.abs(g["thrust"] - c["thrust"])[ok].max() < 2e-6
+    assert np.array_equal(g["active"].view(np.uint32)[ok], c["active"][ok])
+
+
 def test_batch_1024_properties_and_sharding(L, oracle):
     """BASELINE config 3 (1,024 instances, N=20, single faults, random states): size-independent properties,
     and shard-invariance -- solving the batch in 2 / 8 contiguous shards gives bit-identical per-instance results"""
