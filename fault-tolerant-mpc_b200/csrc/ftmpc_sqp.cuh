@@ -975,21 +975,20 @@ struct HBlocks {
 __device__ __forceinline__ bool condense_fast_path(const WsLayout& L, int nt) {
     const int N = L.N, ld = L.nv;
     const int ldp = 7 * N + 1;
-    const size_t panel_doubles = (size_t)64 * ldp + (size_t)N * FTMPC_NE + 90;
+    const size_t panel_doubles = (size_t)64 * ldp + (size_t)N * FTMPC_NE + 90 + (size_t)L.mc + 90;
     return !(N * (N + 1) / 2 > nt || L.n > nt || panel_doubles > (size_t)(ld + FTMPC_NE) * ld);
 }
 __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg, const WsLayout& L, const QpScratch& s,
                                          const double* Jz, const double* Wz_in, const double* X, const double* U,
                                          const double* xref, const double* gradV, const double* hessV, double theta,
-                                         double sigma, const double* lam_prev, HBlocks* hb = nullptr) {
+                                         double sigma, const double* lam_prev_g, HBlocks* hb = nullptr) {
     const int N = L.N, n = L.n, ld = L.nv, tid = blk.tid(), nt = blk.nthreads();
     const int nblk = N * (N + 1) / 2;
     if (hb) hb->fast = false;
     const int ldp = 7 * N + 1;                     // panel row length: block column b starts at 7 b (6 + 1 pad -> lanes of
                                                    // neighbouring blocks are an odd number of doubles apart: no bank conflicts)
-    const size_t panel_doubles = (size_t)64 * ldp + (size_t)N * FTMPC_NE + 90;
     if (!condense_fast_path(L, nt)) {              // very short / long horizons: generic path
-        condense<CudaBlock>(blk, cfg, L, s, Jz, Wz_in, X, U, xref, gradV, hessV, theta, sigma, lam_prev);
+        condense<CudaBlock>(blk, cfg, L, s, Jz, Wz_in, X, U, xref, gradV, hessV, theta, sigma, lam_prev_g);
         return;
     }
     double* Wp = const_cast<double*>(Wz_in);       // scratch copy owned by the caller: symmetrised / scaled in place
@@ -997,6 +996,9 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
     double* qe = s.E + (size_t)64 * ldp;           // [N][9]   2 Q (x_t - xr_t)
     double* Ht = qe + (size_t)N * FTMPC_NE;        // [9][9]   terminal Hessian model (+ augmentation)
     double* tgv = Ht + 81;                         // [9]      augmentation of the terminal gradient
+    double* lam_prev = tgv + 9;                    // [mc]     shared-memory copy of the previous multipliers: the tests
+                                                   //          `lam_prev[i] > 0` sit in serial loops, one L2 round trip each otherwise
+    double* hv = lam_prev + L.mc;                  // [81 + 9] hessV, gradV
     const double* Ah = s.hull;
     // ---- pre-pass: W' = theta * sym(W) (+ 2Q on the omega diagonal), qe, Ht
     for (int idx = tid; idx < N * 169; idx += nt) {
@@ -1013,6 +1015,9 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
         const int t = idx / FTMPC_NE, kk = idx - t * FTMPC_NE;
         qe[idx] = 2.0 * cfg.Q[kk] * (X[t * FTMPC_NX + kk] - xref[t * FTMPC_NE + kk]);
     }
+    if (sigma > 0.0) for (int i = tid; i < L.mc; i += nt) lam_prev[i] = lam_prev_g[i];
+    for (int i = tid; i < 90; i += nt) hv[i] = (i < 81) ? hessV[i] : gradV[i - 81];
+    blk.sync();
     for (int idx = tid; idx < 90; idx += nt) {
         double v = 0.0;
         const int kk = idx / 9, l = idx - kk * 9;
@@ -1028,7 +1033,7 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
         }
         if (idx < 81) {
             const double q0 = s.cg->term_quad[idx];
-            Ht[idx] = q0 + theta * (hessV[idx] - q0) + v;
+            Ht[idx] = q0 + theta * (hv[idx] - q0) + v;
         } else {
             tgv[l] = v;
         }
@@ -1107,7 +1112,7 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
                         for (int l = 0; l < FTMPC_NE; ++l) v += Ht[kk * FTMPC_NE + l] * g[l];
                         buf[kk * ldp + pa_] = g[kk];
                         buf[(13 + kk) * ldp + pa_] = v;
-                        vg += gradV[kk] * g[kk];
+                        vg += hv[81 + kk] * g[kk];
                         va += tgv[kk] * g[kk];
                     }
                     gs += vg;
@@ -1435,6 +1440,14 @@ __device__ __forceinline__ int factor_hessian(CudaBlock& blk, const ftmpc_config
 }
 #endif
 
+// development aid of the CPU port: counts which kind of Hessian attempt failed (compiled out everywhere else)
+#if defined(FTMPC_DEBUG_COUNTERS) && !defined(__CUDACC__)
+extern long g_ftmpc_dbg[8];
+#define FT_DBG_COUNT(k) (__sync_fetch_and_add(&g_ftmpc_dbg[k], 1L))
+#else
+#define FT_DBG_COUNT(k) ((void)0)
+#endif
+
 // ---- phase_qp ------------------------------------------------------------------------------------------
 template <class Blk>
 FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst, int slot, double* scratch) {
@@ -1464,7 +1477,11 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     // while the iterate is still infeasible the exact Hessian is almost always indefinite and no convexification is
     // allowed: once an attempt has fallen all the way back to Gauss-Newton, do not pay for the failing attempts again
     // until feasibility is reached
-    const bool skip_exact = cfg.poll_every == 0 && sc[SC_HFAIL] != 0.0 && sc[SC_CSUM] > feas_aug;
+    // far from the solution (last QP step still large) the blended Hessian is almost always indefinite: start the
+    // blend only once the steps have become moderate (|d|_inf <= blend_dmax; measured: 2x fewer failed attempts for
+    // +0.5 % iterations)
+    const bool far = sc[SC_ITER] > 0.0 && sc[SC_THETA] <= 0.0 && sc[SC_DMAX] > cfg.blend_dmax;
+    const bool skip_exact = (sc[SC_HFAIL] != 0.0 && sc[SC_CSUM] > feas_aug) || far;
     if (skip_exact) theta = 0.0;
     bool aug_allowed = can_aug;
     int fails = 0, qit = 0, nact = 0, st = GI_OK, aug_retry = 0;
@@ -1478,11 +1495,11 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         blk.count(CT_CHOL_FAIL);
         ++fails;
         blk.sync();
-        if (sigma == 0.0 && theta == 1.0 && aug_allowed) { sig0 = 10.0 * dscale; sigma = sig0; }
-        else if (sigma > 0.0 && sig0 > 0.0 && sigma < 50.0 * sig0) sigma *= 10.0;
-        else if (sigma > 0.0) { sigma = 0.0; theta = 0.5; aug_allowed = false; }
+        if (sigma == 0.0 && theta == 1.0 && aug_allowed) { sig0 = 10.0 * dscale; sigma = sig0; FT_DBG_COUNT(0); }
+        else if (sigma > 0.0 && sig0 > 0.0 && sigma < 50.0 * sig0) { sigma *= 10.0; FT_DBG_COUNT(1); }
+        else if (sigma > 0.0) { sigma = 0.0; theta = 0.5; aug_allowed = false; FT_DBG_COUNT(2); }
         else if (theta <= 0.0) { if (tid == 0) { sc[SC_QPST] = 3.0; } return; }
-        else theta = (theta > cfg.theta_first) ? 0.5 * theta : 0.0;      // below the first blend level: Gauss-Newton
+        else { FT_DBG_COUNT(theta == 1.0 ? 3 : 4); theta = (theta > cfg.theta_first) ? 0.5 * theta : 0.0; }     // below the first blend level: Gauss-Newton
     }
     // slack variable column/row, extension rows  X J  (X = d x_N[0:9] / d U)
     for (int i = tid; i < nv; i += nt) {
@@ -1534,6 +1551,7 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
             if (lam_prev[i] > 0.0 && s.gi.pos[i] < 0 && s.gi.s[i] > 1e-9) viol = 1;
         if (blk.any(viol)) {
             ++fails;
+            FT_DBG_COUNT(5);
             if (aug_retry < 2) {
                 // drop the rows that came out inactive from the predicted set and convexify again: the exact Hessian
                 // with the corrected set keeps the Newton-like rate, the theta = 1/2 fallback below does not

@@ -59,7 +59,7 @@ typedef struct ftmpc_config {
     int32_t dtype;             /* 0 = fp64 (only mode implemented)                                          */
     int32_t max_sqp_iter;      /* outer iteration cap (default 60)                                          */
     int32_t max_qp_iter;       /* active-set iteration cap per QP (default 20*(n+m))                        */
-    int32_t poll_every;        /* reserved; non-zero disables the "skip exact-Hessian attempts while infeasible" heuristic (debugging) */
+    int32_t poll_every;        /* reserved (unused: ftmpc_step never synchronises; a persistent CTA stops iterating when its instance converges) */
     int32_t n_poly, n_root, n_hull_sets;
     double dt, mass, inertia[3], r[3], f_virt[3], max_thrust;   /* sys_model.py:52-61, spiral_parameters.py:33-39 */
     double Q[FTMPC_NE], R[FTMPC_NU];                            /* reactive.yaml:32-33                      */
@@ -80,6 +80,7 @@ typedef struct ftmpc_config {
     double clip_tol;           /* hull membership tolerance of clip_generalized_input (default 1e-9)        */
     double theta_first;        /* Hessian schedule: blend of exact second-order terms in SQP iteration 1 (iteration 0 is   */
     double theta_growth;       /* Gauss-Newton), multiplied by theta_growth per iteration up to 1 (defaults 0.5, 2)       */
+    double blend_dmax;         /* the blend is first attempted once the QP step satisfies |d|_inf <= blend_dmax (default 1) */
 } ftmpc_config;
 
 typedef struct ftmpc_ctx* ftmpc_handle;

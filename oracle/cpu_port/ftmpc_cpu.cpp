@@ -12,6 +12,8 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#define FTMPC_DEBUG_COUNTERS 1
+namespace ftmpc { long g_ftmpc_dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0}; }
 #include "ftmpc_alloc.cuh"
 using namespace ftmpc;
 
@@ -101,6 +103,10 @@ int ftmpc_cpu_allocate(const ftmpc_config* cfg, int batch, const double* u_des, 
                        int32_t* status) {
     for (int b = 0; b < batch; ++b) status[b] = allocate_thrust(*cfg, u_des + b * 6, ub + b * 16, thrust + b * 16);
     return 0;
+}
+
+void ftmpc_cpu_debug_counters(long* out, int reset) {
+    for (int i = 0; i < 8; ++i) { out[i] = ftmpc::g_ftmpc_dbg[i]; if (reset) ftmpc::g_ftmpc_dbg[i] = 0; }
 }
 
 // read back per-instance scalars of the workspace (diagnostics)

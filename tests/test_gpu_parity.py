@@ -124,7 +124,7 @@ def test_terminal_vs_oracle(L, eng6, oracle):
             assert np.allclose(Hs[b].reshape(9, 9)[i], fd, rtol=1e-5, atol=1e-4)
 
 
-@pytest.mark.parametrize("N", [8, 12, 20])      # 8: generic path, 12 / 20: register-tiled path
+@pytest.mark.parametrize("N", [8, 15, 20])      # 8: generic path, 15 / 20: register-tiled path
 def test_condense_gauss_newton_vs_oracle(L, oracle, N):
     """K2: condensed Hessian / gradient at theta = 0 == 2R + sum_t G_t' 2Q G_t + G_N' Hq G_N from the
     oracle's complex-step sensitivities (Hq = quadratic part of V_f)"""
