@@ -83,8 +83,10 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
         phase_ls_block(blk, cfg, L, io, inst, slot, 1, scratch);
         for (int it = 0; it < cfg.max_sqp_iter; ++it) {
             if (sc[SC_STATUS] != (double)FTMPC_ST_RUNNING) break;      // uniform: written before the last barrier
-            phase_lin(blk, cfg, L, io, inst, slot, scratch);
-            phase_qp(blk, cfg, L, io, inst, slot, scratch);
+            // with the shared-memory scratch the linearisation leaves Jz / Wz where condensing reads them
+            const bool staged = !GS && lin_scratch_doubles(L.N) <= (size_t)(L.nv + FTMPC_NE) * L.nv && condense_fast_path(L, blockDim.x);
+            phase_lin(blk, cfg, L, io, inst, slot, scratch, staged);
+            phase_qp(blk, cfg, L, io, inst, slot, scratch, staged);
             phase_ls_block(blk, cfg, L, io, inst, slot, 0, scratch);
         }
         phase_out_write(blk, cfg, L, io, inst, slot);

@@ -616,6 +616,8 @@ struct MpcCons {
 // per-CTA scratch carved out of one buffer of doubles (shared memory on the device)
 struct QpScratch {
     const ftmpc_config* cg;      // configuration copy addressable per thread (global memory on the device)
+    const double* tf_val;        // compact terminal-set rows (see StepIO), nullptr -> dense rows of cg->Af
+    const int* tf_idx;
     double *E, *RS, *G, *T, *g, *ga, *taug, *cv, *hull;
     GiWork gi;
     double* dg;
@@ -637,6 +639,8 @@ FT_HD QpScratch qp_carve(double* buf, int N, const ftmpc_config* cg = nullptr) {
     const size_t nv = L.nv, ne = nv + FTMPC_NE, n = L.n;
     QpScratch s;
     s.cg = cg;
+    s.tf_val = nullptr;
+    s.tf_idx = nullptr;
     double* p = buf;
     s.E = p; p += ne * nv;
     size_t rs = nv * (nv + 1) / 2;
@@ -851,7 +855,7 @@ __device__ __noinline__ void lin_reverse_task(const DynConsts& k, const double* 
 }
 
 __device__ __forceinline__ void phase_lin(CudaBlock& blk, const ftmpc_config& cfg, const WsLayout& L, const StepIO& io,
-                                          int inst, int slot, double* scratch) {
+                                          int inst, int slot, double* scratch, bool stage_rs) {
     double* w = ws_slot(io, L, slot);
     const double* sc = w + L.oSc;
     if (sc[SC_STATUS] != FTMPC_ST_RUNNING) return;
@@ -865,7 +869,13 @@ __device__ __forceinline__ void phase_lin(CudaBlock& blk, const ftmpc_config& cf
     double* Wz = w + L.oWz;
     double* Mu = w + L.oMu;
     const double* lam = w + L.oLam;
-    const LinScratch s = lin_carve(scratch, N);
+    LinScratch s = lin_carve(scratch, N);
+    double* WzS = nullptr;
+    if (stage_rs) {                              // leave Jz / Wz where condense expects them (RS region of the QP scratch)
+        const QpScratch q = qp_carve(scratch, N);
+        s.Jz = q.RS;
+        WzS = q.RS + (size_t)N * 169;
+    }
     const int ntask = 10 * N;
     // stage states and wrenches -> shared memory
     for (int i = tid; i < (N + 1) * FTMPC_NX; i += nt) s.X[i] = X[i];
@@ -939,15 +949,16 @@ __device__ __forceinline__ void phase_lin(CudaBlock& blk, const ftmpc_config& cf
         double hc[13];
         lin_reverse_task(k, s.nom + (size_t)t * 40, s.tang + it, ntask, col, s.mu + (t + 1) * FTMPC_NX, hc);
         double* wg = Wz + (size_t)t * 169;
+        double* wsm = WzS ? WzS + (size_t)t * 169 : wg;
 #pragma unroll
-        for (int i = 0; i < 13; ++i) wg[col * 13 + i] = hc[i];
+        for (int i = 0; i < 13; ++i) { wg[col * 13 + i] = hc[i]; wsm[col * 13 + i] = hc[i]; }
 #pragma unroll
-        for (int j = 0; j < 3; ++j) wg[(7 + j) * 13 + col] = hc[7 + j];      // W[F_j][col] = W[col][F_j]
+        for (int j = 0; j < 3; ++j) { wg[(7 + j) * 13 + col] = hc[7 + j]; wsm[(7 + j) * 13 + col] = hc[7 + j]; }   // W[F_j][col] = W[col][F_j]
         if (c == 0) {
 #pragma unroll
             for (int j = 0; j < 3; ++j)
 #pragma unroll
-                for (int l = 0; l < 3; ++l) wg[(7 + j) * 13 + 7 + l] = 0.0;   // the dynamics are linear in F
+                for (int l = 0; l < 3; ++l) { wg[(7 + j) * 13 + 7 + l] = 0.0; wsm[(7 + j) * 13 + 7 + l] = 0.0; }   // the dynamics are linear in F
         }
     }
     blk.sync();
@@ -1022,11 +1033,23 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
         double v = 0.0;
         const int kk = idx / 9, l = idx - kk * 9;
         if (sigma > 0.0) {
-            const double* Af = s.cg->Af;
-            for (int i = 0; i < FTMPC_NF; ++i) {
-                if (lam_prev[FTMPC_NH * N + i] > 0.0) {
-                    const double a = Af[i * FTMPC_NE + l];
-                    v += (idx < 81) ? Af[i * FTMPC_NE + kk] * a : s.cv[FTMPC_NH * N + i] * a;
+            if (s.tf_val) {                        // <= 2 non-zeros per row, tables in shared memory
+                for (int i = 0; i < FTMPC_NF; ++i) {
+                    if (lam_prev[FTMPC_NH * N + i] > 0.0) {
+                        const int k0 = s.tf_idx[2 * i], k1 = s.tf_idx[2 * i + 1];
+                        const double v0 = s.tf_val[2 * i], v1 = s.tf_val[2 * i + 1];
+                        const double al = (l == k0) ? v0 : ((l == k1) ? v1 : 0.0);
+                        const double ak = (kk == k0) ? v0 : ((kk == k1) ? v1 : 0.0);
+                        v += (idx < 81) ? ak * al : s.cv[FTMPC_NH * N + i] * al;
+                    }
+                }
+            } else {
+                const double* Af = s.cg->Af;
+                for (int i = 0; i < FTMPC_NF; ++i) {
+                    if (lam_prev[FTMPC_NH * N + i] > 0.0) {
+                        const double al = Af[i * FTMPC_NE + l];
+                        v += (idx < 81) ? Af[i * FTMPC_NE + kk] * al : s.cv[FTMPC_NH * N + i] * al;
+                    }
                 }
             }
             v *= sigma;
@@ -1394,8 +1417,9 @@ template <class Blk>
 FT_HD int factor_hessian(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const QpScratch& s, double* Jz, double* Wz,
                          const double* Jz_src, const double* Wz_src, const double* X, const double* U, const double* xref,
                          const double* gradV, const double* hessV, double theta, double sigma, const double* lam_prev,
-                         double* dscale_out) {
+                         double* dscale_out, bool copy_j = true, bool copy_w = true) {
     const int N = L.N, n = L.n, ld = L.nv, tid = blk.tid(), nt = blk.nthreads();
+    (void)copy_j; (void)copy_w;
     for (int i = tid; i < N * 169; i += nt) { Jz[i] = Jz_src[i]; Wz[i] = Wz_src[i]; }     // (the QP reuses this region)
     blk.sync();
     condense(blk, cfg, L, s, Jz, Wz, X, U, xref, gradV, hessV, theta, sigma, lam_prev);
@@ -1417,12 +1441,15 @@ __device__ __forceinline__ int factor_hessian(CudaBlock& blk, const ftmpc_config
                                               double* Jz, double* Wz, const double* Jz_src, const double* Wz_src,
                                               const double* X, const double* U, const double* xref, const double* gradV,
                                               const double* hessV, double theta, double sigma, const double* lam_prev,
-                                              double* dscale_out) {
+                                              double* dscale_out, bool copy_j = true, bool copy_w = true) {
     const int N = L.N, n = L.n, ld = L.nv, tid = blk.tid(), nt = blk.nthreads();
     if (!condense_fast_path(L, nt))
         return factor_hessian<CudaBlock>(blk, cfg, L, s, Jz, Wz, Jz_src, Wz_src, X, U, xref, gradV, hessV, theta, sigma,
                                          lam_prev, dscale_out);
-    for (int i = tid; i < N * 169; i += nt) { Jz[i] = Jz_src[i]; Wz[i] = Wz_src[i]; }     // Wz is scaled in place below
+    // the linearisation leaves Jz / Wz in place (shared memory); Wz is scaled in place below, so a second attempt
+    // re-reads Wz (and, once the active-set solver has reused the region, Jz too) from the global backing copy
+    if (copy_j) for (int i = tid; i < N * 169; i += nt) Jz[i] = Jz_src[i];
+    if (copy_w) for (int i = tid; i < N * 169; i += nt) Wz[i] = Wz_src[i];
     blk.sync();
     HBlocks hb;
     condense(blk, cfg, L, s, Jz, Wz, X, U, xref, gradV, hessV, theta, sigma, lam_prev, &hb);
@@ -1450,12 +1477,15 @@ extern long g_ftmpc_dbg[8];
 
 // ---- phase_qp ------------------------------------------------------------------------------------------
 template <class Blk>
-FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst, int slot, double* scratch) {
+FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst, int slot, double* scratch,
+                   bool staged = false /* Jz, Wz already sit in the scratch (CUDA linearisation) */) {
     double* w = ws_slot(io, L, slot);
     double* sc = w + L.oSc;
     if (sc[SC_STATUS] != FTMPC_ST_RUNNING) return;
     const int N = L.N, n = L.n, nv = L.nv, ne = nv + FTMPC_NE, ld = nv, tid = blk.tid(), nt = blk.nthreads();
-    const QpScratch s = qp_carve(scratch, N, io.cfg_g);
+    QpScratch s = qp_carve(scratch, N, io.cfg_g);
+    s.tf_val = io.tf_val;
+    s.tf_idx = io.tf_idx;
     const double* xref = io.xref + (size_t)inst * (N + 1) * FTMPC_NE;
     const double* hull_g = io.hull_table + (size_t)io.hull_idx[inst] * FTMPC_HULL_STRIDE;
     // stage data -> scratch (the R^-1 region is free until the active-set solve starts)
@@ -1485,12 +1515,15 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     if (skip_exact) theta = 0.0;
     bool aug_allowed = can_aug;
     int fails = 0, qit = 0, nact = 0, st = GI_OK, aug_retry = 0;
+    bool have_j = staged, have_w = staged;
     for (;;) {        // QP attempts (re-solved without augmentation if a predicted-active row came out inactive)
     double sig0 = 0.0;
     for (;;) {
         double dscale = 0.0;
         const int bad = factor_hessian(blk, cfg, L, s, Jz, Wz, w + L.oJz, w + L.oWz, w + L.oX, w + L.oU, xref, w + L.oGV,
-                                       w + L.oHV, theta, sigma, lam_prev, &dscale);
+                                       w + L.oHV, theta, sigma, lam_prev, &dscale, !have_j, !have_w);
+        have_j = true;                  // Jz survives a failed factorisation, the scaled Wz does not
+        have_w = false;
         if (!bad) break;
         blk.count(CT_CHOL_FAIL);
         ++fails;
@@ -1543,6 +1576,7 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     int qit1 = 0;
     // the previous multipliers are still needed if this attempt is rejected: the QP writes to the spare copy
     st = gi_solve(blk, cons, s.gi, nv, ne, ld, L.m, 0, w + L.oLam + L.m, cfg.max_qp_iter, cfg.qp_tol, &qit1, &nact);
+    have_j = false;                     // R^-1 has overwritten the staged Jacobians
     blk.mark(PH_GI);
     qit += qit1;
     if (sigma > 0.0 && st == GI_OK) {       // every predicted-active row must be active in the QP solution
