@@ -21,7 +21,7 @@ MAX_POLY, MAX_ROOT = 32, 16
 PHASE_NAMES = ['ls', 'lin', 'condense', 'cholesky', 'inverse', 'qp_setup', 'qp_active_set', 'qp_post', 'out',
                'ls_rollout', 'ls_eval', 'ls_terminal', 'chol_panel', 'chol_syrk', 'gi_select', 'gi_d', 'gi_z', 'gi_step', 'gi_update',
                'gi_drop', 'lin_jac', 'lin_costate', 'cond_pre', 'cond_col', 'cond_blk',
-               'n_instances', 'n_sqp_iter', 'n_condense', 'n_chol_fail', 'n_qp', 'n_gi_iter', 'n_gi_drop', 'n_ls_backtrack']
+               'n_instances', 'n_sqp_iter', 'n_condense', 'n_chol_fail', 'n_qp', 'n_gi_iter', 'n_gi_drop', 'n_ls_backtrack', 'n_gi_warm_ok', 'n_gi_warm_miss']
 N_PHASES = len(PHASE_NAMES)
 N_CYCLE_PHASES = 25
 ST_OK, ST_MAXITER, ST_QPFAIL, ST_INFEASIBLE, ST_ALLOC = 0, 1, 2, 3, 4
@@ -35,7 +35,7 @@ class FtmpcConfig(C.Structure):
     """struct ftmpc_config of include/ftmpc.h (field order and types must match exactly)."""
     _fields_ = [
         ("horizon", C.c_int32), ("dtype", C.c_int32), ("max_sqp_iter", C.c_int32), ("max_qp_iter", C.c_int32),
-        ("poll_every", C.c_int32), ("n_poly", C.c_int32), ("n_root", C.c_int32), ("n_hull_sets", C.c_int32),
+        ("poll_every", C.c_int32), ("warm_qp", C.c_int32), ("n_poly", C.c_int32), ("n_root", C.c_int32), ("n_hull_sets", C.c_int32),
         ("dt", C.c_double), ("mass", C.c_double), ("inertia", C.c_double * 3), ("r", C.c_double * 3),
         ("f_virt", C.c_double * 3), ("max_thrust", C.c_double),
         ("Q", C.c_double * NE), ("R", C.c_double * NU), ("D", C.c_double * (NU * NTHR)),
@@ -59,7 +59,7 @@ def make_config(horizon: int, Q, R, *, dt: float, mass: float, inertia, r, f_vir
                 terminal: dict | None = None, n_hull_sets: int = 1, max_sqp_iter: int = 60, max_qp_iter: int = 0,
                 poll_every: int = 0, sqp_tol: float = 1e-8, qp_tol: float = 1e-10, feas_tol: float = 1e-7,
                 act_tol: float = 1e-7, rho_slack: float = 1e4, clip_tol: float = 1e-9, theta_first: float = 0.5,
-                theta_growth: float = 2.0, blend_dmax: float = 1.0) -> FtmpcConfig:
+                theta_growth: float = 2.0, blend_dmax: float = 1.0, warm_qp: int = 1) -> FtmpcConfig:
     term = terminal or load_terminal()
     if len(term["poly"]) > MAX_POLY or len(term["root"]) > MAX_ROOT:
         raise ValueError("terminal cost has more terms than the term table holds")
@@ -69,6 +69,7 @@ def make_config(horizon: int, Q, R, *, dt: float, mass: float, inertia, r, f_vir
     n, m = NU * horizon, NH * horizon + NF + 2
     cfg.max_qp_iter = int(max_qp_iter) if max_qp_iter else 20 * (n + m)
     cfg.poll_every = int(poll_every)
+    cfg.warm_qp = int(warm_qp)
     cfg.n_poly, cfg.n_root, cfg.n_hull_sets = len(term["poly"]), len(term["root"]), int(n_hull_sets)
     cfg.dt, cfg.mass, cfg.max_thrust = float(dt), float(mass), float(max_thrust)
     cfg.inertia[:] = [float(x) for x in np.diag(np.asarray(inertia, float))] if np.ndim(inertia) == 2 else list(map(float, inertia))

@@ -130,11 +130,149 @@ FT_HD void gi_drop(Blk& blk, const GiWork& w, int nv, int ne, int ld, int& q, in
     q -= 1;
 }
 
+// ---- warm start of the working set ---------------------------------------------------------------------
+// Consecutive SQP iterations mostly share their active set, yet the dual method has to re-add it one constraint
+// (one O(ne nv) sweep over E plus bookkeeping) at a time.  gi_warm_start puts a PREDICTED set W0 (rows with a
+// positive multiplier in the previous QP) into the working set in one go:
+//   D0 = J' N0  ->  Householder QR (the same reflectors, in the same order, a one-by-one add would build)
+//   E <- E Q,  R^-1,  x = x_unc - J1 R^-T s0,  u = -R^-1 R^-T s0     (s0 = slacks of W0 at x_unc)
+// If every u_k >= 0 the pair (x, W0) is exactly the S-pair the dual algorithm would have reached after adding W0 with
+// full steps, and gi_solve continues from there.  Otherwise (wrong prediction, dependent rows) the start is
+// abandoned: x <- x_unc, empty working set -- E Q is still a valid J, so nothing has to be undone.
+// Returns the size of the working set (0 = cold start).  xe_save: scratch of ne doubles.
+#define FTMPC_GI_WARM_MAX 40
+#define FTMPC_GI_WARM_OFF 2048        /* D0 lives behind the first 2048 entries of the packed R^-1 (q <= 63) */
+template <class Blk, class Cons>
+FT_HD int gi_warm_start(Blk& blk, const Cons& cons, const GiWork& w, int nv, int ne, int ld, int m, int meq,
+                        const double* lam_warm, int m_warm, double* xe_save) {
+    const int tid = blk.tid(), nt = blk.nthreads();
+    if (!lam_warm || meq != 0) return 0;
+    const int cap = (nv * (nv + 1) / 2 + 1 - FTMPC_GI_WARM_OFF) / nv;
+    if (cap < 1) return 0;
+    const int qmax = cap < FTMPC_GI_WARM_MAX ? cap : FTMPC_GI_WARM_MAX;
+    double* Dm = w.Ui + FTMPC_GI_WARM_OFF;       // [q0][nv]
+    double* vk0 = w.tmp;                         // v_k[0]
+    double* fk = w.sub;                          // 2 / v_k'v_k
+    double* rho = w.r;                           // R[k][k]
+    // predicted rows, in index order
+    for (int i = tid; i < m_warm; i += nt) if (lam_warm[i] > 0.0) w.pos[i] = -2;
+    blk.sync();
+    if (tid == 0) {
+        int c = 0;
+        for (int i = 0; i < m_warm; ++i)
+            if (w.pos[i] == -2) {
+                w.pos[i] = -1;
+                if (c <= qmax) w.act[c < qmax ? c : qmax] = i;      // (the count is what matters beyond qmax)
+                ++c;
+            }
+        w.itmp[0] = c;
+    }
+    blk.sync();
+    const int q0 = w.itmp[0];
+    if (q0 == 0 || q0 > qmax) return 0;
+    for (int i = tid; i < ne; i += nt) xe_save[i] = w.xe[i];
+    // D0 = J' N0
+    for (int k = 0; k < q0; ++k) {
+        SparseRow np;
+        cons.row(w.act[k], np);
+        for (int i = tid; i < nv; i += nt) {
+            double v = 0.0;
+            for (int j = 0; j < np.nnz; ++j) v += np.val[j] * w.E[(size_t)np.idx[j] * ld + i];
+            Dm[(size_t)k * nv + i] = v;
+        }
+    }
+    blk.sync();
+    // Householder QR of D0, reflector k built from column k, rows k..nv-1
+    bool ok = true;
+    for (int k = 0; k < q0 && ok; ++k) {
+        const double* dk = Dm + (size_t)k * nv;
+        double p2 = 0.0, pa = 0.0;
+        for (int i = tid; i < nv; i += nt) {
+            const double v = dk[i] * dk[i];
+            pa += v;
+            if (i >= k) p2 += v;
+        }
+        const double d2n = blk.sum(p2);
+        const double dn = blk.sum(pa);
+        if (d2n <= 1e-22 * fmax(1.0, dn) || d2n <= 1e-28) { ok = false; break; }
+        const double alpha = sqrt(d2n), d0 = dk[k];
+        const double sg = (d0 >= 0.0) ? 1.0 : -1.0;
+        const double v0 = d0 + sg * alpha, f = 2.0 / (2.0 * alpha * (alpha + fabs(d0)));
+        blk.sync();                               // everybody has read dk[k]
+        if (tid == 0) { vk0[k] = v0; fk[k] = f; rho[k] = -sg * alpha; }
+        for (int c = k + 1 + tid; c < q0; c += nt) {          // remaining columns, one thread each
+            double* dc = Dm + (size_t)c * nv;
+            double a = v0 * dc[k];
+            for (int i = k + 1; i < nv; ++i) a += dk[i] * dc[i];
+            const double wv = f * a;
+            dc[k] -= wv * v0;
+            for (int i = k + 1; i < nv; ++i) dc[i] -= wv * dk[i];
+        }
+        blk.sync();
+    }
+    if (!ok) return 0;                            // dependent rows: cold start (E untouched so far)
+    // R^-1 (packed upper, by columns): R[j][c] = Dm[c][j] (j < c), R[c][c] = rho[c]
+    for (int c = tid; c < q0; c += nt) {
+        double* col = w.Ui + gi_tri(c);
+        col[c] = 1.0 / rho[c];
+        for (int j = c - 1; j >= 0; --j) {
+            double a = 0.0;
+            for (int l = j + 1; l <= c; ++l) a += Dm[(size_t)l * nv + j] * col[l];
+            col[j] = -a / rho[j];
+        }
+    }
+    // y = R^-T s0 (serial, q0^2 / 2 operations)
+    if (tid == 0) {
+        for (int k = 0; k < q0; ++k) {
+            double a = w.s[w.act[k]];
+            for (int j = 0; j < k; ++j) a -= Dm[(size_t)k * nv + j] * w.d[j];
+            w.d[k] = a / rho[k];
+        }
+    }
+    blk.sync();
+    // u = -R^-1 y
+    double umin = 0.0, umax = 0.0;
+    for (int j = tid; j < q0; j += nt) {
+        double a = 0.0;
+        for (int k = j; k < q0; ++k) a += w.Ui[gi_tri(k) + j] * w.d[k];
+        w.u[j] = -a;
+        umin = fmin(umin, -a);
+        umax = fmax(umax, fabs(a));
+    }
+    umin = -blk.max(-umin);
+    umax = blk.max(umax);
+    if (umin < -1e-9 * fmax(1.0, umax)) return 0; // a predicted row wants a negative multiplier: cold start (E untouched)
+    // E <- E Q  (rows in extended coordinates), then x = x_unc - E[:, :q0] y
+    for (int row = tid; row < ne; row += nt) {
+        double* e = w.E + (size_t)row * ld;
+        for (int k = 0; k < q0; ++k) {
+            const double* dk = Dm + (size_t)k * nv;
+            double a = vk0[k] * e[k];
+            for (int i = k + 1; i < nv; ++i) a += dk[i] * e[i];
+            const double wv = fk[k] * a;
+            e[k] -= wv * vk0[k];
+            for (int i = k + 1; i < nv; ++i) e[i] -= wv * dk[i];
+        }
+        double a = 0.0;
+        for (int k = 0; k < q0; ++k) a += e[k] * w.d[k];
+        w.xe[row] -= a;
+    }
+    for (int j = tid; j < q0; j += nt) {
+        if (w.u[j] < 0.0) w.u[j] = 0.0;
+        w.pos[w.act[j]] = j;
+    }
+    blk.sync();
+    for (int i = tid; i < m; i += nt) w.s[i] = cons.slack(i, w.xe, 1.0);
+    blk.sync();
+    return q0;
+}
+
 // On entry: E = [J ; X J] with J J' = G^-1, xe = [x ; X x] the unconstrained minimiser.
 // On exit : xe the solution, lam[m] multipliers (>=0 for inequalities), returns GI_* status.
 template <class Blk, class Cons>
 FT_HD int gi_solve(Blk& blk, const Cons& cons, const GiWork& w, int nv, int ne, int ld, int m, int meq,
-                   double* lam, int maxit, double tol, int* iters_out, int* nact_out) {
+                   double* lam, int maxit, double tol, int* iters_out, int* nact_out,
+                   const double* lam_warm = nullptr, int m_warm = 0) {
     const int tid = blk.tid(), nt = blk.nthreads();
     int q = 0, iters = 0, status = GI_OK;
     // slack of every constraint at the unconstrained minimiser
@@ -143,6 +281,7 @@ FT_HD int gi_solve(Blk& blk, const Cons& cons, const GiWork& w, int nv, int ne, 
         w.pos[i] = -1;
     }
     blk.sync();
+    q = gi_warm_start(blk, cons, w, nv, ne, ld, m, meq, lam_warm, m_warm, w.ze);
     int eq_next = 0;
     for (;;) {
         // ---- choose the constraint to add: pending equalities first, then the most violated row
@@ -327,7 +466,8 @@ __device__ __forceinline__ void axpy_ilp(double* __restrict__ e, const double* _
 // ---------------------------------------------------------------------------------------------------------
 template <class Cons>
 __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const GiWork& w, int nv, int ne, int ld, int m,
-                                        int meq, double* lam, int maxit, double tol, int* iters_out, int* nact_out) {
+                                        int meq, double* lam, int maxit, double tol, int* iters_out, int* nact_out,
+                                        const double* lam_warm = nullptr, int m_warm = 0) {
     const int tid = blk.tid(), nt = blk.nthreads(), lane = tid & 31, warp = tid >> 5, nw = (nt + 31) >> 5;
     double* gsc = blk.scratch + 128;              // 64 doubles of block scratch reserved for this routine
     int q = 0, iters = 0, status = GI_OK;
@@ -336,6 +476,8 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
         w.pos[i] = -1;
     }
     blk.sync();
+    q = gi_warm_start(blk, cons, w, nv, ne, ld, m, meq, lam_warm, m_warm, w.ze);
+    blk.count(q > 0 ? CT_GI_WARM_OK : CT_GI_WARM_MISS);
     int eq_next = 0;
     bool have_next = false;                       // most violated row already known from the previous full step
     double next_best = 0.0;

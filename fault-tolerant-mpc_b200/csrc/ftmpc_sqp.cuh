@@ -1575,7 +1575,8 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     blk.count(CT_QP);
     int qit1 = 0;
     // the previous multipliers are still needed if this attempt is rejected: the QP writes to the spare copy
-    st = gi_solve(blk, cons, s.gi, nv, ne, ld, L.m, 0, w + L.oLam + L.m, cfg.max_qp_iter, cfg.qp_tol, &qit1, &nact);
+    st = gi_solve(blk, cons, s.gi, nv, ne, ld, L.m, 0, w + L.oLam + L.m, cfg.max_qp_iter, cfg.qp_tol, &qit1, &nact,
+                  (cfg.warm_qp != 0 && sc[SC_ITER] > 0.0) ? lam_prev : nullptr, L.mc);
     have_j = false;                     // R^-1 has overwritten the staged Jacobians
     blk.mark(PH_GI);
     qit += qit1;

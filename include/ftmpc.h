@@ -60,6 +60,7 @@ typedef struct ftmpc_config {
     int32_t max_sqp_iter;      /* outer iteration cap (default 60)                                          */
     int32_t max_qp_iter;       /* active-set iteration cap per QP (default 20*(n+m))                        */
     int32_t poll_every;        /* reserved (unused: ftmpc_step never synchronises; a persistent CTA stops iterating when its instance converges) */
+    int32_t warm_qp;           /* 1 = start each QP from the previous QP's active set (gi_warm_start), default 1 */
     int32_t n_poly, n_root, n_hull_sets;
     double dt, mass, inertia[3], r[3], f_virt[3], max_thrust;   /* sys_model.py:52-61, spiral_parameters.py:33-39 */
     double Q[FTMPC_NE], R[FTMPC_NU];                            /* reactive.yaml:32-33                      */
@@ -116,7 +117,7 @@ int ftmpc_step(ftmpc_handle h, int batch, const double* state, const double* xre
  * phase_cycles[i] = SM cycles summed over all CTAs spent in phase i:
  *   0 step acceptance + rollout, 1 linearisation (Jacobians, costates, stage Hessians), 2 condensing, 3 Cholesky,
  *   4 J = L^-T, 5 QP set-up, 6 dual active-set iterations, 7 QP post-processing, 8 result write-out. */
-#define FTMPC_N_PHASES 33   /* 9 coarse phases, 16 sub-phases, 8 event counters: names in ft_mpc_b200._lib.PHASE_NAMES */
+#define FTMPC_N_PHASES 35   /* 9 coarse phases, 16 sub-phases, 10 event counters: names in ft_mpc_b200._lib.PHASE_NAMES */
 int ftmpc_profile_enable(ftmpc_handle h, int enable);
 int ftmpc_profile_read(ftmpc_handle h, void* stream, double* kernel_ms, int64_t* phase_cycles, int n_phase);
 /* number of kernels ftmpc_step launched on its last call */
