@@ -30,6 +30,9 @@ struct SparseRow {
 };
 
 enum { GI_OK = 0, GI_MAXIT = 1, GI_INFEASIBLE = 2 };
+#if defined(FTMPC_DEBUG_COUNTERS) && !defined(__CUDACC__)
+extern thread_local int g_ftmpc_warm_hit;
+#endif
 
 // n_p . v - beta_p through the generic row() interface (constraint types with structure override `slack`)
 template <class Cons>
@@ -282,6 +285,9 @@ FT_HD int gi_solve(Blk& blk, const Cons& cons, const GiWork& w, int nv, int ne, 
     }
     blk.sync();
     q = gi_warm_start(blk, cons, w, nv, ne, ld, m, meq, lam_warm, m_warm, w.ze);
+#if defined(FTMPC_DEBUG_COUNTERS) && !defined(__CUDACC__)
+    g_ftmpc_warm_hit = q > 0;
+#endif
     int eq_next = 0;
     for (;;) {
         // ---- choose the constraint to add: pending equalities first, then the most violated row
@@ -464,6 +470,191 @@ __device__ __forceinline__ void axpy_ilp(double* __restrict__ e, const double* _
 //     end of the block at the same time, and the dual step length falls out of the same barrier (argmin);
 //   * constraint slacks use Cons::slack (no sparse-row materialisation in the sweeps over all m rows).
 // ---------------------------------------------------------------------------------------------------------
+// CUDA-block specialisation of gi_warm_start (same mathematics; the order of W0 follows the thread mapping instead
+// of the row index, which only changes rounding):
+//   * ordered compaction by a block prefix sum, D0 one warp per predicted row;
+//   * Householder QR with one warp per remaining column (every warp recomputes the pivot column's norm, so a step
+//     needs a single barrier);
+//   * E <- E Q with HALF A ROW OF E IN REGISTERS per thread: a lane pair loads its row once, applies all q0
+//     reflectors (partial dot, one shuffle, update) and stores it once -- two sweeps over E instead of three per
+//     added constraint.
+#define FTMPC_GI_HALF 61
+template <class Cons>
+__device__ __forceinline__ int gi_warm_start(CudaBlock& blk, const Cons& cons, const GiWork& w, int nv, int ne, int ld, int m,
+                                             int meq, const double* lam_warm, int m_warm, double* xe_save) {
+    const int tid = blk.tid(), nt = blk.nthreads(), lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    if (!lam_warm || meq != 0) return 0;
+    if (nv > 2 * FTMPC_GI_HALF || ne > (nt >> 1) + nw)                     // shapes the register path does not cover
+        return gi_warm_start<CudaBlock, Cons>(blk, cons, w, nv, ne, ld, m, meq, lam_warm, m_warm, xe_save);
+    const int cap = (nv * (nv + 1) / 2 + 1 - FTMPC_GI_WARM_OFF) / nv;
+    if (cap < 1) return 0;
+    const int qmax = cap < FTMPC_GI_WARM_MAX ? cap : FTMPC_GI_WARM_MAX;
+    double* Dm = w.Ui + FTMPC_GI_WARM_OFF;       // [q0][nv]
+    double* vk0 = w.tmp;
+    double* fk = w.sub;
+    double* rho = w.r;
+    double* gsc = blk.scratch + 128;
+    int* isc = reinterpret_cast<int*>(gsc + 32);
+    // ---- ordered compaction of the predicted rows (thread t owns rows t, t + nt, ...)
+    int mine = 0;
+    for (int i = tid; i < m_warm; i += nt) mine += (lam_warm[i] > 0.0) ? 1 : 0;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) isc[warp] = incl;
+    blk.sync();
+    int base = 0, q0 = 0;
+    for (int i = 0; i < nw; ++i) { if (i < warp) base += isc[i]; q0 += isc[i]; }
+    if (q0 == 0 || q0 > qmax) return 0;
+    {
+        int o = base + incl - mine;
+        for (int i = tid; i < m_warm; i += nt) if (lam_warm[i] > 0.0) w.act[o++] = i;
+    }
+    for (int i = tid; i < ne; i += nt) xe_save[i] = w.xe[i];
+    blk.sync();
+    // ---- D0 = J' N0, one warp per predicted row
+    for (int k = warp; k < q0; k += nw) {
+        SparseRow np;
+        cons.row(w.act[k], np);
+        for (int i = lane; i < nv; i += 32) {
+            double v = 0.0;
+#pragma unroll
+            for (int j = 0; j < FTMPC_GI_MAXNNZ; ++j)
+                if (j < np.nnz) v += np.val[j] * w.E[(size_t)np.idx[j] * ld + i];
+            Dm[(size_t)k * nv + i] = v;
+        }
+    }
+    blk.sync();
+    // ---- Householder QR: step k = reflector from column k (rows k..nv-1), applied to columns k+1..q0-1
+    for (int k = 0; k < q0; ++k) {
+        const double* dk = Dm + (size_t)k * nv;
+        double p2 = 0.0, pa = 0.0;
+        for (int i = lane; i < nv; i += 32) {
+            const double v = dk[i] * dk[i];
+            pa += v;
+            if (i >= k) p2 += v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            pa += __shfl_xor_sync(0xffffffffu, pa, o);
+            p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+        }
+        if (p2 <= 1e-22 * fmax(1.0, pa) || p2 <= 1e-28) return 0;          // dependent rows (same verdict in every warp)
+        const double alpha = sqrt(p2), d0 = dk[k];
+        const double sg = (d0 >= 0.0) ? 1.0 : -1.0;
+        const double v0 = d0 + sg * alpha, f = 2.0 / (2.0 * alpha * (alpha + fabs(d0)));
+        if (tid == 0) { vk0[k] = v0; fk[k] = f; rho[k] = -sg * alpha; }
+        for (int c = k + 1 + warp; c < q0; c += nw) {
+            double* dc = Dm + (size_t)c * nv;
+            double a = 0.0;
+            for (int i = k + lane; i < nv; i += 32) a += ((i == k) ? v0 : dk[i]) * dc[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            const double wv = f * a;
+            for (int i = k + lane; i < nv; i += 32) dc[i] -= wv * ((i == k) ? v0 : dk[i]);
+        }
+        blk.sync();
+    }
+    // ---- R^-1 (packed upper, by columns): R[j][c] = Dm[c][j] (j < c), R[c][c] = rho[c]
+    for (int c = tid; c < q0; c += nt) {
+        double* col = w.Ui + gi_tri(c);
+        col[c] = 1.0 / rho[c];
+        for (int j = c - 1; j >= 0; --j) {
+            double a = 0.0;
+            for (int l = j + 1; l <= c; ++l) a += Dm[(size_t)l * nv + j] * col[l];
+            col[j] = -a / rho[j];
+        }
+    }
+    blk.sync();
+    // ---- y = R^-T s0 = (R^-1)' s0,  u = -R^-1 y
+    for (int k = tid; k < q0; k += nt) {
+        double a = 0.0;
+        for (int j = 0; j <= k; ++j) a += w.Ui[gi_tri(k) + j] * w.s[w.act[j]];
+        w.d[k] = a;
+    }
+    blk.sync();
+    int bad = 0;
+    {
+        double umax = 0.0;
+        for (int k = 0; k < q0; ++k) umax = fmax(umax, fabs(w.d[k]));      // |y| bounds the scale; cheap and uniform
+        for (int j = tid; j < q0; j += nt) {
+            double a = 0.0;
+            for (int k = j; k < q0; ++k) a += w.Ui[gi_tri(k) + j] * w.d[k];
+            w.u[j] = fmax(-a, 0.0);
+            if (-a < -1e-9 * fmax(1.0, umax)) bad = 1;
+        }
+    }
+    if (blk.any(bad)) return 0;                   // a predicted row wants a negative multiplier: cold start, E untouched
+    // ---- E <- E Q and x = x_unc - E[:, :q0] y, half a row per thread
+    {
+        const int row = tid >> 1, half = tid & 1;
+        const int c0 = half * FTMPC_GI_HALF;
+        const bool live = row < ne;
+        double e[FTMPC_GI_HALF];
+        const double* er = w.E + (size_t)(live ? row : 0) * ld;
+#pragma unroll
+        for (int c = 0; c < FTMPC_GI_HALF; ++c) e[c] = (live && c0 + c < nv) ? er[c0 + c] : 0.0;
+        for (int k = 0; k < q0; ++k) {
+            const double* dk = Dm + (size_t)k * nv;
+            const double v0 = vk0[k], f = fk[k];
+            double a = 0.0;
+#pragma unroll
+            for (int c = 0; c < FTMPC_GI_HALF; ++c) {
+                const int col = c0 + c;
+                const double vv = (col > k && col < nv) ? dk[col] : ((col == k) ? v0 : 0.0);
+                a += vv * e[c];
+            }
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            const double wv = f * a;
+#pragma unroll
+            for (int c = 0; c < FTMPC_GI_HALF; ++c) {
+                const int col = c0 + c;
+                const double vv = (col > k && col < nv) ? dk[col] : ((col == k) ? v0 : 0.0);
+                e[c] -= wv * vv;
+            }
+        }
+        if (live) {
+            double* ew = w.E + (size_t)row * ld;
+#pragma unroll
+            for (int c = 0; c < FTMPC_GI_HALF; ++c) if (c0 + c < nv) ew[c0 + c] = e[c];
+            if (half == 0) {                       // q0 <= 40 < FTMPC_GI_HALF: the first q0 columns sit in half 0
+                double a = 0.0;
+#pragma unroll
+                for (int c = 0; c < FTMPC_GI_WARM_MAX; ++c) if (c < q0) a += e[c] * w.d[c];
+                w.xe[row] -= a;
+            }
+        }
+    }
+    // rows beyond the lane-pair range: one warp each, in shared memory
+    for (int row = (nt >> 1) + warp; row < ne; row += nw) {
+        double* e = w.E + (size_t)row * ld;
+        for (int k = 0; k < q0; ++k) {
+            const double* dk = Dm + (size_t)k * nv;
+            const double v0 = vk0[k];
+            double a = 0.0;
+            for (int i = k + lane; i < nv; i += 32) a += ((i == k) ? v0 : dk[i]) * e[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            const double wv = fk[k] * a;
+            for (int i = k + lane; i < nv; i += 32) e[i] -= wv * ((i == k) ? v0 : dk[i]);
+            __syncwarp();
+        }
+        double a = 0.0;
+        for (int k = lane; k < q0; k += 32) a += e[k] * w.d[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) w.xe[row] -= a;
+    }
+    for (int j = tid; j < q0; j += nt) w.pos[w.act[j]] = j;
+    blk.sync();
+    for (int i = tid; i < m; i += nt) w.s[i] = cons.slack(i, w.xe, 1.0);
+    blk.sync();
+    return q0;
+}
+
 template <class Cons>
 __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const GiWork& w, int nv, int ne, int ld, int m,
                                         int meq, double* lam, int maxit, double tol, int* iters_out, int* nact_out,

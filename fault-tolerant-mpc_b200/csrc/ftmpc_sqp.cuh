@@ -1471,6 +1471,9 @@ __device__ __forceinline__ int factor_hessian(CudaBlock& blk, const ftmpc_config
 #if defined(FTMPC_DEBUG_COUNTERS) && !defined(__CUDACC__)
 extern long g_ftmpc_dbg[8];
 #define FT_DBG_COUNT(k) (__sync_fetch_and_add(&g_ftmpc_dbg[k], 1L))
+extern long g_ftmpc_dbg2[8];
+extern thread_local int g_ftmpc_warm_hit;
+#define FT_DBG_COUNT2(bin, hit) (__sync_fetch_and_add(&g_ftmpc_dbg2[2 * (bin) + (hit)], 1L))
 #else
 #define FT_DBG_COUNT(k) ((void)0)
 #endif
@@ -1576,8 +1579,15 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     int qit1 = 0;
     // the previous multipliers are still needed if this attempt is rejected: the QP writes to the spare copy
     st = gi_solve(blk, cons, s.gi, nv, ne, ld, L.m, 0, w + L.oLam + L.m, cfg.max_qp_iter, cfg.qp_tol, &qit1, &nact,
-                  (cfg.warm_qp != 0 && sc[SC_ITER] > 0.0) ? lam_prev : nullptr, L.mc);
+                  (cfg.warm_qp != 0 && sc[SC_ITER] > 0.0 && sc[SC_DMAX] <= 1.0) ? lam_prev : nullptr, L.mc);    // hit rate 4 % above |d| = 1
     have_j = false;                     // R^-1 has overwritten the staged Jacobians
+#if defined(FTMPC_DEBUG_COUNTERS) && !defined(__CUDACC__)
+    if (cfg.warm_qp != 0 && sc[SC_ITER] > 0.0) {       // warm-start outcome binned by the size of the previous step
+        const double dm = sc[SC_DMAX];
+        const int bin = dm > 1.0 ? 0 : (dm > 0.1 ? 1 : (dm > 1e-2 ? 2 : 3));
+        FT_DBG_COUNT2(bin, g_ftmpc_warm_hit ? 1 : 0);
+    }
+#endif
     blk.mark(PH_GI);
     qit += qit1;
     if (sigma > 0.0 && st == GI_OK) {       // every predicted-active row must be active in the QP solution

@@ -13,7 +13,7 @@
 #include <omp.h>
 #endif
 #define FTMPC_DEBUG_COUNTERS 1
-namespace ftmpc { long g_ftmpc_dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0}; }
+namespace ftmpc { long g_ftmpc_dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long g_ftmpc_dbg2[8] = {0, 0, 0, 0, 0, 0, 0, 0}; thread_local int g_ftmpc_warm_hit = 0; }
 #include "ftmpc_alloc.cuh"
 using namespace ftmpc;
 
@@ -107,6 +107,7 @@ int ftmpc_cpu_allocate(const ftmpc_config* cfg, int batch, const double* u_des, 
 
 void ftmpc_cpu_debug_counters(long* out, int reset) {
     for (int i = 0; i < 8; ++i) { out[i] = ftmpc::g_ftmpc_dbg[i]; if (reset) ftmpc::g_ftmpc_dbg[i] = 0; }
+    for (int i = 0; i < 8; ++i) { out[8 + i] = ftmpc::g_ftmpc_dbg2[i]; if (reset) ftmpc::g_ftmpc_dbg2[i] = 0; }
 }
 
 // read back per-instance scalars of the workspace (diagnostics)
