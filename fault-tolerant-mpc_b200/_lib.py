@@ -20,10 +20,10 @@ MAX_POLY, MAX_ROOT = 32, 16
 
 PHASE_NAMES = ['ls', 'lin', 'condense', 'cholesky', 'inverse', 'qp_setup', 'qp_active_set', 'qp_post', 'out',
                'ls_rollout', 'ls_eval', 'ls_terminal', 'chol_panel', 'chol_syrk', 'gi_select', 'gi_d', 'gi_z', 'gi_step', 'gi_update',
-               'gi_drop', 'lin_jac', 'lin_costate', 'cond_pre', 'cond_col', 'cond_blk',
+               'gi_drop', 'lin_jac', 'lin_costate', 'cond_pre', 'cond_col', 'cond_blk', 'warm_d0', 'warm_qr', 'warm_solve', 'warm_E',
                'n_instances', 'n_sqp_iter', 'n_condense', 'n_chol_fail', 'n_qp', 'n_gi_iter', 'n_gi_drop', 'n_ls_backtrack', 'n_gi_warm_ok', 'n_gi_warm_miss']
 N_PHASES = len(PHASE_NAMES)
-N_CYCLE_PHASES = 25
+N_CYCLE_PHASES = 29
 ST_OK, ST_MAXITER, ST_QPFAIL, ST_INFEASIBLE, ST_ALLOC = 0, 1, 2, 3, 4
 
 _PKG = Path(__file__).resolve().parent

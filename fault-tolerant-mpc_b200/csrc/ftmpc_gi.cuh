@@ -479,12 +479,59 @@ __device__ __forceinline__ void axpy_ilp(double* __restrict__ e, const double* _
 //     reflectors (partial dot, one shuffle, update) and stores it once -- two sweeps over E instead of three per
 //     added constraint.
 #define FTMPC_GI_HALF 61
+#define FTMPC_GI_QUARTER 31
+__device__ __noinline__ void gi_warm_apply_rows(const double* Dm, const double* vk0, const double* fk, const double* y,
+                                                double* E, double* xe, int nv, int ne, int ld, int q0, int tid, int nt) {
+    // a QUARTER row (31 columns) per thread, rows in rounds of nt/4: half rows (61 registers + 61 operands in flight)
+    // do not fit the register file
+    const int quarter = tid & 3;
+    const int c0 = quarter * FTMPC_GI_QUARTER;
+    const int rows_per_round = nt >> 2, rows_cov = (nt >> 1) < ne ? (nt >> 1) : ne;
+    for (int r0 = 0; r0 < rows_cov; r0 += rows_per_round) {
+        const int row = r0 + (tid >> 2);
+        const bool live = row < rows_cov;
+        double e[FTMPC_GI_QUARTER];
+        const double* er = E + (size_t)(live ? row : 0) * ld;
+#pragma unroll
+        for (int c = 0; c < FTMPC_GI_QUARTER; ++c) e[c] = (live && c0 + c < nv) ? er[c0 + c] : 0.0;
+        for (int k = 0; k < q0; ++k) {
+            const double* dk = Dm + (size_t)k * nv;
+            const double v0 = vk0[k], f = fk[k];
+            double vv[FTMPC_GI_QUARTER];
+            double a = 0.0;
+#pragma unroll
+            for (int c = 0; c < FTMPC_GI_QUARTER; ++c) {
+                const int col = c0 + c;
+                vv[c] = (col > k && col < nv) ? dk[col] : ((col == k) ? v0 : 0.0);
+                a += vv[c] * e[c];
+            }
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            const double wv = f * a;
+#pragma unroll
+            for (int c = 0; c < FTMPC_GI_QUARTER; ++c) e[c] -= wv * vv[c];
+        }
+        if (live) {
+            double* ew = E + (size_t)row * ld;
+#pragma unroll
+            for (int c = 0; c < FTMPC_GI_QUARTER; ++c) if (c0 + c < nv) ew[c0 + c] = e[c];
+        }
+        // x = x_unc - E[:, :q0] y : the first q0 <= 40 columns sit in quarters 0 and 1
+        double a = 0.0;
+#pragma unroll
+        for (int c = 0; c < FTMPC_GI_QUARTER; ++c) if (c0 + c < q0) a += e[c] * y[c0 + c];
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        if (live && quarter == 0) xe[row] -= a;
+    }
+}
+
 template <class Cons>
 __device__ __forceinline__ int gi_warm_start(CudaBlock& blk, const Cons& cons, const GiWork& w, int nv, int ne, int ld, int m,
                                              int meq, const double* lam_warm, int m_warm, double* xe_save) {
     const int tid = blk.tid(), nt = blk.nthreads(), lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     if (!lam_warm || meq != 0) return 0;
-    if (nv > 2 * FTMPC_GI_HALF || ne > (nt >> 1) + nw)                     // shapes the register path does not cover
+    if (nv > 4 * FTMPC_GI_QUARTER || ne > (nt >> 1) + nw)                  // shapes the register path does not cover
         return gi_warm_start<CudaBlock, Cons>(blk, cons, w, nv, ne, ld, m, meq, lam_warm, m_warm, xe_save);
     const int cap = (nv * (nv + 1) / 2 + 1 - FTMPC_GI_WARM_OFF) / nv;
     if (cap < 1) return 0;
@@ -528,6 +575,7 @@ __device__ __forceinline__ int gi_warm_start(CudaBlock& blk, const Cons& cons, c
         }
     }
     blk.sync();
+    blk.mark(PH_WS_D0);
     // ---- Householder QR: step k = reflector from column k (rows k..nv-1), applied to columns k+1..q0-1
     for (int k = 0; k < q0; ++k) {
         const double* dk = Dm + (size_t)k * nv;
@@ -558,6 +606,7 @@ __device__ __forceinline__ int gi_warm_start(CudaBlock& blk, const Cons& cons, c
         }
         blk.sync();
     }
+    blk.mark(PH_WS_QR);
     // ---- R^-1 (packed upper, by columns): R[j][c] = Dm[c][j] (j < c), R[c][c] = rho[c]
     for (int c = tid; c < q0; c += nt) {
         double* col = w.Ui + gi_tri(c);
@@ -587,47 +636,12 @@ __device__ __forceinline__ int gi_warm_start(CudaBlock& blk, const Cons& cons, c
             if (-a < -1e-9 * fmax(1.0, umax)) bad = 1;
         }
     }
-    if (blk.any(bad)) return 0;                   // a predicted row wants a negative multiplier: cold start, E untouched
-    // ---- E <- E Q and x = x_unc - E[:, :q0] y, half a row per thread
-    {
-        const int row = tid >> 1, half = tid & 1;
-        const int c0 = half * FTMPC_GI_HALF;
-        const bool live = row < ne;
-        double e[FTMPC_GI_HALF];
-        const double* er = w.E + (size_t)(live ? row : 0) * ld;
-#pragma unroll
-        for (int c = 0; c < FTMPC_GI_HALF; ++c) e[c] = (live && c0 + c < nv) ? er[c0 + c] : 0.0;
-        for (int k = 0; k < q0; ++k) {
-            const double* dk = Dm + (size_t)k * nv;
-            const double v0 = vk0[k], f = fk[k];
-            double a = 0.0;
-#pragma unroll
-            for (int c = 0; c < FTMPC_GI_HALF; ++c) {
-                const int col = c0 + c;
-                const double vv = (col > k && col < nv) ? dk[col] : ((col == k) ? v0 : 0.0);
-                a += vv * e[c];
-            }
-            a += __shfl_xor_sync(0xffffffffu, a, 1);
-            const double wv = f * a;
-#pragma unroll
-            for (int c = 0; c < FTMPC_GI_HALF; ++c) {
-                const int col = c0 + c;
-                const double vv = (col > k && col < nv) ? dk[col] : ((col == k) ? v0 : 0.0);
-                e[c] -= wv * vv;
-            }
-        }
-        if (live) {
-            double* ew = w.E + (size_t)row * ld;
-#pragma unroll
-            for (int c = 0; c < FTMPC_GI_HALF; ++c) if (c0 + c < nv) ew[c0 + c] = e[c];
-            if (half == 0) {                       // q0 <= 40 < FTMPC_GI_HALF: the first q0 columns sit in half 0
-                double a = 0.0;
-#pragma unroll
-                for (int c = 0; c < FTMPC_GI_WARM_MAX; ++c) if (c < q0) a += e[c] * w.d[c];
-                w.xe[row] -= a;
-            }
-        }
-    }
+    const int anybad = blk.any(bad);
+    blk.mark(PH_WS_SOLVE);
+    if (anybad) return 0;                         // a predicted row wants a negative multiplier: cold start, E untouched
+    // ---- E <- E Q and x = x_unc - E[:, :q0] y, half a row per thread (out of line: inside this kernel the 61 row
+    //      registers would be spilled to local memory, which is what made a first version slower than the adds it replaces)
+    gi_warm_apply_rows(Dm, vk0, fk, w.d, w.E, w.xe, nv, ne, ld, q0, tid, nt);
     // rows beyond the lane-pair range: one warp each, in shared memory
     for (int row = (nt >> 1) + warp; row < ne; row += nw) {
         double* e = w.E + (size_t)row * ld;
@@ -652,6 +666,7 @@ __device__ __forceinline__ int gi_warm_start(CudaBlock& blk, const Cons& cons, c
     blk.sync();
     for (int i = tid; i < m; i += nt) w.s[i] = cons.slack(i, w.xe, 1.0);
     blk.sync();
+    blk.mark(PH_WS_E);
     return q0;
 }
 

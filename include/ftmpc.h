@@ -117,7 +117,7 @@ int ftmpc_step(ftmpc_handle h, int batch, const double* state, const double* xre
  * phase_cycles[i] = SM cycles summed over all CTAs spent in phase i:
  *   0 step acceptance + rollout, 1 linearisation (Jacobians, costates, stage Hessians), 2 condensing, 3 Cholesky,
  *   4 J = L^-T, 5 QP set-up, 6 dual active-set iterations, 7 QP post-processing, 8 result write-out. */
-#define FTMPC_N_PHASES 35   /* 9 coarse phases, 16 sub-phases, 10 event counters: names in ft_mpc_b200._lib.PHASE_NAMES */
+#define FTMPC_N_PHASES 39   /* 9 coarse phases, 20 sub-phases, 10 event counters: names in ft_mpc_b200._lib.PHASE_NAMES */
 int ftmpc_profile_enable(ftmpc_handle h, int enable);
 int ftmpc_profile_read(ftmpc_handle h, void* stream, double* kernel_ms, int64_t* phase_cycles, int n_phase);
 /* number of kernels ftmpc_step launched on its last call */
