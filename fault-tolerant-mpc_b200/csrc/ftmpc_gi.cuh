@@ -480,13 +480,21 @@ __device__ __forceinline__ void axpy_ilp(double* __restrict__ e, const double* _
 //     added constraint.
 #define FTMPC_GI_HALF 61
 #define FTMPC_GI_QUARTER 31
+__device__ __forceinline__ double lds_f64(unsigned addr) {       // shared-memory load from a 32-bit shared address
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
 __device__ __noinline__ void gi_warm_apply_rows(const double* Dm, const double* vk0, const double* fk, const double* y,
                                                 double* E, double* xe, int nv, int ne, int ld, int q0, int tid, int nt) {
-    // a QUARTER row (31 columns) per thread, rows in rounds of nt/4: half rows (61 registers + 61 operands in flight)
-    // do not fit the register file
+    // A QUARTER row (31 columns) per thread, rows in rounds of nt/4: half rows (61 registers + 61 operands in flight), or
+    // two quarter rows, do not fit the register file.  The function is out of line, so the operand pointer is generic;
+    // when it points to shared memory the loads are issued as ld.shared explicitly.
     const int quarter = tid & 3;
     const int c0 = quarter * FTMPC_GI_QUARTER;
     const int rows_per_round = nt >> 2, rows_cov = (nt >> 1) < ne ? (nt >> 1) : ne;
+    const bool in_smem = __isShared(Dm);
+    const unsigned dm_s = in_smem ? (unsigned)__cvta_generic_to_shared(Dm) : 0u;
     for (int r0 = 0; r0 < rows_cov; r0 += rows_per_round) {
         const int row = r0 + (tid >> 2);
         const bool live = row < rows_cov;
@@ -495,15 +503,17 @@ __device__ __noinline__ void gi_warm_apply_rows(const double* Dm, const double* 
 #pragma unroll
         for (int c = 0; c < FTMPC_GI_QUARTER; ++c) e[c] = (live && c0 + c < nv) ? er[c0 + c] : 0.0;
         for (int k = 0; k < q0; ++k) {
-            const double* dk = Dm + (size_t)k * nv;
             const double v0 = vk0[k], f = fk[k];
             double vv[FTMPC_GI_QUARTER];
             double a = 0.0;
 #pragma unroll
             for (int c = 0; c < FTMPC_GI_QUARTER; ++c) {
                 const int col = c0 + c;
-                vv[c] = (col > k && col < nv) ? dk[col] : ((col == k) ? v0 : 0.0);
-                a += vv[c] * e[c];
+                double v = 0.0;
+                if (col > k && col < nv) v = in_smem ? lds_f64(dm_s + (unsigned)((k * nv + col) * 8)) : Dm[(size_t)k * nv + col];
+                else if (col == k) v = v0;
+                vv[c] = v;
+                a += v * e[c];
             }
             a += __shfl_xor_sync(0xffffffffu, a, 1);
             a += __shfl_xor_sync(0xffffffffu, a, 2);
