@@ -59,7 +59,7 @@ def make_config(horizon: int, Q, R, *, dt: float, mass: float, inertia, r, f_vir
                 terminal: dict | None = None, n_hull_sets: int = 1, max_sqp_iter: int = 60, max_qp_iter: int = 0,
                 poll_every: int = 0, sqp_tol: float = 1e-8, qp_tol: float = 1e-10, feas_tol: float = 1e-7,
                 act_tol: float = 1e-7, rho_slack: float = 1e4, clip_tol: float = 1e-9, theta_first: float = 0.5,
-                theta_growth: float = 2.0, blend_dmax: float = 1.0, warm_qp: int = 1) -> FtmpcConfig:
+                theta_growth: float = 2.0, blend_dmax: float = 1.0, warm_qp: int = 0) -> FtmpcConfig:
     term = terminal or load_terminal()
     if len(term["poly"]) > MAX_POLY or len(term["root"]) > MAX_ROOT:
         raise ValueError("terminal cost has more terms than the term table holds")

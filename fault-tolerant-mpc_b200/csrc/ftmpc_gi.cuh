@@ -505,7 +505,7 @@ __device__ __noinline__ void gi_warm_apply_rows(const double* Dm, const double* 
         for (int k = 0; k < q0; ++k) {
             const double v0 = vk0[k], f = fk[k];
             double vv[FTMPC_GI_QUARTER];
-            double a = 0.0;
+            double a4[4] = {0.0, 0.0, 0.0, 0.0};          // four partial sums: the 31-long dependent FMA chain was the bottleneck
 #pragma unroll
             for (int c = 0; c < FTMPC_GI_QUARTER; ++c) {
                 const int col = c0 + c;
@@ -513,8 +513,9 @@ __device__ __noinline__ void gi_warm_apply_rows(const double* Dm, const double* 
                 if (col > k && col < nv) v = in_smem ? lds_f64(dm_s + (unsigned)((k * nv + col) * 8)) : Dm[(size_t)k * nv + col];
                 else if (col == k) v = v0;
                 vv[c] = v;
-                a += v * e[c];
+                a4[c & 3] += v * e[c];
             }
+            double a = (a4[0] + a4[1]) + (a4[2] + a4[3]);
             a += __shfl_xor_sync(0xffffffffu, a, 1);
             a += __shfl_xor_sync(0xffffffffu, a, 2);
             const double wv = f * a;

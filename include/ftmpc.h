@@ -60,7 +60,8 @@ typedef struct ftmpc_config {
     int32_t max_sqp_iter;      /* outer iteration cap (default 60)                                          */
     int32_t max_qp_iter;       /* active-set iteration cap per QP (default 20*(n+m))                        */
     int32_t poll_every;        /* reserved (unused: ftmpc_step never synchronises; a persistent CTA stops iterating when its instance converges) */
-    int32_t warm_qp;           /* 1 = start each QP from the previous QP's active set (gi_warm_start), default 1 */
+    int32_t warm_qp;           /* 1 = start each QP from the previous QP's active set (gi_warm_start): -40 % active-set iterations, same
+                                  results; default 0 -- on the B200 the bulk update currently costs what it saves (profiles/README.md) */
     int32_t n_poly, n_root, n_hull_sets;
     double dt, mass, inertia[3], r[3], f_virt[3], max_thrust;   /* sys_model.py:52-61, spiral_parameters.py:33-39 */
     double Q[FTMPC_NE], R[FTMPC_NU];                            /* reactive.yaml:32-33                      */

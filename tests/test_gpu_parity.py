@@ -343,6 +343,21 @@ def test_gpu_matches_cpu_port(L, built, golden):
     assert np.array_equal(g["active"].view(np.uint32)[ok], c["active"][ok])
 
 
+def test_qp_warm_start_gives_identical_results(L, golden):
+    """warm_qp = 1 (working set of each QP started from the previous QP's active set) must not change the answer"""
+    N = 20
+    ks = [k for k in H.cases_with_horizon(golden, N) if not golden["warm"][k]]
+    eng0, out0 = run_cases(golden, ks, N)
+    eng1, out1 = run_cases(golden, ks, N, warm_qp=1)
+    assert (out0["status"] == 0).all() and (out1["status"] == 0).all()
+    assert np.abs(out0["u0"] - out1["u0"]).max() < 2e-6 and np.abs(out0["thrust"] - out1["thrust"]).max() < 2e-6
+    assert np.array_equal(out0["active"], out1["active"])
+    assert out1["iters"][:, 1].sum() < out0["iters"][:, 1].sum()          # fewer active-set iterations
+    for j, k in enumerate(ks):
+        u0 = golden["U"][k, 0]
+        assert np.abs(out1["u0"][j] - u0).max() <= 1e-5 * max(1.0, np.abs(u0).max())
+
+
 def test_long_horizon_global_scratch_path(L, built):
     """N = 30: the QP scratch (275 KB) no longer fits in shared memory -> k_solve<true> keeps it in a per-CTA global
     slice and the generic condensing / factorisation routines run; results must agree with the CPU port"""
