@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances per CPU step (0 = auto)")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--solver-opts", default="{}", help='JSON dict of ftmpc_config overrides for experiments, e.g. {"warm_qp": 1}')
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -173,6 +174,8 @@ def main():
                           f"{a.batch} instances per GPU (BASELINE configs[3] shard)", "horizon": N, "batch_per_gpu": a.batch,
               "global_batch": a.batch * world, "seed": 1, "parallelism": f"dp{world} (independent instances, no data-path collective)",
               "l2_policy": "per-step working set (inputs + per-instance workspace) exceeds the 126 MB L2"}
+    if a.solver_opts != "{}":
+        config["solver_opts"] = json.loads(a.solver_opts)
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
     if a.impl == "reference":
@@ -214,7 +217,7 @@ def main():
     cells, states, scen, xref = make_workload(Btot, N)
     lo, hi = shard_bounds(Btot, rank, world)
     ctrl = SpiralingController(SystemModel(0.1), horizon=N, weights={"Q": [1, 1, 1, 1, 1, 1, 2, 2, 2], "R": [.1, .1, .1, .01, .01, .01]},
-                               fault_sets=cells, device=devs)
+                               fault_sets=cells, device=devs, **json.loads(a.solver_opts))
     eng = ctrl.engine
     f64 = torch.float64
     st_d = torch.tensor(states[lo:hi], dtype=f64, device=devs)
