@@ -1348,24 +1348,34 @@ __device__ __forceinline__ int chol_inv_blocks(CudaBlock& blk, int Nb, int ld, d
         }
     }
     blk.mark(PH_CHOL);
-    // ---- X = L^-1 by block wavefronts; S accumulates in the (now dead) H registers
+    // ---- X = L^-1 by block wavefronts; S accumulates in the (now dead) H registers.
+    // The accumulators start from zero, so the block -> thread assignment is free: here it is COLUMN-major (a warp holds
+    // one block column xj and consecutive block rows xi).  The X operand X_{kb,xj} is then the same for the whole warp
+    // (broadcast) and the L operand rows are 6 rows apart (2-way bank conflict); with the row-major assignment of the
+    // factorisation the X operand was read with a 4-way conflict.
+    int xi = -1, xj = 0;
+    if (tid < Nb * (Nb + 1) / 2) {
+        int off = 0;
+        while (off + (Nb - xj) <= tid) { off += Nb - xj; ++xj; }
+        xi = xj + (tid - off);
+    }
 #pragma unroll
     for (int i = 0; i < 6; ++i)
 #pragma unroll
         for (int j = 0; j < 6; ++j) acc[i][j] = 0.0;
     for (int sdist = 1; sdist < Nb; ++sdist) {
-        if (bi >= 0 && bi - bj >= sdist) {
-            const int kb = bj + sdist - 1;
-            double Xb[6][6];                               // Xb[b][m] = X_{kb,bj}[m][b]
+        if (xi >= 0 && xi - xj >= sdist) {
+            const int kb = xj + sdist - 1;
+            double Xb[6][6];                               // Xb[b][m] = X_{kb,xj}[m][b]
 #pragma unroll
             for (int b = 0; b < 6; ++b) {
-                const double* er = E + (size_t)(6 * bj + b) * ld + 6 * kb;
+                const double* er = E + (size_t)(6 * xj + b) * ld + 6 * kb;
 #pragma unroll
                 for (int m = 0; m < 6; ++m) Xb[b][m] = er[m];
             }
 #pragma unroll
             for (int a = 0; a < 6; ++a) {
-                const double* er = E + (size_t)(6 * bi + a) * ld + 6 * kb;
+                const double* er = E + (size_t)(6 * xi + a) * ld + 6 * kb;
                 double La[6];
 #pragma unroll
                 for (int m = 0; m < 6; ++m) La[m] = er[m];
@@ -1377,8 +1387,8 @@ __device__ __forceinline__ int chol_inv_blocks(CudaBlock& blk, int Nb, int ld, d
                     acc[a][b] = v;
                 }
             }
-            if (bi - bj == sdist) {
-                const double* lk = linv + (size_t)bi * 36;
+            if (xi - xj == sdist) {
+                const double* lk = linv + (size_t)xi * 36;
 #pragma unroll
                 for (int b = 0; b < 6; ++b) {
                     double x[6];
@@ -1389,7 +1399,7 @@ __device__ __forceinline__ int chol_inv_blocks(CudaBlock& blk, int Nb, int ld, d
                         for (int m = 0; m < 6; ++m) if (m <= a) v += lk[a * 6 + m] * acc[m][b];
                         x[a] = -v;
                     }
-                    double* er = E + (size_t)(6 * bj + b) * ld + 6 * bi;
+                    double* er = E + (size_t)(6 * xj + b) * ld + 6 * xi;
 #pragma unroll
                     for (int a = 0; a < 6; ++a) er[a] = x[a];
                 }
@@ -1398,10 +1408,10 @@ __device__ __forceinline__ int chol_inv_blocks(CudaBlock& blk, int Nb, int ld, d
         blk.sync();
     }
     // the strictly lower blocks (L) are dead: J is upper triangular
-    if (bi > bj) {
+    if (xi > xj) {
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-            double* er = E + (size_t)(6 * bi + i) * ld + 6 * bj;
+            double* er = E + (size_t)(6 * xi + i) * ld + 6 * xj;
 #pragma unroll
             for (int j = 0; j < 6; ++j) er[j] = 0.0;
         }
