@@ -27,7 +27,8 @@ N_CYCLE_PHASES = 29
 ST_OK, ST_MAXITER, ST_QPFAIL, ST_INFEASIBLE, ST_ALLOC = 0, 1, 2, 3, 4
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "csrc" / "libftmpc.so"
+# FTMPC_LIB selects another build of the same library (A/B experiments on the GPU box); no fallback either way
+LIB_PATH = Path(os.environ["FTMPC_LIB"]) if os.environ.get("FTMPC_LIB") else _PKG / "csrc" / "libftmpc.so"
 DATA_DIR = _PKG / "data"
 
 
