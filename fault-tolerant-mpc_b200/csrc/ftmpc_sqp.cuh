@@ -1064,8 +1064,10 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
     if (tid == 0) { s.g[n] = 0.0; s.ga[n] = 0.0; }
     for (int r = tid; r < FTMPC_NX; r += nt) s.G[r * ld + n] = 0.0;
     // ---- roles
-    const int a = tid;                             // column role (a < n)
-    const int ta = a / FTMPC_NU, ja = a - ta * FTMPC_NU;
+    // column role: taken by the LAST n threads of the block -- their block role (large bi) has the least work, and
+    // the column phase of stage t + 1 runs in the same barrier interval as the block phase of stage t
+    const int a = tid - (nt - n);                  // column index (0 <= a < n) or negative
+    const int ta = (a >= 0) ? a / FTMPC_NU : 0, ja = a - ta * FTMPC_NU;
     const int pa_ = 7 * ta + ja;                   // column a inside a panel
     int bi = -1, bj = 0;                           // block role (tid < nblk)
     if (tid < nblk) {
@@ -1084,10 +1086,13 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
         for (int j = 0; j < 6; ++j) acc[i][j] = 0.0;
     blk.sync();
     blk.mark(PH_COND_PRE);
-    for (int t = 0; t <= N; ++t) {
-        double* buf = buf0 + (size_t)(t & 1) * 32 * ldp;
-        // ---------------- column phase
-        if (a < n) {
+    // software pipeline: interval tt runs the column phase of stage tt + 1 (writes panel (tt + 1) & 1) and the block
+    // phase of stage tt (reads panel tt & 1, published one barrier earlier); one barrier per stage
+    for (int tt = -1; tt <= N; ++tt) {
+        // ---------------- column phase of stage t = tt + 1
+        if (a >= 0 && tt < N) {
+            const int t = tt + 1;
+            double* buf = buf0 + (size_t)(t & 1) * 32 * ldp;
             if (ta < t) {
                 if (t < N) {
                     const double* jz = Jz + (size_t)t * 169;
@@ -1158,10 +1163,10 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
                 }
             }
         }
-        blk.sync();
-        blk.mark(PH_COND_COL);
-        // ---------------- block phase
-        if (bi >= 0) {
+        // ---------------- block phase of stage t = tt
+        if (bi >= 0 && tt >= 0) {
+            const int t = tt;
+            const double* buf = buf0 + (size_t)(t & 1) * 32 * ldp;
             if (bi < t) {
                 const int K = (t < N) ? FTMPC_NX : FTMPC_NE;
                 const double* Pa = buf + 7 * bi;
@@ -1205,9 +1210,9 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
                 }
             }
         }
+        blk.sync();
         blk.mark(PH_COND_BLK);                     // thread 0 owns block (0,0), the longest-lived accumulator
     }
-    blk.sync();                                    // the panels are dead
     if (hb) {                                      // hand the blocks over in registers
         hb->fast = true;
         hb->bi = bi;
