@@ -47,7 +47,7 @@ class FtmpcConfig(C.Structure):
         ("root_e", (C.c_int8 * NE) * MAX_ROOT),
         ("term_quad", C.c_double * (NE * NE)),
         ("sqp_tol", C.c_double), ("qp_tol", C.c_double), ("feas_tol", C.c_double), ("act_tol", C.c_double),
-        ("rho_slack", C.c_double), ("clip_tol", C.c_double), ("theta_first", C.c_double), ("theta_growth", C.c_double), ("blend_dmax", C.c_double),
+        ("rho_slack", C.c_double), ("clip_tol", C.c_double), ("theta_first", C.c_double), ("theta_growth", C.c_double), ("blend_dmax", C.c_double), ("fast_dmax", C.c_double),
     ]
 
 
@@ -60,7 +60,7 @@ def make_config(horizon: int, Q, R, *, dt: float, mass: float, inertia, r, f_vir
                 terminal: dict | None = None, n_hull_sets: int = 1, max_sqp_iter: int = 60, max_qp_iter: int = 0,
                 poll_every: int = 0, sqp_tol: float = 1e-8, qp_tol: float = 1e-10, feas_tol: float = 1e-7,
                 act_tol: float = 1e-7, rho_slack: float = 1e4, clip_tol: float = 1e-9, theta_first: float = 0.5,
-                theta_growth: float = 2.0, blend_dmax: float = 1.0, warm_qp: int = 0) -> FtmpcConfig:
+                theta_growth: float = 2.0, blend_dmax: float = 1.0, warm_qp: int = 0, fast_dmax: float = 1e-5) -> FtmpcConfig:
     term = terminal or load_terminal()
     if len(term["poly"]) > MAX_POLY or len(term["root"]) > MAX_ROOT:
         raise ValueError("terminal cost has more terms than the term table holds")
@@ -106,6 +106,7 @@ def make_config(horizon: int, Q, R, *, dt: float, mass: float, inertia, r, f_vir
     cfg.sqp_tol, cfg.qp_tol, cfg.feas_tol = sqp_tol, qp_tol, feas_tol
     cfg.act_tol, cfg.rho_slack, cfg.clip_tol = act_tol, rho_slack, clip_tol
     cfg.theta_first, cfg.theta_growth, cfg.blend_dmax = theta_first, theta_growth, blend_dmax
+    cfg.fast_dmax = fast_dmax
     return cfg
 
 

@@ -83,6 +83,11 @@ struct CudaBlock {
         const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
         if ((threadIdx.x & 31) == 0) b[w] = v;
         __syncthreads();
+        if (nw == 8) {                               // the product configuration: independent loads, fixed order
+            const double2 p0 = *reinterpret_cast<const double2*>(b), p1 = *reinterpret_cast<const double2*>(b + 2);
+            const double2 p2 = *reinterpret_cast<const double2*>(b + 4), p3 = *reinterpret_cast<const double2*>(b + 6);
+            return ((p0.x + p0.y) + (p1.x + p1.y)) + ((p2.x + p2.y) + (p3.x + p3.y));
+        }
         double r = 0.0;
         for (int i = 0; i < nw; ++i) r += b[i];
         return r;
@@ -93,6 +98,11 @@ struct CudaBlock {
         const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
         if ((threadIdx.x & 31) == 0) b[w] = v;
         __syncthreads();
+        if (nw == 8) {
+            const double2 p0 = *reinterpret_cast<const double2*>(b), p1 = *reinterpret_cast<const double2*>(b + 2);
+            const double2 p2 = *reinterpret_cast<const double2*>(b + 4), p3 = *reinterpret_cast<const double2*>(b + 6);
+            return fmax(fmax(fmax(p0.x, p0.y), fmax(p1.x, p1.y)), fmax(fmax(p2.x, p2.y), fmax(p3.x, p3.y)));
+        }
         double r = b[0];
         for (int i = 1; i < nw; ++i) r = fmax(r, b[i]);
         return r;
@@ -107,6 +117,22 @@ struct CudaBlock {
         const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
         if ((threadIdx.x & 31) == 0) { b[w] = v; b[32 + w] = (double)idx; }
         __syncthreads();
+        if (nw == 8) {                               // all sixteen loads in flight at once, then a compare tree
+            double vv[8], ii[8];
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+                const double2 pv = *reinterpret_cast<const double2*>(b + i), pi = *reinterpret_cast<const double2*>(b + 32 + i);
+                vv[i] = pv.x; vv[i + 1] = pv.y; ii[i] = pi.x; ii[i + 1] = pi.y;
+            }
+#pragma unroll
+            for (int st = 1; st < 8; st <<= 1)
+#pragma unroll
+                for (int i = 0; i < 8; i += 2 * st)
+                    if (vv[i + st] < vv[i] || (vv[i + st] == vv[i] && ii[i + st] < ii[i])) { vv[i] = vv[i + st]; ii[i] = ii[i + st]; }
+            v = vv[0];
+            idx = (int)ii[0];
+            return;
+        }
         double rv = b[0];
         int ri = (int)b[32];
         for (int i = 1; i < nw; ++i) {

@@ -447,6 +447,52 @@ __device__ __forceinline__ double dot_ilp(const double* __restrict__ a, const do
     for (; k < k1; ++k) s0 += a[k] * b[k];
     return (s0 + s1) + (s2 + s3);
 }
+// The same two row kernels for a LANE PAIR per row: lane `part` of the pair owns the columns of its parity (k, k + 2, ...).
+// With rows 2 apart inside a half-warp (see gi_pair_row) the 16 lanes of a shared-memory phase hit 16 distinct 8-byte
+// banks for any odd row stride, so the pair split costs no extra wavefronts, every thread of the block works, and the
+// dependent chain per thread is half as long.
+__device__ __forceinline__ double dot_stride2(const double* __restrict__ a, const double* __restrict__ b, int k0, int k1) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int k = k0;
+    for (; k + 14 < k1; k += 16) {
+        double x[8], y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { x[j] = a[k + 2 * j]; y[j] = b[k + 2 * j]; }
+        s0 += x[0] * y[0]; s1 += x[1] * y[1]; s2 += x[2] * y[2]; s3 += x[3] * y[3];
+        s0 += x[4] * y[4]; s1 += x[5] * y[5]; s2 += x[6] * y[6]; s3 += x[7] * y[7];
+    }
+    for (; k + 6 < k1; k += 8) {
+        double x[4], y[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { x[j] = a[k + 2 * j]; y[j] = b[k + 2 * j]; }
+        s0 += x[0] * y[0]; s1 += x[1] * y[1]; s2 += x[2] * y[2]; s3 += x[3] * y[3];
+    }
+    for (; k < k1; k += 2) s0 += a[k] * b[k];
+    return (s0 + s1) + (s2 + s3);
+}
+__device__ __forceinline__ void axpy_stride2(double* __restrict__ e, const double* __restrict__ d, double wv, int k0, int k1) {
+    int k = k0;
+    for (; k + 14 < k1; k += 16) {
+        double x[8], y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { x[j] = e[k + 2 * j]; y[j] = d[k + 2 * j]; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[k + 2 * j] = x[j] - wv * y[j];
+    }
+    for (; k + 6 < k1; k += 8) {
+        double x[4], y[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { x[j] = e[k + 2 * j]; y[j] = d[k + 2 * j]; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) e[k + 2 * j] = x[j] - wv * y[j];
+    }
+    for (; k < k1; k += 2) e[k] -= wv * d[k];
+}
+// row of a lane pair inside a group of nt / 2 rows: half-warp hw holds the rows  16 (hw / 2) + (hw & 1) + 2 j,  j = 0..7
+__device__ __forceinline__ int gi_pair_row(int tid) {
+    const int hw = tid >> 4, j = (tid & 15) >> 1;
+    return ((hw >> 1) << 4) + (hw & 1) + (j << 1);
+}
 // e[k] -= wv * d[k], k in [k0, k1)
 __device__ __forceinline__ void axpy_ilp(double* __restrict__ e, const double* __restrict__ d, double wv, int k0, int k1) {
     int k = k0;
@@ -687,6 +733,10 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
                                         const double* lam_warm = nullptr, int m_warm = 0) {
     const int tid = blk.tid(), nt = blk.nthreads(), lane = tid & 31, warp = tid >> 5, nw = (nt + 31) >> 5;
     double* gsc = blk.scratch + 128;              // 64 doubles of block scratch reserved for this routine
+    // row sweeps over E: a lane pair per row (gi_pair_row), rpp = nt / 2 rows per pass; ne_main rows are covered by full
+    // passes, up to 2 nw rows left over after the last full pass are swept one per warp instead of paying a whole pass
+    const int rpp = nt >> 1, prow = gi_pair_row(tid), part = tid & 1;
+    const int ne_main = ((nt & 31) != 0) ? 0 : ((ne % rpp <= 2 * nw) ? ne - ne % rpp : ne);
     int q = 0, iters = 0, status = GI_OK;
     for (int i = tid; i < m; i += nt) {
         w.s[i] = cons.slack(i, w.xe, 1.0);
@@ -767,7 +817,22 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
             for (int i = 0; i < nw; ++i) { dn += gsc[i]; d2n += gsc[32 + i]; }
             // ze = E[:, q:] d[q:]  (thread per row: a lane-pair split was measured slower -- the two halves of a row
             // land on the same banks as their neighbours and double the shared-memory wavefronts)
-            for (int row = tid; row < ne; row += nt) w.ze[row] = dot_ilp(w.E + (size_t)row * ld, w.d, q, nv);
+            // -- lane pair per row, nt / 2 rows per pass; the few rows left over after the last full pass go one per warp
+            for (int rb = 0; rb < ne_main; rb += rpp) {
+                const int row = rb + prow;
+                double sv = 0.0;
+                if (row < ne_main) sv = dot_stride2(w.E + (size_t)row * ld, w.d, q + ((q ^ part) & 1), nv);
+                sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+                if (part == 0 && row < ne_main) w.ze[row] = sv;
+            }
+            for (int row = ne_main + warp; row < ne; row += nw) {
+                const double* e = w.E + (size_t)row * ld;
+                double sv = 0.0;
+                for (int k = q + lane; k < nv; k += 32) sv += e[k] * w.d[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+                if (lane == 0) w.ze[row] = sv;
+            }
             // r = R^-1 d[:q] and the dual step length
             double t1 = INFINITY;
             int l = 0x7fffffff;
@@ -816,7 +881,9 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
                 if (i >= meq && i != p && w.pos[i] < 0 && (v < nb || (v == nb && i < nbi))) { nb = v; nbi = i; }
             }
             sp += t * d2n;
-            blk.sync();
+            // a full step goes straight on to the update: it reads ze, d, r and writes E, R^-1, act/pos[p] -- nothing the
+            // sweep above writes (xe, u, s) or reads (pos[i], i != p) -- so the barrier is only needed before a drop
+            if (!full) blk.sync();
             blk.mark(PH_GI_STEP);
             if (full) {
                 const double alpha = sqrt(d2n);
@@ -826,11 +893,25 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
                 const double rho = -sg * alpha;
                 if (vv > 0.0) {
                     const double f = 2.0 / vv;
-                    for (int row = tid; row < ne; row += nt) {
+                    for (int rb = 0; rb < ne_main; rb += rpp) {
+                        const int row = rb + prow;
+                        const bool on = row < ne_main;
+                        double* e = w.E + (size_t)(on ? row : 0) * ld;
+                        const double eq = e[q];
+                        const double wv = f * (w.ze[on ? row : 0] + sg * alpha * eq);
+                        __syncwarp();                               // both lanes of the pair have read e[q]
+                        if (on) {
+                            if (((q ^ part) & 1) == 0) e[q] = eq - wv * (d0 + sg * alpha);
+                            axpy_stride2(e, w.d, wv, q + 1 + (((q + 1) ^ part) & 1), nv);
+                        }
+                    }
+                    for (int row = ne_main + warp; row < ne; row += nw) {
                         double* e = w.E + (size_t)row * ld;
-                        const double wv = f * (w.ze[row] + sg * alpha * e[q]);
-                        e[q] -= wv * (d0 + sg * alpha);
-                        axpy_ilp(e, w.d, wv, q + 1, nv);
+                        const double eq = e[q];
+                        const double wv = f * (w.ze[row] + sg * alpha * eq);
+                        __syncwarp();
+                        if (lane == 0) e[q] = eq - wv * (d0 + sg * alpha);
+                        for (int k = q + 1 + lane; k < nv; k += 32) e[k] -= wv * w.d[k];
                     }
                 }
                 double* col = w.Ui + gi_tri(q);

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
     k_solve(const __grid_constant__ ftmpc_config cfg, WsLayout L, StepIO io, int* queue, double* gscratch, size_t sdoubles,
             long long* prof) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ double red[192];
+    __shared__ __align__(16) double red[192];
     __shared__ int s_inst;
     double* scratch = GS ? gscratch + (size_t)blockIdx.x * sdoubles : smem;
     __shared__ double s_tfv[2 * FTMPC_NF];
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
                const double* x, const double* u, const double* xref, const double* gradV, const double* hessV,
                double theta, double* H, double* g, double* gscratch, size_t sdoubles) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ double red[192];
+    __shared__ __align__(16) double red[192];
     double* scratch = smem;
     (void)gscratch; (void)sdoubles;
     CudaBlock blk(red);
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
     k_qp_generic(int batch, int n, int m, const double* H, const double* g, const int32_t* ptr, const int32_t* idx,
                  const double* val, const double* b, double* x, double* lam, int32_t* status, int maxit, double tol) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ double red[192];
+    __shared__ __align__(16) double red[192];
     CudaBlock blk(red);
     const int ld = n | 1, tid = threadIdx.x, nt = blockDim.x;
     double* p = smem;

@@ -28,7 +28,7 @@ struct WsLayout {
 };
 enum {      // scalar slots
     SC_F = 0, SC_CSUM, SC_NU, SC_GD, SC_THETA, SC_DMAX, SC_DELTA, SC_LAMMAX, SC_STATUS, SC_ITER, SC_QPIT,
-    SC_NACT, SC_CHOLFAIL, SC_QPST, SC_ALPHA, SC_CMAX, SC_SIGMA, SC_HFAIL, SC_COUNT
+    SC_NACT, SC_CHOLFAIL, SC_QPST, SC_ALPHA, SC_CMAX, SC_SIGMA, SC_HFAIL, SC_DPREV, SC_COUNT
 };
 FT_HD WsLayout ws_layout(int N) {
     WsLayout L;
@@ -101,6 +101,15 @@ FT_HD void stage_wrench(const ftmpc_config& c, const double* u, const double* ur
 // gradient divided by a small curvature and never shrinks further, although the iterate no longer moves.
 FT_HD bool sqp_step_converged(const ftmpc_config& cfg, double dmax, double gd, double f) {
     return dmax <= cfg.sqp_tol || (dmax <= 100.0 * cfg.sqp_tol && fabs(gd) <= 1e-13 * fmax(1.0, fabs(f)));
+}
+// Early stop in the quadratic regime: the full step d_k just taken and the full step d_{k-1} before it both came from
+// the exact-Hessian QP (theta = 1; the augmented-Lagrangian convexification leaves the QP solution unchanged), so
+// |d_{k+1}| ~ C |d_k|^2 with C estimated by |d_k| / |d_{k-1}|^2.  When that prediction is a decade below sqp_tol the QP
+// that would only confirm it is not solved.  dprev = 0 disables the rule (phase_qp stores |d_{k-1}| only when iteration
+// k-1 qualified); fast_dmax = 0 in the configuration switches it off altogether.
+FT_HD bool sqp_fast_converged(const ftmpc_config& cfg, double dmax, double dprev, double alpha, double theta) {
+    return cfg.fast_dmax > 0.0 && alpha == 1.0 && theta == 1.0 && dprev > 0.0 && dmax < dprev && dmax <= cfg.fast_dmax &&
+           dmax * dmax * dmax <= 0.1 * cfg.sqp_tol * dprev * dprev;
 }
 
 // forward rollout at U + alpha*d: states, cost, constraint values (c <= 0 feasible).
@@ -189,7 +198,8 @@ FT_HD void phase_ls(const ftmpc_config& cfg, const WsLayout& L, const StepIO& io
         sc[SC_ALPHA] = alpha;
         if (!(f < INFINITY)) { sc[SC_STATUS] = FTMPC_ST_QPFAIL; return; }
         for (int i = 0; i < L.n; ++i) U[i] += alpha * D[i];
-        if (sqp_step_converged(cfg, sc[SC_DMAX], sc[SC_GD], sc[SC_F])) {
+        if (sqp_step_converged(cfg, sc[SC_DMAX], sc[SC_GD], sc[SC_F]) ||
+            sqp_fast_converged(cfg, sc[SC_DMAX], sc[SC_DPREV], alpha, sc[SC_THETA])) {
             sc[SC_STATUS] = (cmax <= cfg.feas_tol) ? FTMPC_ST_OK : FTMPC_ST_INFEASIBLE;
         } else if (sc[SC_ITER] >= cfg.max_sqp_iter) {
             sc[SC_STATUS] = FTMPC_ST_MAXITER;
@@ -302,7 +312,7 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
     double* C = w + L.oC;
     const LsScratch s = ls_carve(scratch, N);
     const int nterm = cfg.n_poly + cfg.n_root;
-    double nu = 1.0, phi0 = 0.0, dphi = 0.0, dmax = 0.0, iter = 0.0, gd_prev = 0.0, f_prev = 0.0;
+    double nu = 1.0, phi0 = 0.0, dphi = 0.0, dmax = 0.0, iter = 0.0, gd_prev = 0.0, f_prev = 0.0, dprev = 0.0, theta_qp = 0.0;
     if (first) {
         if (tid == 0) robot_to_center(dyn_consts(cfg), io.state + (size_t)inst * FTMPC_NX, X);      // spiraling_mpc.py:290
         const double* zw = io.z_warm + (size_t)inst * (L.n + (size_t)(N + 1) * FTMPC_NX);
@@ -322,6 +332,8 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
         gd_prev = sc[SC_GD];
         f_prev = sc[SC_F];
         iter = sc[SC_ITER] + 1.0;
+        dprev = sc[SC_DPREV];
+        theta_qp = sc[SC_THETA];
         blk.sync();                                   // everybody has read the scalars
         if (status != FTMPC_ST_RUNNING) return;
         if (qpst != 0.0) {
@@ -460,7 +472,7 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
             sc[SC_NU] = nu;
             sc[SC_ALPHA] = alpha;
             if (!finite) sc[SC_STATUS] = FTMPC_ST_QPFAIL;
-            else if (sqp_step_converged(cfg, dmax, gd_prev, f_prev)) sc[SC_STATUS] = (cmax <= cfg.feas_tol) ? FTMPC_ST_OK : FTMPC_ST_INFEASIBLE;
+            else if (sqp_step_converged(cfg, dmax, gd_prev, f_prev) || sqp_fast_converged(cfg, dmax, dprev, alpha, theta_qp)) sc[SC_STATUS] = (cmax <= cfg.feas_tol) ? FTMPC_ST_OK : FTMPC_ST_INFEASIBLE;
             else if (iter >= cfg.max_sqp_iter) sc[SC_STATUS] = FTMPC_ST_MAXITER;
         }
         if (finite || first) { sc[SC_F] = f; sc[SC_CSUM] = csum; sc[SC_CMAX] = cmax; }
@@ -1066,7 +1078,9 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
     // ---- roles
     // column role: taken by the LAST n threads of the block -- their block role (large bi) has the least work, and
     // the column phase of stage t + 1 runs in the same barrier interval as the block phase of stage t
-    const int a = tid - (nt - n);                  // column index (0 <= a < n) or negative
+    // (reversed: the first columns -- the only ones alive in the early stages -- sit in the LAST warp, which shares its
+    // scheduler with block warp 3, idle until stage 14; warp 0 owns the blocks that are busy from stage 1 on)
+    const int a = (nt - 1 - tid < n) ? nt - 1 - tid : -1;   // column index (0 <= a < n) or negative
     const int ta = (a >= 0) ? a / FTMPC_NU : 0, ja = a - ta * FTMPC_NU;
     const int pa_ = 7 * ta + ja;                   // column a inside a panel
     int bi = -1, bj = 0;                           // block role (tid < nblk)
@@ -1235,77 +1249,86 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
     blk.sync();
 }
 
-// ---- register-resident block Cholesky + L^-T ------------------------------------------------------------
+// ---- register-resident block Cholesky + L^-T, ONE sweep -------------------------------------------------
 // H arrives as 6x6 blocks in the registers of their owner threads (from `condense`), so the factorisation never
-// read-modify-writes shared memory: per block column k
-//   A  the owner of (k,k) factors its block, inverts it (6x6 lower) and publishes L_kk^-1;
-//   B  owners of (i,k), i > k:  L_ik = A_ik L_kk^-T  -> published to the lower triangle of E;
-//   C  owners of (i,j), i >= j > k:  A_ij -= L_ik L_jk'  (operands from E, accumulators in registers);
-// two barriers per block column.  Then X = L^-1 by block wavefronts (distance s = i - j): every owner adds
-// L_{i,j+s-1} X_{j+s-1,j} as soon as that X block exists and the owners at distance s finish
-// X_ij = -L_ii^-1 S_ij; X is stored TRANSPOSED in the upper triangle of E, i.e. directly as J = L^-T.
+// read-modify-writes shared memory.  The triangular inverse X = L^-1 is built inside the same sweep: once block (i,j)
+// has become L_ij (step j) its accumulator is dead, so it is reused for  S_ij = sum_{m=j}^{i-1} L_im X_mj , and
+// X_ij = -L_ii^-1 S_ij falls out at step i.  Per block column k, two barrier intervals:
+//   panel   owners of (i,k), i > k:  L_ik = A_ik L_kk^-T            -> lower triangle of E (kept in registers too);
+//           owners of (k,j), j < k:  X_kj = -L_kk^-1 S_kj           -> stored TRANSPOSED in the upper triangle (J = L^-T);
+//   update  owners of (i,j), i > k:  j > k:  A_ij -= L_ik L_jk'     (Cholesky trailing update)
+//                                    j = k:  S_ik  = L_ik X_kk      (first term of the inverse recurrence, from registers)
+//                                    j < k:  S_ij += L_ik X_kj
+//           every thread below block row k does exactly one 6x6x6 product per step (the two kinds of update are
+//           complementary), the active threads are a contiguous suffix of the block, and the separate wavefront pass of
+//           the inverse (19 more barrier intervals) is gone.  The owner of (k+1,k+1) factors and inverts its block at
+//           the end of the same interval, overlapped with the other warps' updates.
 // Returns 0, or 6k+1.. when a pivot of block column k is not safely positive (uniform over the block).
+__device__ __forceinline__ void chol_diag_block(double (&acc)[6][6], int k, int ld, double* E, double* linv, double* flag,
+                                                double piv_tol) {
+    int bad = 0;
+    double inv[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double d = acc[j][j];
+#pragma unroll
+        for (int m = 0; m < 6; ++m) if (m < j) d -= acc[j][m] * acc[j][m];
+        if (!(d > piv_tol)) bad = 1;
+        const double rs = rsqrt(d);
+        inv[j] = rs;
+        acc[j][j] = d * rs;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            if (i > j) {
+                double v = acc[i][j];
+#pragma unroll
+                for (int m = 0; m < 6; ++m) if (m < j) v -= acc[i][m] * acc[j][m];
+                acc[i][j] = v * rs;
+            }
+        }
+    }
+    // Y = L_kk^-1 (lower)
+    double Y[6][6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            if (i < j) Y[i][j] = 0.0;
+            else if (i == j) Y[i][j] = inv[j];
+            else {
+                double v = 0.0;
+#pragma unroll
+                for (int m = 0; m < 6; ++m) if (m >= j && m < i) v += acc[i][m] * Y[m][j];
+                Y[i][j] = -v * inv[i];
+            }
+        }
+    }
+    double* lk = linv + (size_t)k * 36;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            lk[i * 6 + j] = Y[i][j];
+            // diagonal block of E: X_kk^T in the upper triangle (incl. diagonal), zeros strictly below
+            E[(size_t)(6 * k + j) * ld + 6 * k + i] = Y[i][j];      // (j,i) <- Y[i][j]; for i < j this writes the zeros
+        }
+    if (bad) *flag = (double)(6 * k + 1);
+}
+
 __device__ __forceinline__ int chol_inv_blocks(CudaBlock& blk, int Nb, int ld, double* E, double* linv, HBlocks& hb,
                                                double piv_tol) {
-    const int tid = blk.tid();
     const int bi = hb.bi, bj = hb.bj;
     double (&acc)[6][6] = hb.acc;
     double* flag = linv + (size_t)Nb * 36;
-    if (tid == 0) *flag = 0.0;
+    if (bi == 0 && bj == 0) {                      // thread 0
+        *flag = 0.0;
+        chol_diag_block(acc, 0, ld, E, linv, flag, piv_tol);
+    }
     blk.sync();
     for (int k = 0; k < Nb; ++k) {
-        if (bi == k && bj == k) {
-            int bad = 0;
-            double inv[6];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                double d = acc[j][j];
-#pragma unroll
-                for (int m = 0; m < 6; ++m) if (m < j) d -= acc[j][m] * acc[j][m];
-                if (!(d > piv_tol)) bad = 1;
-                const double rs = rsqrt(d);
-                inv[j] = rs;
-                acc[j][j] = d * rs;
-#pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    if (i > j) {
-                        double v = acc[i][j];
-#pragma unroll
-                        for (int m = 0; m < 6; ++m) if (m < j) v -= acc[i][m] * acc[j][m];
-                        acc[i][j] = v * rs;
-                    }
-                }
-            }
-            // Y = L_kk^-1 (lower)
-            double Y[6][6];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    if (i < j) Y[i][j] = 0.0;
-                    else if (i == j) Y[i][j] = inv[j];
-                    else {
-                        double v = 0.0;
-#pragma unroll
-                        for (int m = 0; m < 6; ++m) if (m >= j && m < i) v += acc[i][m] * Y[m][j];
-                        Y[i][j] = -v * inv[i];
-                    }
-                }
-            }
-            double* lk = linv + (size_t)k * 36;
-#pragma unroll
-            for (int i = 0; i < 6; ++i)
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    lk[i * 6 + j] = Y[i][j];
-                    // diagonal block of E: X_kk^T in the upper triangle (incl. diagonal), zeros strictly below
-                    E[(size_t)(6 * k + j) * ld + 6 * k + i] = Y[i][j];      // (j,i) <- Y[i][j]; for i < j this writes the zeros
-                }
-            if (bad) *flag = (double)(6 * k + 1);
-        }
-        blk.sync();
         if (*flag != 0.0) return (int)*flag;
-        if (bj == k && bi > k) {
+        // ---------------- panel
+        if (bj == k && bi > k) {                   // L_ik = A_ik L_kk^-T
             const double* lk = linv + (size_t)k * 36;
             double Y[6][6];
 #pragma unroll
@@ -1326,97 +1349,82 @@ __device__ __forceinline__ int chol_inv_blocks(CudaBlock& blk, int Nb, int ld, d
 #pragma unroll
                 for (int j = 0; j < 6; ++j) { acc[i][j] = x[j]; er[j] = x[j]; }
             }
-        }
-        blk.sync();
-        if (bi >= 0 && bj > k) {
-            double Lb[6][6];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                const double* er = E + (size_t)(6 * bj + j) * ld + 6 * k;
-#pragma unroll
-                for (int m = 0; m < 6; ++m) Lb[j][m] = er[m];
-            }
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                const double* er = E + (size_t)(6 * bi + i) * ld + 6 * k;
-                double La[6];
-#pragma unroll
-                for (int m = 0; m < 6; ++m) La[m] = er[m];
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    double v = acc[i][j];
-#pragma unroll
-                    for (int m = 0; m < 6; ++m) v -= La[m] * Lb[j][m];
-                    acc[i][j] = v;
-                }
-            }
-        }
-    }
-    blk.mark(PH_CHOL);
-    // ---- X = L^-1 by block wavefronts; S accumulates in the (now dead) H registers.
-    // The accumulators start from zero, so the block -> thread assignment is free: here it is COLUMN-major (a warp holds
-    // one block column xj and consecutive block rows xi).  The X operand X_{kb,xj} is then the same for the whole warp
-    // (broadcast) and the L operand rows are 6 rows apart (2-way bank conflict); with the row-major assignment of the
-    // factorisation the X operand was read with a 4-way conflict.
-    int xi = -1, xj = 0;
-    if (tid < Nb * (Nb + 1) / 2) {
-        int off = 0;
-        while (off + (Nb - xj) <= tid) { off += Nb - xj; ++xj; }
-        xi = xj + (tid - off);
-    }
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = 0; j < 6; ++j) acc[i][j] = 0.0;
-    for (int sdist = 1; sdist < Nb; ++sdist) {
-        if (xi >= 0 && xi - xj >= sdist) {
-            const int kb = xj + sdist - 1;
-            double Xb[6][6];                               // Xb[b][m] = X_{kb,xj}[m][b]
+        } else if (bi == k && bj >= 0 && bj < k) { // X_kj = -L_kk^-1 S_kj, stored transposed
+            const double* lk = linv + (size_t)k * 36;
 #pragma unroll
             for (int b = 0; b < 6; ++b) {
-                const double* er = E + (size_t)(6 * xj + b) * ld + 6 * kb;
+                double x[6];
 #pragma unroll
-                for (int m = 0; m < 6; ++m) Xb[b][m] = er[m];
-            }
+                for (int a = 0; a < 6; ++a) {
+                    double v = 0.0;
 #pragma unroll
-            for (int a = 0; a < 6; ++a) {
-                const double* er = E + (size_t)(6 * xi + a) * ld + 6 * kb;
-                double La[6];
-#pragma unroll
-                for (int m = 0; m < 6; ++m) La[m] = er[m];
-#pragma unroll
-                for (int b = 0; b < 6; ++b) {
-                    double v = acc[a][b];
-#pragma unroll
-                    for (int m = 0; m < 6; ++m) v += La[m] * Xb[b][m];
-                    acc[a][b] = v;
+                    for (int m = 0; m < 6; ++m) if (m <= a) v += lk[a * 6 + m] * acc[m][b];
+                    x[a] = -v;
                 }
-            }
-            if (xi - xj == sdist) {
-                const double* lk = linv + (size_t)xi * 36;
+                double* er = E + (size_t)(6 * bj + b) * ld + 6 * k;
 #pragma unroll
-                for (int b = 0; b < 6; ++b) {
+                for (int a = 0; a < 6; ++a) er[a] = x[a];
+            }
+        }
+        blk.sync();
+        // ---------------- update
+        if (bi > k) {
+            if (bj == k) {                         // S_ik = L_ik X_kk  (L_ik is still in the registers)
+                const double* lk = linv + (size_t)k * 36;
+                double Y[6][6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) Y[i][j] = (j <= i) ? lk[i * 6 + j] : 0.0;
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
                     double x[6];
 #pragma unroll
-                    for (int a = 0; a < 6; ++a) {
+                    for (int b = 0; b < 6; ++b) {
                         double v = 0.0;
 #pragma unroll
-                        for (int m = 0; m < 6; ++m) if (m <= a) v += lk[a * 6 + m] * acc[m][b];
-                        x[a] = -v;
+                        for (int m = 0; m < 6; ++m) if (m >= b) v += acc[a][m] * Y[m][b];
+                        x[b] = v;
                     }
-                    double* er = E + (size_t)(6 * xj + b) * ld + 6 * xi;
 #pragma unroll
-                    for (int a = 0; a < 6; ++a) er[a] = x[a];
+                    for (int b = 0; b < 6; ++b) acc[a][b] = x[b];
                 }
+            } else {
+                // second operand: rows 6 bj .. of E at columns 6k..: L_jk (j > k, lower triangle) or X_kj^T (j < k, upper
+                // triangle) -- the same addressing, only the sign of the product differs
+                double Ob[6][6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const double* er = E + (size_t)(6 * bj + j) * ld + 6 * k;
+#pragma unroll
+                    for (int m = 0; m < 6; ++m) Ob[j][m] = er[m];
+                }
+                const double sgn = (bj > k) ? -1.0 : 1.0;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    const double* er = E + (size_t)(6 * bi + i) * ld + 6 * k;
+                    double La[6];
+#pragma unroll
+                    for (int m = 0; m < 6; ++m) La[m] = sgn * er[m];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        double v = acc[i][j];
+#pragma unroll
+                        for (int m = 0; m < 6; ++m) v += La[m] * Ob[j][m];
+                        acc[i][j] = v;
+                    }
+                }
+                if (bi == k + 1 && bj == k + 1) chol_diag_block(acc, k + 1, ld, E, linv, flag, piv_tol);
             }
         }
         blk.sync();
     }
+    blk.mark(PH_CHOL);
     // the strictly lower blocks (L) are dead: J is upper triangular
-    if (xi > xj) {
+    if (bi > bj) {
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-            double* er = E + (size_t)(6 * xi + i) * ld + 6 * xj;
+            double* er = E + (size_t)(6 * bi + i) * ld + 6 * bj;
 #pragma unroll
             for (int j = 0; j < 6; ++j) er[j] = 0.0;
         }
@@ -1519,6 +1527,8 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     // iterate; it is only kept away from the first, wildly infeasible iterations (elastic variable far from zero)
     const double feas_aug = 1e-2;
     const bool can_aug = (sc[SC_ITER] > 0.0 || sc[SC_THETA] >= 0.0) && sc[SC_CSUM] <= feas_aug;
+    // |d| of the previous iteration is remembered for sqp_fast_converged when that iteration was an exact-Hessian full step
+    const double dprev_keep = (sc[SC_ITER] > 0.0 && sc[SC_THETA] == 1.0 && sc[SC_ALPHA] == 1.0) ? sc[SC_DMAX] : 0.0;
     double theta = sc[SC_THETA], sigma = 0.0;
     theta = (theta < 0.0) ? 0.0 : ((theta == 0.0) ? cfg.theta_first : fmin(1.0, cfg.theta_growth * theta));
     if (can_aug && sc[SC_SIGMA] > 0.0) { theta = 1.0; sigma = sc[SC_SIGMA]; }
@@ -1644,6 +1654,7 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     lmx = blk.max(lmx);
     if (tid == 0) {
         w[L.oD + n] = s.gi.xe[n];
+        sc[SC_DPREV] = dprev_keep;
         sc[SC_GD] = gd; sc[SC_DMAX] = dmx; sc[SC_LAMMAX] = lmx; sc[SC_DELTA] = s.gi.xe[n];
         sc[SC_HFAIL] = (skip_exact || (fails > 0 && theta == 0.0)) ? 1.0 : 0.0;
         sc[SC_THETA] = theta; sc[SC_SIGMA] = sigma; sc[SC_QPIT] += qit; sc[SC_NACT] = nact; sc[SC_CHOLFAIL] += fails;

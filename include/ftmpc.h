@@ -83,6 +83,9 @@ typedef struct ftmpc_config {
     double theta_first;        /* Hessian schedule: blend of exact second-order terms in SQP iteration 1 (iteration 0 is   */
     double theta_growth;       /* Gauss-Newton), multiplied by theta_growth per iteration up to 1 (defaults 0.5, 2)       */
     double blend_dmax;         /* the blend is first attempted once the QP step satisfies |d|_inf <= blend_dmax (default 1) */
+    double fast_dmax;          /* early stop in the quadratic regime (sqp_fast_converged): after two consecutive exact-Hessian full
+                                  steps with |d_k| <= fast_dmax and predicted next step |d_k|^3/|d_{k-1}|^2 <= 0.1 sqp_tol the
+                                  confirming QP is skipped (default 1e-5; 0 = always confirm)                              */
 } ftmpc_config;
 
 typedef struct ftmpc_ctx* ftmpc_handle;
