@@ -20,6 +20,7 @@ import torch
 
 from .. import _lib as L
 from ..util.broken_thruster import BrokenThruster
+from ..util.controller_debug import DebugVal
 from ..util.get_trajectory import load_trajectory
 from .tools.input_bounds import hull_of_faults
 from .tools.spiral_parameters import SpiralParameters
@@ -133,6 +134,7 @@ class BatchedMPC:
         mask, ff, hidx = scenario if isinstance(scenario, tuple) else self.scenario_tensors(scenario)
         assert state.shape == (B, L.NX) and xref.shape == (B, self.N + 1, L.NE)
         assert state.is_contiguous() and xref.is_contiguous() and state.dtype == torch.float64
+        assert uref is None or (uref.shape == (B, self.N + 1, L.NU) and uref.is_contiguous() and uref.dtype == torch.float64)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         L.check(self.lib.ftmpc_step(self.handle, B, _ptr(state), _ptr(xref), _ptr(uref), _ptr(mask), _ptr(ff),
                                     _ptr(hidx), int(bool(warm)), _ptr(b["z"]), _ptr(b["thrust"]), _ptr(b["u0"]),
@@ -151,11 +153,12 @@ class BatchedMPC:
                                           int(bool(normalize)), _ptr(nxt), C.c_void_p(stream)), "ftmpc_plant_step")
         return nxt
 
-    def closed_loop(self, state0, trajectory, scenario=None, steps=1, noise=None, start_step=0):
+    def closed_loop(self, state0, trajectory, scenario=None, steps=1, noise=None, start_step=0, nominal_input=None):
         """`steps` x (ftmpc_step -> ftmpc_plant_step) entirely on the device: SimulationEnvironment.run_simulation
         (sim_env.py:77-112) for a batch.  trajectory: [T,9] device reference table (assign_trajectory), shared by
-        all instances; noise: optional [steps,B,13] tensor added after each plant step (the reference draws
-        unseeded U(0,1e-3), sim_env.py:88-91).  Warm start from the second step on (spiraling_mpc.py:324-331).
+        all instances; nominal_input: optional [T,6] device table of the nominal wrench of an accelerating reference
+        (assign_trajectory, spiraling_mpc.py:279-286); noise: optional [steps,B,13] tensor added after each plant step
+        (the reference draws unseeded U(0,1e-3), sim_env.py:88-91).  Warm start from the second step on (spiraling_mpc.py:324-331).
         Returns (final_state [B,13], cumulative optimal cost [B], worst status [B], steps done [B])."""
         B = state0.shape[0]
         if scenario is None:
@@ -167,7 +170,10 @@ class BatchedMPC:
         for k in range(steps):
             w = trajectory[start_step + k: start_step + k + self.N + 1]
             xref = w.unsqueeze(0).expand(B, -1, -1).contiguous()
-            out = self.step(state, xref, scenario=sc, warm=k > 0)
+            uref = None
+            if nominal_input is not None:
+                uref = nominal_input[start_step + k: start_step + k + self.N + 1].unsqueeze(0).expand(B, -1, -1).contiguous()
+            out = self.step(state, xref, uref, scenario=sc, warm=k > 0)
             cost += out["cost"]
             worst = torch.maximum(worst, out["status"])
             state = self.plant_step(state, out["thrust"], sc, noise[k] if noise is not None else None, True)
@@ -240,10 +246,11 @@ class SpiralingController:
         self.trajectory = np.concatenate((orig[0:6, :], om))                                    # :274-277
         second = np.gradient(np.gradient(self.trajectory[0:3, :], axis=1), axis=1) / self.dt ** 2   # :283
         self.nominal_input = np.vstack((second * self.mass, np.zeros_like(second)))             # :285
-        if np.abs(self.nominal_input[0:3]).max() > 1e-12:
-            raise NotImplementedError("references with non-zero nominal force (accelerating trajectories) are the "
-                                      "'next' row f-3 of SURVEY.md section 8 and not supported yet")
         self._traj_dev = torch.tensor(self.trajectory.T.copy(), dtype=torch.float64, device=self.device)
+        # accelerating references: the nominal wrench travels with the window and is rotated into the body frame per
+        # stage inside the kernels (stage_wrench, spiraling_mpc.py:156-166); a hover reference keeps the NULL fast path
+        self._accelerating = bool(np.abs(self.nominal_input).max() > 0.0)
+        self._uref_dev = torch.tensor(self.nominal_input.T.copy(), dtype=torch.float64, device=self.device)
 
     def get_next_trajectory_part(self, t):
         """Window of N+1 reference points starting at int(t/dt) (spiraling_mpc.py:356-365)."""
@@ -255,16 +262,33 @@ class SpiralingController:
         w = self._traj_dev[step_index:step_index + self.Nt + 1]
         return w.unsqueeze(0).expand(batch, -1, -1).contiguous()
 
+    def nominal_window(self, step_index, batch=1):
+        """[batch, N+1, 6] device window of the nominal wrench, or None for a reference without acceleration."""
+        if not self._accelerating:
+            return None
+        w = self._uref_dev[step_index:step_index + self.Nt + 1]
+        return w.unsqueeze(0).expand(batch, -1, -1).contiguous()
+
     # ---- single-instance reference API ------------------------------------------ spiraling_mpc.py:288-317
     def get_control(self, x0, t):
         x0 = np.asarray(x0, float).reshape(1, 13)
         state = torch.tensor(x0, dtype=torch.float64, device=self.device)
-        xref = self.reference_window(int(t / self.dt))
-        out = self.engine.step(state, xref, warm=self.optimal_solution is not None)
+        k = int(t / self.dt)                                                               # spiraling_mpc.py:360
+        xref = self.reference_window(k)
+        out = self.engine.step(state, xref, self.nominal_window(k), warm=self.optimal_solution is not None)
         self.optimal_solution = out["z"]
         self.last_status = int(out["status"][0].item())
         self.last_u0 = out["u0"][0].cpu().numpy()
-        return out["thrust"][0].cpu().numpy()
+        thrust = out["thrust"][0].cpu().numpy()
+        if self.debug is not None:                                                         # spiraling_mpc.py:309-315
+            dv = DebugVal(self, t)
+            dv.set_state(x0[0])
+            dv.set_circle_state(out["z"][0, 6 * self.Nt:6 * self.Nt + 9].cpu().numpy())     # c0 = x_0 of the decision vector
+            dv.set_input(thrust, self.model)
+            dv.set_desired_state(self.trajectory[:, k])
+            dv.calculate_errors()
+            self.debug.add_debug_val(dv)
+        return thrust
 
     # ---- batched API -------------------------------------------------------------------------------------
     def step(self, state, ref, uref=None, scenario=None, warm=False):

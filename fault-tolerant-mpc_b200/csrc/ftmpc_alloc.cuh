@@ -106,9 +106,23 @@ FT_HD void phase_out_write(Blk& blk, const ftmpc_config& cfg, const WsLayout& L,
     const double* C = w + L.oC;
     // optimal decision vector, reference layout [u | x]   (spiraling_mpc.py:110-114)
     double* zw = io.z_warm + (size_t)inst * (L.n + (size_t)(N + 1) * FTMPC_NX);
-    for (int i = tid; i < L.n; i += nt) zw[i] = U[i];
+    const double* uref = io.uref ? io.uref + (size_t)inst * (N + 1) * FTMPC_NU : nullptr;
+    if (uref) {
+        // the solver iterated on u~ = u + rho_t(q_t) (ftmpc_sqp.cuh, FTMPC_CQ): hand back the reference's variable u
+        for (int t = tid; t < N; t += nt) {
+            double rho[FTMPC_NU];
+            nominal_rot(X + t * FTMPC_NX + 9, uref + t * FTMPC_NU, rho);
+            for (int j = 0; j < FTMPC_NU; ++j) {
+                const double u = U[t * FTMPC_NU + j] - rho[j];
+                zw[t * FTMPC_NU + j] = u;
+                if (t == 0) io.u0[(size_t)inst * FTMPC_NU + j] = u;
+            }
+        }
+    } else {
+        for (int i = tid; i < L.n; i += nt) zw[i] = U[i];
+        for (int j = tid; j < FTMPC_NU; j += nt) io.u0[(size_t)inst * FTMPC_NU + j] = U[j];
+    }
     for (int i = tid; i < (N + 1) * FTMPC_NX; i += nt) zw[L.n + i] = X[i];
-    for (int j = tid; j < FTMPC_NU; j += nt) io.u0[(size_t)inst * FTMPC_NU + j] = U[j];
     // active set: row i active <=> b_i - g_i <= act_tol  <=>  c_i >= -act_tol
     const int nw = (L.mc + 31) / 32;
     for (int wd = tid; wd < nw; wd += nt) {

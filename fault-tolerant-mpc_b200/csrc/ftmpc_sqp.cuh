@@ -22,9 +22,23 @@
 namespace ftmpc {
 
 // ---- per-instance workspace (global memory), offsets in doubles ------------------------------
+// Accelerating references (non-zero nominal wrench u_r, spiraling_mpc.py:156-172, 279-286).  The reference NLP applies
+//   W_t = u_t + rho_t(q_t) + u_comp,   rho_t(q) = [Rot(q)' u_r,F ; u_r,tau]
+// to the dynamics AND to the hull rows, so in the variable u both depend on the attitude q_t.  The solver therefore
+// iterates on  u~_t = u_t + rho_t(q_t)  (a bijection for fixed states): dynamics and hull rows are then exactly those of
+// the hover problem, and the attitude enters only through the input cost  sum_j R_j (u~_j - rho_j(q_t))^2 .  Per stage
+// that cost contributes (record of FTMPC_CQ doubles, written by phase_lin):
+//   [0..3]   gq   = d l / d q              = -2 Jrho' r,            r = R o (u~ - rho)
+//   [4..15]  cx   = d2 l / d u~_i d q_b     = -2 R_i Jrho[i][b]      (i < 3: only the force rotates)
+//   [16..31] cqq  = 2 Jrho' R Jrho                                   (Gauss-Newton part of d2 l / d q2)
+//   [32..37] rho
+//   [40..55] sx   = -2 sum_i r_i d2 rho_i / d q2   (exact remainder, added to the (q,q) block of W_t)
+// and the exact remainder  -2 sum_i r_i d2 rho_i / d q2  goes into the (q,q) block of W_t next to the dynamics' second-
+// order terms (blended by theta like them).  u = u~ - rho is restored when results are written (phase_out_write).
+#define FTMPC_CQ 56
 struct WsLayout {
     int N, n, nv, mc, m;
-    size_t oU, oD, oX, oC, oLam, oMu, oJz, oWz, oGV, oHV, oSc, stride;
+    size_t oU, oD, oX, oC, oLam, oMu, oJz, oWz, oGV, oHV, oSc, oCq, stride;
 };
 enum {      // scalar slots
     SC_F = 0, SC_CSUM, SC_NU, SC_GD, SC_THETA, SC_DMAX, SC_DELTA, SC_LAMMAX, SC_STATUS, SC_ITER, SC_QPIT,
@@ -45,6 +59,7 @@ FT_HD WsLayout ws_layout(int N) {
     L.oGV = o; o += FTMPC_NE;
     L.oHV = o; o += FTMPC_NE * FTMPC_NE;
     L.oSc = o; o += SC_COUNT;
+    L.oCq = o; o += (size_t)N * FTMPC_CQ;      // input-cost coupling records (accelerating references only)
     L.stride = (o + 7) & ~(size_t)7;
     return L;
 }
@@ -96,6 +111,47 @@ FT_HD void stage_wrench(const ftmpc_config& c, const double* u, const double* ur
     }
 }
 
+// rho_t(q) = [Rot(q)' u_r,F ; u_r,tau]
+FT_HD void nominal_rot(const double* q, const double* ur, double* rho) {
+    double R[9];
+    rot_mat(q, R);
+    mat3_tmul(R, ur, rho);
+    for (int i = 0; i < 3; ++i) rho[3 + i] = ur[3 + i];
+}
+// record described at FTMPC_CQ
+FT_HD void stage_cost_coupling(const ftmpc_config& c, const double* ut, const double* ur, const double* q, double* rec) {
+    double* Sx = rec + 40;
+    double rho[6], r[3], Jr[3][4];
+    nominal_rot(q, ur, rho);
+    for (int i = 0; i < 3; ++i) r[i] = c.R[i] * (ut[i] - rho[i]);
+    for (int j = 0; j < 4; ++j) {
+        double e[4] = {0.0, 0.0, 0.0, 0.0}, B[9], col[3];
+        e[j] = 1.0;
+        rot_bilinear(q, e, B);                       // d Rot / d q_j
+        mat3_tmul(B, ur, col);
+        for (int i = 0; i < 3; ++i) Jr[i][j] = col[i];
+    }
+    for (int j = 0; j < 4; ++j) {
+        rec[j] = -2.0 * (r[0] * Jr[0][j] + r[1] * Jr[1][j] + r[2] * Jr[2][j]);
+        for (int i = 0; i < 3; ++i) rec[4 + i * 4 + j] = -2.0 * c.R[i] * Jr[i][j];
+        for (int l = 0; l < 4; ++l)
+            rec[16 + j * 4 + l] = 2.0 * (c.R[0] * Jr[0][j] * Jr[0][l] + c.R[1] * Jr[1][j] * Jr[1][l] + c.R[2] * Jr[2][j] * Jr[2][l]);
+    }
+    for (int i = 0; i < 6; ++i) rec[32 + i] = rho[i];
+    rec[38] = rec[39] = 0.0;
+    {
+        for (int j = 0; j < 4; ++j)
+            for (int l = 0; l <= j; ++l) {
+                double ej[4] = {0.0, 0.0, 0.0, 0.0}, el[4] = {0.0, 0.0, 0.0, 0.0}, B[9], col[3];
+                ej[j] = 1.0; el[l] = 1.0;
+                rot_bilinear(ej, el, B);             // d2 Rot / d q_j d q_l
+                mat3_tmul(B, ur, col);
+                const double v = -2.0 * (r[0] * col[0] + r[1] * col[1] + r[2] * col[2]);
+                Sx[j * 4 + l] = v; Sx[l * 4 + j] = v;
+            }
+    }
+}
+
 // SQP termination: the QP step is below sqp_tol, or it is within 100 sqp_tol AND the decrease it predicts is at the
 // rounding level of the objective (|g'd| <= 1e-13 max(1,|f|)): at that point the step is numerical noise of the
 // gradient divided by a small curvature and never shrinks further, although the iterate no longer moves.
@@ -115,22 +171,27 @@ FT_HD bool sqp_fast_converged(const ftmpc_config& cfg, double dmax, double dprev
 // forward rollout at U + alpha*d: states, cost, constraint values (c <= 0 feasible).
 FT_HD void rollout_eval(const ftmpc_config& cfg, const WsLayout& L, const double* hull, const double* xref,
                         const double* uref, const double* U, const double* d, double alpha, double* X, double* C,
-                        double& f, double& csum, double& cmax) {
+                        double& f, double& csum, double& cmax, double* Uconv = nullptr) {
+    // U holds u~ (see FTMPC_CQ); with Uconv != nullptr it still holds u (warm start / zeros) and is converted on the fly
     const DynConsts k = dyn_consts(cfg);
     const int N = L.N;
-    double x[FTMPC_NX], xn[FTMPC_NX], u[FTMPC_NU], Wr[FTMPC_NU];
+    double x[FTMPC_NX], xn[FTMPC_NX], u[FTMPC_NU], Wr[FTMPC_NU], rho[FTMPC_NU] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     for (int i = 0; i < FTMPC_NX; ++i) x[i] = X[i];
     f = 0.0; csum = 0.0; cmax = 0.0;
     const double* Ah = hull;
     const double* bh = hull + FTMPC_NH * FTMPC_NU;
     for (int t = 0; t < N; ++t) {
         for (int j = 0; j < FTMPC_NU; ++j) u[j] = U[t * FTMPC_NU + j] + alpha * d[t * FTMPC_NU + j];
-        stage_wrench(cfg, u, uref ? uref + t * FTMPC_NU : nullptr, x + 9, Wr);
+        if (uref) {
+            nominal_rot(x + 9, uref + t * FTMPC_NU, rho);
+            if (Uconv) for (int j = 0; j < FTMPC_NU; ++j) { u[j] += rho[j]; Uconv[t * FTMPC_NU + j] = u[j]; }
+        }
+        stage_wrench(cfg, u, nullptr, x + 9, Wr);
         for (int j = 0; j < FTMPC_NE; ++j) {                            // running cost, spiraling_mpc.py:188
             const double e = x[j] - xref[t * FTMPC_NE + j];
             f += cfg.Q[j] * e * e;
         }
-        for (int j = 0; j < FTMPC_NU; ++j) f += cfg.R[j] * u[j] * u[j];
+        for (int j = 0; j < FTMPC_NU; ++j) f += cfg.R[j] * (u[j] - rho[j]) * (u[j] - rho[j]);
         for (int i = 0; i < FTMPC_NH; ++i) {                            // hull rows, spiraling_mpc.py:175-177
             double v = -bh[i];
             for (int j = 0; j < FTMPC_NU; ++j) v += Ah[i * FTMPC_NU + j] * Wr[j];
@@ -178,7 +239,7 @@ FT_HD void phase_ls(const ftmpc_config& cfg, const WsLayout& L, const StepIO& io
         sc[SC_NU] = 1.0;
         sc[SC_THETA] = -1.0;                       // first QP uses the Gauss-Newton model
         sc[SC_STATUS] = FTMPC_ST_RUNNING;
-        rollout_eval(cfg, L, hull, xref, uref, U, D, 0.0, X, C, f, csum, cmax);
+        rollout_eval(cfg, L, hull, xref, uref, U, D, 0.0, X, C, f, csum, cmax, uref ? U : nullptr);
         if (!(f < INFINITY)) sc[SC_STATUS] = FTMPC_ST_QPFAIL;
     } else {
         if (sc[SC_STATUS] != FTMPC_ST_RUNNING) return;
@@ -255,23 +316,30 @@ __device__ __forceinline__ LsScratch ls_carve(double* buf, int N) {
 // returns the running cost (the terminal cost is added term-parallel afterwards)
 __device__ __noinline__ double rollout_states(const ftmpc_config& cfg, int N, const double* xref, const double* uref,
                                               const double* U, const double* d, double alpha, const double* x0,
-                                              double* Xs, double* Ws) {
+                                              double* Xs, double* Ws, double* Uconv_s = nullptr, double* Uconv_g = nullptr) {
     const DynConsts k = dyn_consts(cfg);
-    double x[FTMPC_NX], xn[FTMPC_NX], u[FTMPC_NU], Wr[FTMPC_NU];
+    double x[FTMPC_NX], xn[FTMPC_NX], u[FTMPC_NU], Wr[FTMPC_NU], rho[FTMPC_NU] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
     for (int i = 0; i < FTMPC_NX; ++i) { x[i] = x0[i]; Xs[i] = x[i]; }
     double f = 0.0;
     for (int t = 0; t < N; ++t) {
 #pragma unroll
         for (int j = 0; j < FTMPC_NU; ++j) u[j] = U[t * FTMPC_NU + j] + alpha * d[t * FTMPC_NU + j];
-        stage_wrench(cfg, u, uref ? uref + t * FTMPC_NU : nullptr, x + 9, Wr);
+        if (uref) {                                   // U holds u~ = u + rho(q_t), see FTMPC_CQ
+            nominal_rot(x + 9, uref + t * FTMPC_NU, rho);
+            if (Uconv_s) {                            // first rollout: U still holds u
+#pragma unroll
+                for (int j = 0; j < FTMPC_NU; ++j) { u[j] += rho[j]; Uconv_s[t * FTMPC_NU + j] = u[j]; Uconv_g[t * FTMPC_NU + j] = u[j]; }
+            }
+        }
+        stage_wrench(cfg, u, nullptr, x + 9, Wr);
 #pragma unroll
         for (int j = 0; j < FTMPC_NE; ++j) {
             const double e = x[j] - xref[t * FTMPC_NE + j];
             f += cfg.Q[j] * e * e;
         }
 #pragma unroll
-        for (int j = 0; j < FTMPC_NU; ++j) { f += cfg.R[j] * u[j] * u[j]; Ws[t * FTMPC_NU + j] = Wr[j]; }
+        for (int j = 0; j < FTMPC_NU; ++j) { f += cfg.R[j] * (u[j] - rho[j]) * (u[j] - rho[j]); Ws[t * FTMPC_NU + j] = Wr[j]; }
         rk4_step(k, x, Wr, xn);
 #pragma unroll
         for (int i = 0; i < FTMPC_NX; ++i) { x[i] = xn[i]; Xs[(t + 1) * FTMPC_NX + i] = xn[i]; }
@@ -353,7 +421,8 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
     if (warp == 0 && lane < nalpha) {
         const double alpha = first ? 0.0 : ldexp(1.0, -lane);
         s.fa[lane] = rollout_states(cfg, N, s.xref, uref_g ? s.uref : nullptr, s.U, s.D, alpha, X,
-                                    s.Xs + (size_t)lane * s.xs_stride, s.Ws + (size_t)lane * s.ws_stride);
+                                    s.Xs + (size_t)lane * s.xs_stride, s.Ws + (size_t)lane * s.ws_stride,
+                                    (first && uref_g) ? s.U : nullptr, U);
     }
     blk.sync();
     blk.mark(PH_LS_ROLL);
@@ -514,15 +583,19 @@ FT_HD void phase_lin(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const
     double* Wz = w + L.oWz;
     double* Mu = w + L.oMu;
     const double* lam = w + L.oLam;
-    // first-order columns
+    double* Cq = w + L.oCq;
+    // first-order columns (U holds u~: the wrench does not depend on the attitude, see FTMPC_CQ)
     for (int it = tid; it < N * 13; it += nt) {
         const int t = it / 13, col = it % 13;
         double Wr[FTMPC_NU];
-        stage_wrench(cfg, U + t * FTMPC_NU, uref ? uref + t * FTMPC_NU : nullptr, X + t * FTMPC_NX + 9, Wr);
+        stage_wrench(cfg, U + t * FTMPC_NU, nullptr, X + t * FTMPC_NX + 9, Wr);
         double jc[13];
         rk4_column_call(k, X + t * FTMPC_NX, Wr, col, nullptr, jc, nullptr);
         for (int i = 0; i < 13; ++i) Jz[(size_t)it * 13 + i] = jc[i];
     }
+    if (uref)
+        for (int t = tid; t < N; t += nt)
+            stage_cost_coupling(cfg, U + t * FTMPC_NU, uref + t * FTMPC_NU, X + t * FTMPC_NX + 9, Cq + (size_t)t * FTMPC_CQ);
     blk.sync();
     blk.mark(PH_LIN_JAC);
     // costates  mu_N = [grad V_f + A_f' lam_term ; 0],  mu_t = [2Q e_t ; 0] + A_t' mu_{t+1}
@@ -538,7 +611,8 @@ FT_HD void phase_lin(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const
     for (int t = N - 1; t >= 1; --t) {
         const double* mn = Mu + (t + 1) * FTMPC_NX;
         for (int i = tid; i < FTMPC_NX; i += nt) {
-            double v = (i < FTMPC_NE) ? 2.0 * cfg.Q[i] * (X[t * FTMPC_NX + i] - xref[t * FTMPC_NE + i]) : 0.0;
+            double v = (i < FTMPC_NE) ? 2.0 * cfg.Q[i] * (X[t * FTMPC_NX + i] - xref[t * FTMPC_NE + i])
+                                      : (uref ? Cq[(size_t)t * FTMPC_CQ + i - FTMPC_NE] : 0.0);
             if (i < 3) v += mn[i];
             else if (i < 6) v += k.dt * mn[i - 3] + mn[i];
             else {
@@ -554,12 +628,19 @@ FT_HD void phase_lin(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const
     for (int it = tid; it < N * 13; it += nt) {
         const int t = it / 13, col = it % 13;
         double Wr[FTMPC_NU];
-        stage_wrench(cfg, U + t * FTMPC_NU, uref ? uref + t * FTMPC_NU : nullptr, X + t * FTMPC_NX + 9, Wr);
+        stage_wrench(cfg, U + t * FTMPC_NU, nullptr, X + t * FTMPC_NX + 9, Wr);
         double jc[13], hc[13];
         rk4_column_call(k, X + t * FTMPC_NX, Wr, col, Mu + (t + 1) * FTMPC_NX, jc, hc);
         for (int i = 0; i < 13; ++i) Wz[(size_t)it * 13 + i] = hc[i];
     }
     blk.sync();
+    if (uref) {                                     // exact remainder of the input cost's (q,q) Hessian
+        for (int idx = tid; idx < N * 16; idx += nt) {
+            const int t = idx >> 4, a = (idx >> 2) & 3, b = idx & 3;
+            Wz[(size_t)t * 169 + (3 + a) * 13 + 3 + b] += Cq[(size_t)t * FTMPC_CQ + 40 + a * 4 + b];
+        }
+        blk.sync();
+    }
     blk.mark(PH_LIN);
 }
 
@@ -692,7 +773,8 @@ FT_HD QpScratch qp_carve(double* buf, int N, const ftmpc_config* cg = nullptr) {
 template <class Blk>
 FT_HD void condense(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const QpScratch& s, const double* Jz,
                     const double* Wz, const double* X, const double* U, const double* xref, const double* gradV,
-                    const double* hessV, double theta, double sigma, const double* lam_prev) {
+                    const double* hessV, double theta, double sigma, const double* lam_prev, const double* Cq = nullptr) {
+    // Cq: input-cost coupling records of an accelerating reference (FTMPC_CQ) or nullptr
     const int N = L.N, n = L.n, ld = L.nv, tid = blk.tid(), nt = blk.nthreads();
     double* H = s.E;
     double* G = s.G;          // 13 x ld, current d x_t / d U
@@ -727,7 +809,10 @@ FT_HD void condense(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
             const int kk = idx / nc, b = idx % nc;
             double v = 0.0;
             for (int l = 0; l < 7; ++l) v += 0.5 * (wz[kk * 13 + l] + wz[l * 13 + kk]) * G[(6 + l) * ld + b];
-            T[kk * n + b] = theta * v;
+            v *= theta;
+            if (Cq && kk >= 3)
+                for (int l = 0; l < 4; ++l) v += Cq[(size_t)t * FTMPC_CQ + 16 + (kk - 3) * 4 + l] * G[(9 + l) * ld + b];
+            T[kk * n + b] = v;
         }
         blk.sync();
         // accumulate into the live block  H[a][b], a,b < nc
@@ -749,6 +834,8 @@ FT_HD void condense(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
             if (b < nc) {
                 for (int l = 0; l < 7; ++l) v += 0.5 * (wz[(7 + j) * 13 + l] + wz[l * 13 + 7 + j]) * G[(6 + l) * ld + b];
                 v *= theta;
+                if (Cq && j < 3)
+                    for (int l = 0; l < 4; ++l) v += Cq[(size_t)t * FTMPC_CQ + 4 + j * 4 + l] * G[(9 + l) * ld + b];
             } else {
                 const int j2 = b - nc;
                 v = theta * 0.5 * (wz[(7 + j) * 13 + 7 + j2] + wz[(7 + j2) * 13 + 7 + j]);
@@ -768,9 +855,10 @@ FT_HD void condense(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
                 double v = 0.0;
                 for (int kk = 0; kk < FTMPC_NE; ++kk)
                     v += 2.0 * cfg.Q[kk] * (X[t * FTMPC_NX + kk] - xref[t * FTMPC_NE + kk]) * G[kk * ld + a];
+                if (Cq) for (int l = 0; l < 4; ++l) v += Cq[(size_t)t * FTMPC_CQ + l] * G[(9 + l) * ld + a];
                 s.g[a] += v;
             } else {
-                s.g[a] = 2.0 * cfg.R[a - nc] * U[a];
+                s.g[a] = 2.0 * cfg.R[a - nc] * (U[a] - (Cq ? Cq[(size_t)t * FTMPC_CQ + 32 + a - nc] : 0.0));
                 if (sigma > 0.0) {
                     double av = 0.0;
                     for (int i = 0; i < FTMPC_NH; ++i)
@@ -892,8 +980,11 @@ __device__ __forceinline__ void phase_lin(CudaBlock& blk, const ftmpc_config& cf
     // stage states and wrenches -> shared memory
     for (int i = tid; i < (N + 1) * FTMPC_NX; i += nt) s.X[i] = X[i];
     blk.sync();
-    for (int t = tid; t < N; t += nt)
-        stage_wrench(cfg, U + t * FTMPC_NU, uref ? uref + t * FTMPC_NU : nullptr, s.X + t * FTMPC_NX + 9, s.wr + t * 6);
+    double* Cq = w + L.oCq;
+    for (int t = tid; t < N; t += nt) {
+        stage_wrench(cfg, U + t * FTMPC_NU, nullptr, s.X + t * FTMPC_NX + 9, s.wr + t * 6);      // U holds u~ (FTMPC_CQ)
+        if (uref) stage_cost_coupling(cfg, U + t * FTMPC_NU, uref + t * FTMPC_NU, s.X + t * FTMPC_NX + 9, Cq + (size_t)t * FTMPC_CQ);
+    }
     blk.sync();
     // pass 1: first-order columns
     for (int it = tid; it < ntask; it += nt) {
@@ -910,7 +1001,8 @@ __device__ __forceinline__ void phase_lin(CudaBlock& blk, const ftmpc_config& cf
     // running-cost gradient 2Q (x_t - xr_t) of every stage, parked in the (not yet used) costate slots
     for (int i = tid; i < N * FTMPC_NX; i += nt) {
         const int t = i / FTMPC_NX, r = i - t * FTMPC_NX;
-        s.mu[i] = (r < FTMPC_NE) ? 2.0 * cfg.Q[r] * (s.X[i] - xref[t * FTMPC_NE + r]) : 0.0;
+        s.mu[i] = (r < FTMPC_NE) ? 2.0 * cfg.Q[r] * (s.X[i] - xref[t * FTMPC_NE + r])
+                                 : (uref ? Cq[(size_t)t * FTMPC_CQ + r - FTMPC_NE] : 0.0);
     }
     // terminal costate  mu_N = [grad V_f + A_f' lam_term ; 0]   (threads from the other end of the block)
     for (int i = nt - 1 - tid; i < FTMPC_NX; i += nt) {
@@ -974,6 +1066,16 @@ __device__ __forceinline__ void phase_lin(CudaBlock& blk, const ftmpc_config& cf
         }
     }
     blk.sync();
+    if (uref) {                                     // exact remainder of the input cost's (q,q) Hessian
+        for (int idx = tid; idx < N * 16; idx += nt) {
+            const int t = idx >> 4, a = (idx >> 2) & 3, b = idx & 3;
+            const double v = Cq[(size_t)t * FTMPC_CQ + 40 + a * 4 + b];
+            const size_t o = (size_t)t * 169 + (3 + a) * 13 + 3 + b;
+            Wz[o] += v;
+            if (WzS) WzS[o] += v;
+        }
+        blk.sync();
+    }
     blk.mark(PH_LIN);
 }
 #endif  // __CUDACC__
@@ -998,20 +1100,20 @@ struct HBlocks {
 __device__ __forceinline__ bool condense_fast_path(const WsLayout& L, int nt) {
     const int N = L.N, ld = L.nv;
     const int ldp = 7 * N + 1;
-    const size_t panel_doubles = (size_t)64 * ldp + (size_t)N * FTMPC_NE + 90 + (size_t)L.mc + 90;
+    const size_t panel_doubles = (size_t)64 * ldp + (size_t)N * FTMPC_NE + 90 + (size_t)L.mc + 90 + (size_t)N * 10;
     return !(N * (N + 1) / 2 > nt || L.n > nt || panel_doubles > (size_t)(ld + FTMPC_NE) * ld);
 }
 __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg, const WsLayout& L, const QpScratch& s,
                                          const double* Jz, const double* Wz_in, const double* X, const double* U,
                                          const double* xref, const double* gradV, const double* hessV, double theta,
-                                         double sigma, const double* lam_prev_g, HBlocks* hb = nullptr) {
+                                         double sigma, const double* lam_prev_g, HBlocks* hb = nullptr, const double* Cq = nullptr) {
     const int N = L.N, n = L.n, ld = L.nv, tid = blk.tid(), nt = blk.nthreads();
     const int nblk = N * (N + 1) / 2;
     if (hb) hb->fast = false;
     const int ldp = 7 * N + 1;                     // panel row length: block column b starts at 7 b (6 + 1 pad -> lanes of
                                                    // neighbouring blocks are an odd number of doubles apart: no bank conflicts)
     if (!condense_fast_path(L, nt)) {              // very short / long horizons: generic path
-        condense<CudaBlock>(blk, cfg, L, s, Jz, Wz_in, X, U, xref, gradV, hessV, theta, sigma, lam_prev_g);
+        condense<CudaBlock>(blk, cfg, L, s, Jz, Wz_in, X, U, xref, gradV, hessV, theta, sigma, lam_prev_g, Cq);
         return;
     }
     double* Wp = const_cast<double*>(Wz_in);       // scratch copy owned by the caller: symmetrised / scaled in place
@@ -1022,6 +1124,7 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
     double* lam_prev = tgv + 9;                    // [mc]     shared-memory copy of the previous multipliers: the tests
                                                    //          `lam_prev[i] > 0` sit in serial loops, one L2 round trip each otherwise
     double* hv = lam_prev + L.mc;                  // [81 + 9] hessV, gradV
+    double* cqs = hv + 90;                         // [N][10]  accelerating references (FTMPC_CQ): gq (4), rho (6)
     const double* Ah = s.hull;
     // ---- pre-pass: W' = theta * sym(W) (+ 2Q on the omega diagonal), qe, Ht
     for (int idx = tid; idx < N * 169; idx += nt) {
@@ -1040,7 +1143,26 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
     }
     if (sigma > 0.0) for (int i = tid; i < L.mc; i += nt) lam_prev[i] = lam_prev_g[i];
     for (int i = tid; i < 90; i += nt) hv[i] = (i < 81) ? hessV[i] : gradV[i - 81];
+    if (Cq)
+        for (int i = tid; i < N * 10; i += nt) {
+            const int t = i / 10, e = i - t * 10;
+            cqs[i] = Cq[(size_t)t * FTMPC_CQ + (e < 4 ? e : 28 + e)];
+        }
     blk.sync();
+    if (Cq) {       // Gauss-Newton part of the input cost's attitude coupling: NOT blended (added after the theta scaling)
+        for (int idx = tid; idx < N * 28; idx += nt) {
+            const int t = idx / 28, e = idx - t * 28;
+            double* wz = Wp + (size_t)t * 169;
+            if (e < 16) {
+                wz[(3 + (e >> 2)) * 13 + 3 + (e & 3)] += Cq[(size_t)t * FTMPC_CQ + 16 + e];
+            } else {
+                const int i = (e - 16) >> 2, b = (e - 16) & 3;
+                const double v = Cq[(size_t)t * FTMPC_CQ + 4 + i * 4 + b];
+                wz[(7 + i) * 13 + 3 + b] += v;
+                wz[(3 + b) * 13 + 7 + i] += v;
+            }
+        }
+    }
     for (int idx = tid; idx < 90; idx += nt) {
         double v = 0.0;
         const int kk = idx / 9, l = idx - kk * 9;
@@ -1134,6 +1256,10 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
                     for (int i = 0; i < FTMPC_NU; ++i) buf[(26 + i) * ldp + pa_] = sx[i];
 #pragma unroll
                     for (int kk = 0; kk < FTMPC_NE; ++kk) gs += qe[t * FTMPC_NE + kk] * g[kk];
+                    if (Cq) {
+#pragma unroll
+                        for (int l = 0; l < 4; ++l) gs += cqs[t * 10 + l] * g[9 + l];
+                    }
                     double gn[FTMPC_NX];
 #pragma unroll
                     for (int r = 0; r < FTMPC_NX; ++r) {
@@ -1168,7 +1294,7 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
                 const double* jz = Jz + (size_t)t * 169;
 #pragma unroll
                 for (int r = 0; r < FTMPC_NX; ++r) g[r] = jz[(7 + ja) * 13 + r];
-                gs = 2.0 * cfg.R[ja] * U[a];
+                gs = 2.0 * cfg.R[ja] * (U[a] - (Cq ? cqs[t * 10 + 4 + ja] : 0.0));
                 if (sigma > 0.0) {
                     double av = 0.0;
                     for (int i = 0; i < FTMPC_NH; ++i)
@@ -1440,12 +1566,12 @@ template <class Blk>
 FT_HD int factor_hessian(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const QpScratch& s, double* Jz, double* Wz,
                          const double* Jz_src, const double* Wz_src, const double* X, const double* U, const double* xref,
                          const double* gradV, const double* hessV, double theta, double sigma, const double* lam_prev,
-                         double* dscale_out, bool copy_j = true, bool copy_w = true) {
+                         double* dscale_out, bool copy_j = true, bool copy_w = true, const double* Cq = nullptr) {
     const int N = L.N, n = L.n, ld = L.nv, tid = blk.tid(), nt = blk.nthreads();
     (void)copy_j; (void)copy_w;
     for (int i = tid; i < N * 169; i += nt) { Jz[i] = Jz_src[i]; Wz[i] = Wz_src[i]; }     // (the QP reuses this region)
     blk.sync();
-    condense(blk, cfg, L, s, Jz, Wz, X, U, xref, gradV, hessV, theta, sigma, lam_prev);
+    condense(blk, cfg, L, s, Jz, Wz, X, U, xref, gradV, hessV, theta, sigma, lam_prev, Cq);
     blk.mark(PH_COND);
     blk.count(CT_CONDENSE);
     double dmaxl = 0.0;
@@ -1464,18 +1590,18 @@ __device__ __forceinline__ int factor_hessian(CudaBlock& blk, const ftmpc_config
                                               double* Jz, double* Wz, const double* Jz_src, const double* Wz_src,
                                               const double* X, const double* U, const double* xref, const double* gradV,
                                               const double* hessV, double theta, double sigma, const double* lam_prev,
-                                              double* dscale_out, bool copy_j = true, bool copy_w = true) {
+                                              double* dscale_out, bool copy_j = true, bool copy_w = true, const double* Cq = nullptr) {
     const int N = L.N, n = L.n, ld = L.nv, tid = blk.tid(), nt = blk.nthreads();
     if (!condense_fast_path(L, nt))
         return factor_hessian<CudaBlock>(blk, cfg, L, s, Jz, Wz, Jz_src, Wz_src, X, U, xref, gradV, hessV, theta, sigma,
-                                         lam_prev, dscale_out);
+                                         lam_prev, dscale_out, true, true, Cq);
     // the linearisation leaves Jz / Wz in place (shared memory); Wz is scaled in place below, so a second attempt
     // re-reads Wz (and, once the active-set solver has reused the region, Jz too) from the global backing copy
     if (copy_j) for (int i = tid; i < N * 169; i += nt) Jz[i] = Jz_src[i];
     if (copy_w) for (int i = tid; i < N * 169; i += nt) Wz[i] = Wz_src[i];
     blk.sync();
     HBlocks hb;
-    condense(blk, cfg, L, s, Jz, Wz, X, U, xref, gradV, hessV, theta, sigma, lam_prev, &hb);
+    condense(blk, cfg, L, s, Jz, Wz, X, U, xref, gradV, hessV, theta, sigma, lam_prev, &hb, Cq);
     blk.mark(PH_COND);
     blk.count(CT_CONDENSE);
     double dmaxl = 0.0;
@@ -1549,7 +1675,7 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     for (;;) {
         double dscale = 0.0;
         const int bad = factor_hessian(blk, cfg, L, s, Jz, Wz, w + L.oJz, w + L.oWz, w + L.oX, w + L.oU, xref, w + L.oGV,
-                                       w + L.oHV, theta, sigma, lam_prev, &dscale, !have_j, !have_w);
+                                       w + L.oHV, theta, sigma, lam_prev, &dscale, !have_j, !have_w, io.uref ? w + L.oCq : nullptr);
         have_j = true;                  // Jz survives a failed factorisation, the scaled Wz does not
         have_w = false;
         if (!bad) break;

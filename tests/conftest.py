@@ -56,3 +56,10 @@ def built():
 def golden():
     import numpy as np
     return np.load(ROOT / "tests" / "golden" / "nlp_cases.npz")
+
+
+@pytest.fixture(scope="session")
+def accel_golden():
+    """oracle KKT points for accelerating (circle) references: non-zero nominal wrench (tools/gen_golden.py --accel)"""
+    import numpy as np
+    return np.load(ROOT / "tests" / "golden" / "nlp_cases_accel.npz")

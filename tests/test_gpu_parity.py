@@ -264,6 +264,54 @@ def test_step_vs_golden(L, oracle, golden, N):
         assert np.allclose(out["z"][j, 6 * N:].reshape(N + 1, 13), X, rtol=1e-12, atol=1e-12), name
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [15, 20])
+def test_step_accelerating_reference_vs_golden(L, oracle, accel_golden, N):
+    """row f-3: circle references (non-zero nominal wrench, rotated per stage inside the kernels) against the oracle"""
+    g = accel_golden
+    ks = H.cases_with_horizon(g, N)
+    assert len(ks) == 2 and np.abs(g["uref"][ks]).max() > 1.0
+    eng, out = run_cases(g, ks, N)
+    assert (out["status"] == 0).all(), out["status"]
+    nbits = 26 * N + 72
+    for j, k in enumerate(ks):
+        name, u0 = g["name"][k], g["U"][k, 0]
+        assert out["cost"][j] == pytest.approx(g["f"][k], rel=1e-9), name
+        assert np.abs(out["u0"][j] - u0).max() <= 1e-5 * max(1.0, np.abs(u0).max()), name
+        assert H.active_bits(out["active"][j].view(np.uint32), nbits) == H.active_bits(g["active"][k], nbits), name
+        assert np.allclose(out["thrust"][j], g["thrust"][k], atol=2e-5), name
+        kk = oracle.kkt_residual(H.case_problem(oracle, g, k), out["z"][j, :6 * N])
+        assert kk["stat"] < 1e-5 and kk["viol"] < 1e-7, (name, kk["stat"], kk["viol"])
+
+
+@pytest.mark.gpu
+def test_get_control_tracks_circle_reference(L, oracle, accel_golden):
+    """the reference-facing call with an accelerating trajectory: load_trajectory("generate_circle") + get_control(x, t)
+    reproduces the oracle's thrust for the golden window (circle0_N15 starts at step 5, t = 0.5), and the debug
+    history records the step in the reference's export format"""
+    from ft_mpc_b200.controllers import SpiralingController
+    from ft_mpc_b200.models import SpiralModel, SystemModel
+    from ft_mpc_b200.util import BrokenThruster, ControllerDebug
+    g = accel_golden
+    k = list(g["name"]).index("circle0_N15")
+    model = SystemModel(0.1)
+    for i, a in H.case_faults(g, k):
+        model.set_fault(BrokenThruster(i, a))
+    dbg = ControllerDebug()
+    ctrl = SpiralingController(SpiralModel.from_system_model(model), {"horizon": 15}, dbg)
+    ctrl.load_trajectory("generate_circle", 3)
+    xr, ur = ctrl.get_next_trajectory_part(0.5)
+    assert np.allclose(xr.T, g["xref"][k, :16], atol=1e-14) and np.allclose(ur.T, g["uref"][k, :16], rtol=1e-12, atol=1e-11)
+    thrust = ctrl.get_control(g["x0"][k], 0.5)
+    assert ctrl.last_status == 0
+    assert np.abs(ctrl.last_u0 - g["U"][k, 0]).max() <= 1e-5 * max(1.0, np.abs(g["U"][k, 0]).max())
+    assert np.allclose(thrust, g["thrust"][k], atol=2e-5)
+    row = dbg.table()
+    assert row.shape == (1, 67) and row[0, 0] == 0.5 and np.allclose(row[0, 14:30], thrust)
+    assert np.allclose(row[0, 36:45], oracle.robot_to_center(g["x0"][k])[:9], atol=1e-12)          # circle state = c0[:9]
+    assert np.allclose(row[0, 45:48], g["xref"][k, 0, 0:3] - g["x0"][k, 0:3])                       # position error
+
+
 def test_step_kkt_residual_through_oracle(L, oracle, golden):
     """solver-independent check: the GPU's U* satisfies the KKT conditions of the oracle's restatement of the NLP"""
     N = 20

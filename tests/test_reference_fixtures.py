@@ -101,3 +101,51 @@ def test_cuda_kernels_match_reference(ft, built, ref, tag):
     jac = torch.zeros(K, 1, 13, 13, dtype=torch.float64, device="cuda")
     L.check(L.lib().ftmpc_rk4_jac(eng.handle, K, p(xs), p(wrench), p(jac), None, None, None))
     assert np.allclose(xs[:, 1].cpu().numpy(), ref[f"{tag}::spiral_next"], rtol=1e-13, atol=1e-14)
+
+
+ASSIGN_CMDS = ("hover", "generate_line", "generate_circle", "circle_r_1.5_sPerFullCircle_12")
+
+
+def test_assign_trajectory_matches_reference(ft, oracle, ref):
+    """Row f-3: assign_trajectory (padding, omega_des rows, finite-difference nominal wrench) and the window slicing of
+    the reference's controller (spiraling_mpc.py:255-286, 356-365) -- the reference methods were executed unbound on a
+    namespace by tools/gen_ref_fixtures.py; the host mirror is run the same way (its constructor needs a GPU)."""
+    import types
+    from ft_mpc_b200.controllers import SpiralingController
+    from ft_mpc_b200.util.get_trajectory import load_trajectory
+    for cmd in ASSIGN_CMDS:
+        ns = types.SimpleNamespace(Nt=20, dt=0.1, mass=16.8, device="cpu",
+                                   spiral_params=types.SimpleNamespace(omega_des=np.array([0.0, 0.0, 0.6])))
+        SpiralingController.assign_trajectory(ns, load_trajectory(cmd, 0.1, 3))
+        assert np.allclose(ns.trajectory, ref[f"assign::{cmd}::trajectory"], rtol=0, atol=1e-14), cmd
+        assert np.allclose(ns.nominal_input, ref[f"assign::{cmd}::nominal_input"], rtol=1e-12, atol=1e-11), cmd
+        xr, ur = SpiralingController.get_next_trajectory_part(ns, 1.7)
+        assert np.allclose(xr, ref[f"assign::{cmd}::window_x"], atol=1e-14) and np.allclose(ur, ref[f"assign::{cmd}::window_u"], rtol=1e-12, atol=1e-11)
+        # (the padded tail of the line reference brakes, so only `hover` has an identically zero nominal wrench)
+        assert ns._accelerating == bool(np.abs(ref[f"assign::{cmd}::nominal_input"]).max() > 0) and ns._accelerating == (cmd != "hover")
+        # device tables are the transposed host tables; windows are contiguous [batch, N+1, .]
+        ns.reference_window = types.MethodType(SpiralingController.reference_window, ns)
+        w = SpiralingController.nominal_window(ns, 17, batch=3)
+        if ns._accelerating:
+            assert w.shape == (3, 21, 6) and w.is_contiguous() and np.allclose(w[1].numpy().T, ur, rtol=1e-12, atol=1e-11)
+        else:
+            assert w is None
+        # the oracle's restatement agrees as well
+        traj, nom = oracle.assign_trajectory(load_trajectory(cmd, 0.1, 3), 20, 0.1)
+        assert np.allclose(traj, ref[f"assign::{cmd}::trajectory"], atol=1e-14) and np.allclose(nom, ref[f"assign::{cmd}::nominal_input"], rtol=1e-12, atol=1e-11)
+
+
+def test_debug_export_matches_reference(ft, ref, tmp_path):
+    """Row f-4: the 67-column ';'-CSV of ControllerDebug.export and the error definitions of DebugVal
+    (controller_debug.py:9-79, 216-260).  The fixture is the file the reference's own classes wrote for a synthetic
+    5-step history; the mirror must write the same bytes."""
+    import types
+    from ft_mpc_b200.util.controller_debug import HEADER, ControllerDebug
+    holder = types.SimpleNamespace(model=types.SimpleNamespace(D=ref["debug::D"], faulty_force=np.zeros(16)))
+    dbg = ControllerDebug.from_batch(holder, 0.1 * np.arange(5), ref["debug::states"], ref["debug::centers"],
+                                     ref["debug::thrusts"], ref["debug::desired"])
+    dbg.export(tmp_path / "dbg")
+    got = (tmp_path / "dbg.csv").read_bytes()
+    want = ref["debug::csv"].tobytes()
+    assert len(HEADER) == 67 and dbg.table().shape == (5, 67)
+    assert got == want

@@ -134,7 +134,40 @@ def main():
     print("wrote", dst, "cases", len(cases))
 
 
-if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1].startswith("--")):
+def make_accel_cases():
+    """(6) accelerating references: circles of get_trajectory.generate_circle, non-zero nominal
+    wrench rotated into the body frame per stage (spiraling_mpc.py:156-166, 279-286)."""
+    from ft_mpc_b200.util.get_trajectory import load_trajectory
+    cases = []
+    st = scenarios.random_states(4, 11)
+    specs = [("generate_circle", 15, [(10, 1.0), (11, 1.0)], 5), ("generate_circle", 20, [(3, 0.0)], 12),
+             ("circle_r_1_sPerFullCircle_15", 15, [(3, 0.0)], 7), ("circle_r_1_sPerFullCircle_15", 20, [(10, 1.0), (11, 1.0)], 30)]
+    for i, (cmd, N, faults, k0) in enumerate(specs):
+        traj, nom = o.assign_trajectory(load_trajectory(cmd, 0.1, 3), N, 0.1)
+        xr, ur = o.window(traj, nom, k0, N)
+        x0 = st[i].copy()
+        x0[0:3] = 0.5 * x0[0:3] + xr[0, 0:3]                 # start in the neighbourhood of the moving target
+        cases.append(dict(name=f"circle{i}_N{N}", faults=faults, N=N, x0=x0, xref=xr, uref=ur))
+    return cases
+
+
+def main_accel():
+    cases = make_accel_cases()
+    with Pool(4) as p:
+        results = {}
+        for name, res, dt in p.imap_unordered(solve_case, cases):
+            results[name] = res
+            print(f"{name}: f={res['f']:.6f} kkt={res['kkt_stat']:.1e} viol={res['kkt_viol']:.1e} polished={res['polished']} "
+                  f"nact={len(res['active'])} {dt:.0f}s", flush=True)
+    out = pack(cases, [results[c["name"]] for c in cases])
+    dst = ROOT / "tests" / "golden" / "nlp_cases_accel.npz"
+    np.savez_compressed(dst, **out)
+    print("wrote", dst, "cases", len(cases), "max |uref|", np.abs(out["uref"]).max())
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "--accel":
+    main_accel()
+elif __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1].startswith("--")):
     main()
 
 

@@ -158,10 +158,19 @@ def _install_stubs():
     ca.norm_2 = lambda a: (MX(lambda env: np.array([[np.linalg.norm(_val(a, env))]]), (1, 1)) if isinstance(a, MX)
                            else float(np.linalg.norm(np.asarray(a, dtype=float))))
     sys.modules["casadi"] = ca
-    sys.modules["casadi.tools"] = types.ModuleType("casadi.tools")
-    for name in ("cvxpy", "polytope", "matplotlib", "matplotlib.pyplot", "matplotlib.animation", "mpl_toolkits",
-                 "mpl_toolkits.mplot3d", "mpl_toolkits.mplot3d.art3d", "qpsolvers"):
-        sys.modules.setdefault(name, types.ModuleType(name))
+
+    class _Any(types.ModuleType):
+        """imported-but-not-reached packages: any attribute is an empty class"""
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return type(name, (), {})
+
+    for name in ("casadi.tools", "cvxpy", "polytope", "matplotlib", "matplotlib.pyplot", "matplotlib.animation", "mpl_toolkits",
+                 "mpl_toolkits.mplot3d", "mpl_toolkits.mplot3d.art3d", "qpsolvers", "pympc", "pympc.geometry",
+                 "pympc.geometry.polyhedron", "pympc.dynamics", "pympc.dynamics.discrete_time_systems", "pympc.control",
+                 "pympc.control.controllers", "pympc.plot", "control"):
+        sys.modules.setdefault(name, _Any(name))
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
 
 
@@ -225,6 +234,37 @@ def main():
         out[f"{tag}::spiral_next"] = np.stack([np.asarray(spiral.dynamics(c[k], u6[k]), float).ravel() for k in range(K)])   # RK4 of spiral_model.py:44-76
     for cmd in ("hover", "hover_1_-2_0.5", "generate_line", "generate_circle"):
         out[f"traj::{cmd}"] = np.asarray(load_trajectory(cmd, dt, 3), float)          # (action, dt, duration), get_trajectory.py:6
+    # ---- reference-window code of the controller (spiraling_mpc.py:255-286, 356-365), run UNBOUND on a namespace that
+    # carries exactly the attributes those two methods read (the constructor would build the CasADi NLP)
+    from ft_mpc.controllers.spiraling_mpc import SpiralingController as RefController
+    for cmd in ("hover", "generate_line", "generate_circle", "circle_r_1.5_sPerFullCircle_12"):
+        ns = types.SimpleNamespace(Nt=20, dt=dt, mass=model.mass, spiral_params=types.SimpleNamespace(omega_des=np.array([0.0, 0.0, 0.6])))
+        RefController.assign_trajectory(ns, np.asarray(load_trajectory(cmd, dt, 3), float))
+        out[f"assign::{cmd}::trajectory"] = np.asarray(ns.trajectory, float)
+        out[f"assign::{cmd}::nominal_input"] = np.asarray(ns.nominal_input, float)
+        xr, ur = RefController.get_next_trajectory_part(ns, 1.7)
+        out[f"assign::{cmd}::window_x"], out[f"assign::{cmd}::window_u"] = np.asarray(xr, float), np.asarray(ur, float)
+    # ---- export format (controller_debug.py:9-79, 216-260): a synthetic 5-step history through the reference's own
+    # DebugVal / ControllerDebug.export; the CSV text is the fixture
+    import tempfile
+    from ft_mpc.util.controller_debug import ControllerDebug as RefDebug, DebugVal as RefVal
+    dbg = RefDebug()
+    holder = types.SimpleNamespace(model=model)
+    T = 5
+    xs = np.concatenate([rng.uniform(-1, 1, (T, 6)), q[:T], rng.uniform(-.5, .5, (T, 3))], axis=1)
+    cs = rng.uniform(-1, 1, (T, 13))
+    us = rng.uniform(0, model.max_thrust, (T, 16))
+    des = rng.uniform(-1, 1, (T, 9))
+    for k in range(T):
+        dv = RefVal(holder, 0.1 * k)
+        dv.set_state(xs[k]); dv.set_circle_state(cs[k]); dv.set_input(us[k], model); dv.set_desired_state(des[k])
+        dv.calculate_errors()
+        dbg.add_debug_val(dv)
+    with tempfile.TemporaryDirectory() as td:
+        dbg.export(td + "/dbg")
+        out["debug::csv"] = np.frombuffer(Path(td + "/dbg.csv").read_bytes(), dtype=np.uint8)
+    out["debug::D"] = np.asarray(model.D, float)
+    out["debug::states"], out["debug::centers"], out["debug::thrusts"], out["debug::desired"] = xs, cs, us, des
     dst = ROOT / "tests" / "golden" / "ref_fixtures.npz"
     np.savez_compressed(dst, **out)
     print("wrote", dst, "with", len(out), "arrays")
