@@ -185,3 +185,43 @@ def test_all_gather_results_world2_gloo(batch):
     assert full.shape == (batch, 16)
     assert np.array_equal(full[:, 0], ids) and np.array_equal(full[:, 13], 2 * ids)
     assert np.array_equal(full[:, 14], ids % 5) and (full[:, 15] == 300).all()
+
+
+def test_analytic_zonotope_facets_match_qhull_table(ft):
+    """Row f-2: facets of the wrench zonotope by direct enumeration == the Qhull hulls of the reference's InputBounds
+    (input_bounds.py:43-76) for every tabulated single / double fault cell, as SETS of rows (the reference's row order
+    is an artefact of Qhull's rounding noise); rank-deficient cells, where Qhull raises, come back as flat polytopes."""
+    from ft_mpc_b200.controllers.tools.input_bounds import hull_of_faults, zonotope_facets
+    from ft_mpc_b200.models import SystemModel
+    from ft_mpc_b200 import _lib as L
+    z = np.load(L.DATA_DIR / "hull_cells.npz")
+    m = SystemModel(0.1)
+    checked = 0
+    for c in range(0, len(z["nh"]), 3):                       # every third cell keeps the CPU suite short
+        nh = int(z["nh"][c])
+        if nh == 0:
+            continue
+        faults = [(int(z["idx"][c, j]), float(z["inten"][c, j])) for j in range(int(z["nfault"][c]))]
+        A, b, r = zonotope_facets(m.D, m.max_thrust, faults)
+        assert r == 6 and A.shape == (nh, 6)
+        assert np.allclose(np.linalg.norm(A, axis=1), 1.0, atol=1e-12)
+        got = {tuple(x) for x in np.round(np.column_stack([A, b]), 7) + 0.0}
+        want = {tuple(x) for x in np.round(np.column_stack([z["A"][c, :nh], z["b"][c, :nh]]), 7) + 0.0}
+        assert got == want, faults
+        checked += 1
+    assert checked > 100
+    # canonical order is deterministic and independent of the intensities (A depends on the mask only)
+    A0, b0 = hull_of_faults(m.D, m.max_thrust, [(3, 0.0)], method="analytic")
+    A1, b1 = hull_of_faults(m.D, m.max_thrust, [(3, 0.37)], method="analytic")
+    assert np.array_equal(A0, A1) and np.allclose(b1 - b0, A0 @ (m.D[:, 3] * 0.37 * m.max_thrust), atol=1e-12)
+    # every corner wrench satisfies the rows, and each row is tight for some corner
+    rng = np.random.default_rng(0)
+    u = rng.integers(0, 2, (400, 16)) * m.max_thrust
+    u[:, 3] = 0.37 * m.max_thrust
+    s = (m.D @ u.T).T @ A1.T - b1
+    assert s.max() <= 1e-9
+    # rank-deficient pair (Qhull raises QhullError for it): flat polytope, opposite rows with zero width
+    A, b, r = zonotope_facets(m.D, m.max_thrust, [(12, 0.0), (13, 0.0)])
+    assert r == 5 and np.isfinite(A).all()
+    flat = [(i, j) for i in range(len(A)) for j in range(i) if np.allclose(A[i], -A[j], atol=1e-9) and abs(b[i] + b[j]) < 1e-9]
+    assert len(flat) == 1
