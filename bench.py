@@ -320,11 +320,13 @@ def main():
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+            # DRAM bytes of the ncu capture are per SOLVE (the capture runs a smaller batch): scale to this launch
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_solve") * B
         except Exception:
             traffic = None
     roofline = {"bound": "fp64", "kernel": "k_solve", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved / peak.value if peak.value > 0 else None, "traffic": traffic,
+                "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, per solve, x instances of this launch",
                 "peak_source": "FP64 FMA probe run live on this device (ftmpc_fp64_peak); MEASURED_PEAKS.json has no fp64 figure",
                 "flops_model": "SURVEY.md 8d: K_sqp(F_lin+F_cond+F_chol)+K_qp F_iter+F_alloc with the kernel's own iteration counters",
                 "algorithmic_flops_per_launch": solve_flops, "kernel_ms": kernel_ms,
