@@ -36,7 +36,7 @@ class FtmpcConfig(C.Structure):
     """struct ftmpc_config of include/ftmpc.h (field order and types must match exactly)."""
     _fields_ = [
         ("horizon", C.c_int32), ("dtype", C.c_int32), ("max_sqp_iter", C.c_int32), ("max_qp_iter", C.c_int32),
-        ("poll_every", C.c_int32), ("warm_qp", C.c_int32), ("n_poly", C.c_int32), ("n_root", C.c_int32), ("n_hull_sets", C.c_int32),
+        ("stall_window", C.c_int32), ("warm_qp", C.c_int32), ("n_poly", C.c_int32), ("n_root", C.c_int32), ("n_hull_sets", C.c_int32),
         ("dt", C.c_double), ("mass", C.c_double), ("inertia", C.c_double * 3), ("r", C.c_double * 3),
         ("f_virt", C.c_double * 3), ("max_thrust", C.c_double),
         ("Q", C.c_double * NE), ("R", C.c_double * NU), ("D", C.c_double * (NU * NTHR)),
@@ -58,7 +58,7 @@ def load_terminal(path=None) -> dict:
 
 def make_config(horizon: int, Q, R, *, dt: float, mass: float, inertia, r, f_virt, max_thrust: float, D,
                 terminal: dict | None = None, n_hull_sets: int = 1, max_sqp_iter: int = 60, max_qp_iter: int = 0,
-                poll_every: int = 0, sqp_tol: float = 1e-8, qp_tol: float = 1e-10, feas_tol: float = 1e-7,
+                stall_window: int = 10, sqp_tol: float = 1e-8, qp_tol: float = 1e-10, feas_tol: float = 1e-7,
                 act_tol: float = 1e-7, rho_slack: float = 1e4, clip_tol: float = 1e-9, theta_first: float = 0.5,
                 theta_growth: float = 2.0, blend_dmax: float = 1.0, warm_qp: int = 0, fast_dmax: float = 1e-5) -> FtmpcConfig:
     term = terminal or load_terminal()
@@ -69,7 +69,7 @@ def make_config(horizon: int, Q, R, *, dt: float, mass: float, inertia, r, f_vir
     cfg.max_sqp_iter = int(max_sqp_iter)
     n, m = NU * horizon, NH * horizon + NF + 2
     cfg.max_qp_iter = int(max_qp_iter) if max_qp_iter else 20 * (n + m)
-    cfg.poll_every = int(poll_every)
+    cfg.stall_window = int(stall_window)
     cfg.warm_qp = int(warm_qp)
     cfg.n_poly, cfg.n_root, cfg.n_hull_sets = len(term["poly"]), len(term["root"]), int(n_hull_sets)
     cfg.dt, cfg.mass, cfg.max_thrust = float(dt), float(mass), float(max_thrust)

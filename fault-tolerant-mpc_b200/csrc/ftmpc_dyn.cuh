@@ -136,6 +136,27 @@ FT_HD void dyn_f(const DynConsts& k, const double* v, const double* w, const dou
     if (g_out) for (int i = 0; i < 3; ++i) g_out[i] = g[i];
 }
 
+// The right-hand side splits into an attitude part that does not see (p, v) and a translational part that is a pure
+// function of the attitude stages: the same arithmetic as dyn_f, in two pieces (used by the split rollout of the step
+// acceptance, where only the attitude chain is serial).
+FT_HD void dyn_wq(const DynConsts& k, const double* w, const double* q, const double* tau, double* dw, double* dq) {
+    double c[3];
+    gyro_bilinear(k, w, w, c);
+    for (int i = 0; i < 3; ++i) dw[i] = (tau[i] - 0.5 * c[i]) * k.iJ[i];
+    double oq[4];
+    omega_apply(w, q, oq);
+    for (int i = 0; i < 4; ++i) dq[i] = 0.5 * oq[i];
+}
+FT_HD void dyn_v(const DynConsts& k, const double* w, const double* q, const double* dw, const double* F, double* dv) {
+    double e[3], g[3], t[3];
+    centri_bilinear(k, w, w, e);
+    cross3(dw, k.r, t);
+    for (int i = 0; i < 3; ++i) g[i] = F[i] * k.im + t[i] + 0.5 * e[i];
+    double R[9];
+    rot_mat(q, R);
+    mat3_tmul(R, g, dv);
+}
+
 // One RK4 step of the full 13-state.                                   sys_model.py:150-158
 FT_HD void rk4_step(const DynConsts& k, const double* x, const double* Wr, double* xn) {
     double s[13], kk[13], acc[13];

@@ -42,7 +42,7 @@ struct WsLayout {
 };
 enum {      // scalar slots
     SC_F = 0, SC_CSUM, SC_NU, SC_GD, SC_THETA, SC_DMAX, SC_DELTA, SC_LAMMAX, SC_STATUS, SC_ITER, SC_QPIT,
-    SC_NACT, SC_CHOLFAIL, SC_QPST, SC_ALPHA, SC_CMAX, SC_SIGMA, SC_HFAIL, SC_DPREV, SC_COUNT
+    SC_NACT, SC_CHOLFAIL, SC_QPST, SC_ALPHA, SC_CMAX, SC_SIGMA, SC_HFAIL, SC_DPREV, SC_DREF, SC_FREF, SC_COUNT
 };
 FT_HD WsLayout ws_layout(int N) {
     WsLayout L;
@@ -168,6 +168,23 @@ FT_HD bool sqp_fast_converged(const ftmpc_config& cfg, double dmax, double dprev
            dmax * dmax * dmax <= 0.1 * cfg.sqp_tol * dprev * dprev;
 }
 
+// Stall detector: every stall_window iterations (from 2 stall_window on) step size and objective are compared with those a
+// window earlier.  An iterate whose steps have not halved AND whose objective has moved by less than 1e-7 relative over a
+// whole window is creeping along a flat, non-convex valley (the exact Hessian is indefinite there and every attempt falls
+// back to the damped blend): it will not reach sqp_tol before the iteration cap and is reported as FTMPC_ST_MAXITER right
+// away instead of occupying its SM for the remaining iterations (each with several failed factorisations).
+// sc_ref = {step, objective} a window ago.  Returns true when stalled.
+FT_HD bool sqp_stalled(const ftmpc_config& cfg, double iter, double dmax, double f, double* sc_dref, double* sc_fref) {
+    const int w = cfg.stall_window;
+    if (w <= 0) return false;
+    const int it = (int)iter;
+    if (it % w != 0) return false;
+    const double dref = *sc_dref, fref = *sc_fref;
+    *sc_dref = dmax;
+    *sc_fref = f;
+    return it >= 2 * w && dref > 0.0 && dmax > 0.5 * dref && fabs(fref - f) <= 1e-7 * fmax(1.0, fabs(f));
+}
+
 // forward rollout at U + alpha*d: states, cost, constraint values (c <= 0 feasible).
 FT_HD void rollout_eval(const ftmpc_config& cfg, const WsLayout& L, const double* hull, const double* xref,
                         const double* uref, const double* U, const double* d, double alpha, double* X, double* C,
@@ -262,7 +279,7 @@ FT_HD void phase_ls(const ftmpc_config& cfg, const WsLayout& L, const StepIO& io
         if (sqp_step_converged(cfg, sc[SC_DMAX], sc[SC_GD], sc[SC_F]) ||
             sqp_fast_converged(cfg, sc[SC_DMAX], sc[SC_DPREV], alpha, sc[SC_THETA])) {
             sc[SC_STATUS] = (cmax <= cfg.feas_tol) ? FTMPC_ST_OK : FTMPC_ST_INFEASIBLE;
-        } else if (sc[SC_ITER] >= cfg.max_sqp_iter) {
+        } else if (sc[SC_ITER] >= cfg.max_sqp_iter || sqp_stalled(cfg, sc[SC_ITER], sc[SC_DMAX], f, sc + SC_DREF, sc + SC_FREF)) {
             sc[SC_STATUS] = FTMPC_ST_MAXITER;
         }
     }
@@ -347,6 +364,125 @@ __device__ __noinline__ double rollout_states(const ftmpc_config& cfg, int N, co
     return f;
 }
 
+// ---- split rollout --------------------------------------------------------------------------------------
+// The attitude (omega, q) of the centre state evolves on its own (torque in, no dependence on p, v), and the translation
+// is a quadrature over the attitude stages:  v_{t+1} = v_t + dv_t,  p_{t+1} = p_t + dt v_t + cp_t  with
+//   dv_t = dt/6 (kv1 + 2 kv2 + 2 kv3 + kv4),  cp_t = dt^2/6 (kv1 + kv2 + kv3)      (exactly the RK4 update of rk4_step),
+// kv_s = dyn_v at the s-th attitude stage.  Only the 7-state attitude chain is serial (40 % of the instructions of the full
+// step); the per-stage quadrature terms are independent tasks for the whole block, followed by a 2-FMA-per-stage scan.
+__device__ __noinline__ void rollout_attitude(const ftmpc_config& cfg, int N, const double* U, const double* d, double alpha,
+                                              const double* ur_conv /* u_ref when U still holds u (first rollout) */,
+                                              const double* x0, double* Xs) {
+    const DynConsts k = dyn_consts(cfg);
+    double w[3], q[4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) w[i] = x0[6 + i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = x0[9 + i];
+#pragma unroll
+    for (int i = 0; i < FTMPC_NX; ++i) Xs[i] = x0[i];
+    const double cs[4] = {0.0, 0.5 * k.dt, 0.5 * k.dt, k.dt};
+    const double bs[4] = {k.dt / 6.0, k.dt / 3.0, k.dt / 3.0, k.dt / 6.0};
+    for (int t = 0; t < N; ++t) {
+        double tau[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            tau[j] = U[t * FTMPC_NU + 3 + j] + alpha * d[t * FTMPC_NU + 3 + j];
+            if (ur_conv) tau[j] += ur_conv[t * FTMPC_NU + 3 + j];
+        }
+        double kw[3] = {0.0, 0.0, 0.0}, kq[4] = {0.0, 0.0, 0.0, 0.0}, aw[3], aq[4];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) aw[i] = w[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) aq[i] = q[i];
+#pragma unroll
+        for (int st = 0; st < 4; ++st) {
+            double sw[3], sq[4];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) sw[i] = w[i] + cs[st] * kw[i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sq[i] = q[i] + cs[st] * kq[i];
+            dyn_wq(k, sw, sq, tau, kw, kq);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) aw[i] += bs[st] * kw[i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) aq[i] += bs[st] * kq[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { w[i] = aw[i]; Xs[(t + 1) * FTMPC_NX + 6 + i] = aw[i]; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { q[i] = aq[i]; Xs[(t + 1) * FTMPC_NX + 9 + i] = aq[i]; }
+    }
+}
+// One (step length, stage) task: stage wrench -> Ws, quadrature terms dv_t / cp_t -> the (v, p) slots of stage t + 1 of Xs
+// (turned into states by rollout_scan), input + attitude-rate cost of the stage -> *cost.
+__device__ __noinline__ void rollout_stage_task(const ftmpc_config& cfg, int t, const double* xref, const double* uref,
+                                                const double* U, const double* d, double alpha, double* Xs, double* Ws,
+                                                double* cost, double* Uconv_s, double* Uconv_g) {
+    const DynConsts k = dyn_consts(cfg);
+    const double* xt = Xs + t * FTMPC_NX;
+    double u[FTMPC_NU], rho[FTMPC_NU] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, Wr[FTMPC_NU];
+#pragma unroll
+    for (int j = 0; j < FTMPC_NU; ++j) u[j] = U[t * FTMPC_NU + j] + alpha * d[t * FTMPC_NU + j];
+    if (uref) {                                       // U holds u~ = u + rho(q_t), see FTMPC_CQ
+        nominal_rot(xt + 9, uref + t * FTMPC_NU, rho);
+        if (Uconv_s) {                                // first rollout: U still holds u
+#pragma unroll
+            for (int j = 0; j < FTMPC_NU; ++j) { u[j] += rho[j]; Uconv_s[t * FTMPC_NU + j] = u[j]; Uconv_g[t * FTMPC_NU + j] = u[j]; }
+        }
+    }
+    stage_wrench(cfg, u, nullptr, xt + 9, Wr);
+    double f = 0.0;
+#pragma unroll
+    for (int j = 0; j < FTMPC_NU; ++j) { f += cfg.R[j] * (u[j] - rho[j]) * (u[j] - rho[j]); Ws[t * FTMPC_NU + j] = Wr[j]; }
+#pragma unroll
+    for (int j = 6; j < FTMPC_NE; ++j) {
+        const double e = xt[j] - xref[t * FTMPC_NE + j];
+        f += cfg.Q[j] * e * e;
+    }
+    *cost = f;
+    // attitude stages of this step again (cheaper than parking 4 x 10 doubles per stage and step length)
+    double w[3], q[4], kw[3] = {0.0, 0.0, 0.0}, kq[4] = {0.0, 0.0, 0.0, 0.0}, dv[3] = {0.0, 0.0, 0.0}, cp[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) w[i] = xt[6 + i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = xt[9 + i];
+    const double cs[4] = {0.0, 0.5 * k.dt, 0.5 * k.dt, k.dt};
+    const double bs[4] = {k.dt / 6.0, k.dt / 3.0, k.dt / 3.0, k.dt / 6.0};
+    const double cq = k.dt * k.dt / 6.0;
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+        double sw[3], sq[4], kv[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) sw[i] = w[i] + cs[st] * kw[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sq[i] = q[i] + cs[st] * kq[i];
+        dyn_wq(k, sw, sq, Wr + 3, kw, kq);
+        dyn_v(k, sw, sq, kw, Wr, kv);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            dv[i] += bs[st] * kv[i];
+            if (st < 3) cp[i] += cq * kv[i];
+        }
+    }
+    double* xn = Xs + (t + 1) * FTMPC_NX;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { xn[i] = cp[i]; xn[3 + i] = dv[i]; }
+}
+// component c of (p, v) along the horizon from the quadrature terms; returns the position + velocity cost of that component
+__device__ __forceinline__ double rollout_scan(const ftmpc_config& cfg, int N, int c, const double* xref, double* Xs) {
+    double p = Xs[c], v = Xs[3 + c], f = 0.0;
+    for (int t = 0; t < N; ++t) {
+        const double ep = p - xref[t * FTMPC_NE + c], ev = v - xref[t * FTMPC_NE + 3 + c];
+        f += cfg.Q[c] * ep * ep + cfg.Q[3 + c] * ev * ev;
+        double* xn = Xs + (t + 1) * FTMPC_NX;
+        const double pn = p + cfg.dt * v + xn[c], vn = v + xn[3 + c];
+        xn[c] = pn; xn[3 + c] = vn;
+        p = pn; v = vn;
+    }
+    return f;
+}
+
 // value of constraint row p (c <= 0 feasible) from stored stage wrenches / terminal state
 __device__ __forceinline__ double cons_value(const ftmpc_config& cg /* global copy: per-thread rows */, int N,
                                              const double* hull, const double* xrefN, const double* Xs,
@@ -418,13 +554,38 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
     const double* xrefN = s.xref + N * FTMPC_NE;
     // A. rollouts, one step length per lane
     const int nalpha = first ? 1 : FTMPC_LS_NALPHA;
-    if (warp == 0 && lane < nalpha) {
-        const double alpha = first ? 0.0 : ldexp(1.0, -lane);
-        s.fa[lane] = rollout_states(cfg, N, s.xref, uref_g ? s.uref : nullptr, s.U, s.D, alpha, X,
-                                    s.Xs + (size_t)lane * s.xs_stride, s.Ws + (size_t)lane * s.ws_stride,
-                                    (first && uref_g) ? s.U : nullptr, U);
-    }
+    const bool conv = first && uref_g;              // accelerating reference: U still holds u (warm start), see FTMPC_CQ
+    // A1. attitude chains, one step length per lane of warp 0
+    if (warp == 0 && lane < nalpha)
+        rollout_attitude(cfg, N, s.U, s.D, first ? 0.0 : ldexp(1.0, -lane), conv ? s.uref : nullptr, X,
+                         s.Xs + (size_t)lane * s.xs_stride);
     blk.sync();
+    // A2-A4 for the step lengths [a0, a1): stage tasks spread over the warps (task k runs on lane k / nw of warp k % nw, so a
+    // handful of tasks costs one pass of one lane per warp), (p, v) scan per component, cost per step length
+    double* stage_cost = s.rec;                     // [nalpha][N], free until the terminal records are built
+    double* pv_cost = s.rec + (size_t)FTMPC_LS_NALPHA * N;    // [nalpha][3]
+    auto rollout_rest = [&](int a0, int a1) {
+        const int ntask = (a1 - a0) * N;
+        for (int idx = lane * nw + warp; idx < ntask; idx += nt) {
+            const int a = a0 + idx / N, t = idx - (a - a0) * N;
+            rollout_stage_task(cfg, t, s.xref, uref_g ? s.uref : nullptr, s.U, s.D, first ? 0.0 : ldexp(1.0, -a),
+                               s.Xs + (size_t)a * s.xs_stride, s.Ws + (size_t)a * s.ws_stride, stage_cost + a * N + t,
+                               conv ? s.U : nullptr, U);
+        }
+        blk.sync();
+        for (int idx = tid; idx < 3 * (a1 - a0); idx += nt) {
+            const int a = a0 + idx / 3, c = idx - (a - a0) * 3;
+            pv_cost[a * 3 + c] = rollout_scan(cfg, N, c, s.xref, s.Xs + (size_t)a * s.xs_stride);
+        }
+        blk.sync();
+        for (int a = a0 + tid; a < a1; a += nt) {
+            double f = (pv_cost[a * 3] + pv_cost[a * 3 + 1]) + pv_cost[a * 3 + 2];
+            for (int t = 0; t < N; ++t) f += stage_cost[a * N + t];
+            s.fa[a] = f;
+        }
+        blk.sync();
+    };
+    rollout_rest(0, 1);
     blk.mark(PH_LS_ROLL);
     // B0. alpha index 0: constraint rows by the whole block (straight into C), terminal cost with its
     //     gradient / Hessian records one term per thread (alpha = 1 is accepted most of the time)
@@ -460,6 +621,7 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
     }
     blk.sync();
     if (win < 0) {
+        rollout_rest(1, nalpha);                      // translations of the other step lengths (their attitude chains exist)
         // B1. the remaining step lengths: rows one warp per alpha, terminal cost one thread per (alpha, term)
         for (int idx = tid; idx < (nalpha - 1) * nterm; idx += nt) {
             const int a = 1 + idx / nterm, k = idx - (a - 1) * nterm;
@@ -542,7 +704,7 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
             sc[SC_ALPHA] = alpha;
             if (!finite) sc[SC_STATUS] = FTMPC_ST_QPFAIL;
             else if (sqp_step_converged(cfg, dmax, gd_prev, f_prev) || sqp_fast_converged(cfg, dmax, dprev, alpha, theta_qp)) sc[SC_STATUS] = (cmax <= cfg.feas_tol) ? FTMPC_ST_OK : FTMPC_ST_INFEASIBLE;
-            else if (iter >= cfg.max_sqp_iter) sc[SC_STATUS] = FTMPC_ST_MAXITER;
+            else if (iter >= cfg.max_sqp_iter || sqp_stalled(cfg, iter, dmax, f, sc + SC_DREF, sc + SC_FREF)) sc[SC_STATUS] = FTMPC_ST_MAXITER;
         }
         if (finite || first) { sc[SC_F] = f; sc[SC_CSUM] = csum; sc[SC_CMAX] = cmax; }
     }
@@ -1308,17 +1470,27 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
             const int t = tt;
             const double* buf = buf0 + (size_t)(t & 1) * 32 * ldp;
             if (bi < t) {
-                const int K = (t < N) ? FTMPC_NX : FTMPC_NE;
                 const double* Pa = buf + 7 * bi;
                 const double* Tb = buf + (size_t)13 * ldp + 7 * bj;
-                for (int r = 0; r < K; ++r) {
-                    double pa[6], tb[6];
+                // rank-13 update, software-pipelined by hand: the operands of row r + 1 are in flight while the 36 FMAs of
+                // row r issue (with one block warp on a scheduler nothing else hides the shared-memory latency)
+                double pa[6], tb[6], pn[6], tn[6];
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) { pa[i] = Pa[(size_t)r * ldp + i]; tb[i] = Tb[(size_t)r * ldp + i]; }
+                for (int i = 0; i < 6; ++i) { pa[i] = Pa[i]; tb[i] = Tb[i]; }
 #pragma unroll
-                    for (int i = 0; i < 6; ++i)
+                for (int r = 0; r < FTMPC_NX; ++r) {
+                    if (r < FTMPC_NE || t < N) {               // the terminal stage has 9 rows (uniform branch)
+                        if (r + 1 < FTMPC_NX) {
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) acc[i][j] += pa[i] * tb[j];
+                            for (int i = 0; i < 6; ++i) { pn[i] = Pa[(size_t)(r + 1) * ldp + i]; tn[i] = Tb[(size_t)(r + 1) * ldp + i]; }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 6; ++i)
+#pragma unroll
+                            for (int j = 0; j < 6; ++j) acc[i][j] += pa[i] * tb[j];
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) { pa[i] = pn[i]; tb[i] = tn[i]; }
+                    }
                 }
             } else if (bi == t) {
                 if (bj < t) {

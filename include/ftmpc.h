@@ -59,7 +59,8 @@ typedef struct ftmpc_config {
     int32_t dtype;             /* 0 = fp64 (only mode implemented)                                          */
     int32_t max_sqp_iter;      /* outer iteration cap (default 60)                                          */
     int32_t max_qp_iter;       /* active-set iteration cap per QP (default 20*(n+m))                        */
-    int32_t poll_every;        /* reserved (unused: ftmpc_step never synchronises; a persistent CTA stops iterating when its instance converges) */
+    int32_t stall_window;      /* stall detector (sqp_stalled): give up (FTMPC_ST_MAXITER) when the step has not halved over this many
+                                  iterations, checked from 2 windows on (default 10; 0 = run to max_sqp_iter)                  */
     int32_t warm_qp;           /* 1 = start each QP from the previous QP's active set (gi_warm_start): -40 % active-set iterations, same
                                   results; default 0 -- on the B200 the bulk update currently costs what it saves (profiles/README.md) */
     int32_t n_poly, n_root, n_hull_sets;
