@@ -192,7 +192,7 @@ def main():
                                            "the reference's casadi/IPOPT solve is not installable offline, this is the C++ port of the same SQP "
                                            "on the reference NLP (oracle/cpu_port)", "converged_frac": okf},
                 "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        _emit(line)
         return 0
 
     # ------------------------------------------------------------------ B200 arm
@@ -377,12 +377,22 @@ def main():
             "status_hist": np.bincount(status, minlength=5).tolist(), "clocks": clk.summary(), "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "latency": latency,
             "target": {"solves_per_s_8gpu": 1e6, "per_gpu": 125000.0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+def _emit(line: dict) -> None:
+    """the ONE JSON line goes to the process's original stdout; everything else written to fd 1 while the bench runs
+    (NCCL prints its version banner there) has been sent to stderr"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     sys.exit(main())

@@ -276,10 +276,16 @@ FT_HD void rk4_column(const DynConsts& k, const double* x, const double* Wr, int
     // nominal stage states (v,w,q) and body accelerations, tangents of (v,w,q)
     double sw[4][3], sq[4][4], sg[4][3];
     double tws[4][3], tqs[4][4];
-    double tW[6] = {0, 0, 0, 0, 0, 0};
-    double tx0[13];
-    for (int i = 0; i < 13; ++i) tx0[i] = 0.0;
-    if (col < 7) tx0[6 + col] = 1.0; else tW[col - 7] = 1.0;
+    // unit tangent by comparison, not by a run-time index: a dynamically indexed local array lives in local memory
+    double tW[6], tx0[13];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 13; ++i) tx0[i] = (i == 6 + col) ? 1.0 : 0.0;       // col >= 7 never matches
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 6; ++i) tW[i] = (i == col - 7) ? 1.0 : 0.0;
     double kn[13], kt[13], accn[13], acct[13];
     for (int i = 0; i < 13; ++i) { kn[i] = 0.0; kt[i] = 0.0; acct[i] = tx0[i]; accn[i] = x[i]; }
     for (int st = 0; st < 4; ++st) {
@@ -338,10 +344,16 @@ FT_HD void rk4_col_forward(const DynConsts& k, const double* x, const double* Wr
                            double* nom /* or nullptr */, double* tang, int tstride) {
     const double cs[4] = {0.0, 0.5 * k.dt, 0.5 * k.dt, k.dt};
     const double bs[4] = {k.dt / 6.0, k.dt / 3.0, k.dt / 3.0, k.dt / 6.0};
-    double tW[6] = {0, 0, 0, 0, 0, 0};
-    double tx0[13];
-    for (int i = 0; i < 13; ++i) tx0[i] = 0.0;
-    if (col < 7) tx0[6 + col] = 1.0; else tW[col - 7] = 1.0;
+    // unit tangent by comparison, not by a run-time index: a dynamically indexed local array lives in local memory
+    double tW[6], tx0[13];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 13; ++i) tx0[i] = (i == 6 + col) ? 1.0 : 0.0;       // col >= 7 never matches
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 6; ++i) tW[i] = (i == col - 7) ? 1.0 : 0.0;
     double kn[13], kt[13], accn[13], acct[13];
     for (int i = 0; i < 13; ++i) { kn[i] = 0.0; kt[i] = 0.0; acct[i] = tx0[i]; accn[i] = x[i]; }
 #if defined(__CUDA_ARCH__)
@@ -386,8 +398,11 @@ FT_HD void rk4_force_columns(const DynConsts& k, const double* nom, double* jacF
 // Reverse sweep: column `col` of the Hessian of lam^T RK4(x, W) in z-space from the parked forward data.
 FT_HD void rk4_col_reverse(const DynConsts& k, const double* nom, const double* tang, int tstride, int col,
                            const double* lam, double* hess_col) {
-    double tW[6] = {0, 0, 0, 0, 0, 0};
-    if (col >= 7) tW[col - 7] = 1.0;
+    double tW[6];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 6; ++i) tW[i] = (i == col - 7) ? 1.0 : 0.0;
     double hw[3] = {0, 0, 0}, hq[4] = {0, 0, 0, 0}, hF[3] = {0, 0, 0}, hT[3] = {0, 0, 0};
     double psi_v[3] = {0, 0, 0}, psi_w[3] = {0, 0, 0}, psi_q[4] = {0, 0, 0, 0};
     double dps_w[3] = {0, 0, 0}, dps_q[4] = {0, 0, 0, 0};

@@ -1855,7 +1855,7 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         ++fails;
         blk.sync();
         if (sigma == 0.0 && theta == 1.0 && aug_allowed) { sig0 = 10.0 * dscale; sigma = sig0; FT_DBG_COUNT(0); }
-        else if (sigma > 0.0 && sig0 > 0.0 && sigma < 50.0 * sig0) { sigma *= 10.0; FT_DBG_COUNT(1); }
+        else if (sigma > 0.0 && sig0 > 0.0 && sigma < 5.0 * sig0) { sigma *= 10.0; FT_DBG_COUNT(1); }
         else if (sigma > 0.0) { sigma = 0.0; theta = 0.5; aug_allowed = false; FT_DBG_COUNT(2); }
         else if (theta <= 0.0) { if (tid == 0) { sc[SC_QPST] = 3.0; } return; }
         else { FT_DBG_COUNT(theta == 1.0 ? 3 : 4); theta = (theta > cfg.theta_first) ? 0.5 * theta : 0.0; }     // below the first blend level: Gauss-Newton

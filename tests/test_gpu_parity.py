@@ -486,6 +486,41 @@ def test_closed_loop_driver_matches_host_loop(L, oracle, golden):
     assert float(cost[0]) == pytest.approx(fsum, rel=1e-8)
 
 
+@pytest.mark.gpu
+def test_closed_loop_on_circle_matches_get_control_loop(L, oracle, accel_golden):
+    """accelerating reference in closed loop: the device-side driver (windows of trajectory AND nominal wrench sliced on
+    the device, warm start from the second step) reproduces the reference-style host loop get_control -> plant step
+    (sim_env.py:77-99, noise off), whose first step is pinned by the oracle golden circle0_N15"""
+    from ft_mpc_b200.controllers import SpiralingController
+    from ft_mpc_b200.models import SpiralModel, SystemModel
+    from ft_mpc_b200.util import BrokenThruster
+    g = accel_golden
+    k = list(g["name"]).index("circle0_N15")
+    faults = H.case_faults(g, k)
+    model = SystemModel(0.1)
+    for i, a in faults:
+        model.set_fault(BrokenThruster(i, a))
+    ctrl = SpiralingController(SpiralModel.from_system_model(model), {"horizon": 15}, None)
+    ctrl.load_trajectory("generate_circle", 3)
+    fs = oracle.FaultSet(faults)
+    x = g["x0"][k].copy()
+    steps, k0 = 4, 5
+    for j in range(steps):                                    # host loop, oracle plant
+        thrust = ctrl.get_control(x, 0.1 * (k0 + j) + 1e-9)
+        assert ctrl.last_status == 0
+        if j == 0:
+            assert np.allclose(thrust, g["thrust"][k], atol=2e-5)
+        x = oracle.normalize_quaternion_robot(oracle.plant_rk4(x, thrust, fs, 0.1))
+    eng = ctrl.engine
+    xf, cost, worst, done = eng.closed_loop(dev(g["x0"][[k]]), ctrl._traj_dev, steps=steps, start_step=k0,
+                                            nominal_input=ctrl._uref_dev)
+    assert int(worst.max()) == 0 and int(done[0]) == steps
+    assert np.allclose(xf.cpu().numpy()[0], x, atol=1e-6)
+    # without the nominal wrench the loop ends somewhere else: the windows really are used
+    xh, *_ = eng.closed_loop(dev(g["x0"][[k]]), ctrl._traj_dev, steps=steps, start_step=k0)
+    assert np.abs(xh.cpu().numpy()[0] - x).max() > 1e-4
+
+
 def test_edge_cases_and_errors(L, oracle):
     from ft_mpc_b200.util import scenarios
     # horizon 1 and a single instance
