@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--horizon", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances per CPU step (0 = auto)")
+    ap.add_argument("--streams", type=int, default=2, help="independent batches in flight (1 = strictly serial steps)")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--solver-opts", default="{}", help='JSON dict of ftmpc_config overrides for experiments, e.g. {"warm_qp": 1}')
@@ -173,7 +174,10 @@ def main():
     config = {"workload": f"mc_fault_scenarios single+double(dead|stuck) well-posed cells, N={N}, cold start, hover, "
                           f"{a.batch} instances per GPU (BASELINE configs[3] shard)", "horizon": N, "batch_per_gpu": a.batch,
               "global_batch": a.batch * world, "seed": 1, "parallelism": f"dp{world} (independent instances, no data-path collective)",
-              "l2_policy": "per-step working set (inputs + per-instance workspace) exceeds the 126 MB L2"}
+              "l2_policy": "per-step working set (inputs + per-instance workspace) exceeds the 126 MB L2",
+              "pipelining": (f"{a.streams} CUDA streams: consecutive steps (independent batches, separate output/workspace buffers) are enqueued on "
+                             "alternating streams, so the SMs that run out of instances at the tail of one launch start on the next batch"
+                             if a.streams > 1 else "none (steps strictly serial on one stream)")}
     if a.solver_opts != "{}":
         config["solver_opts"] = json.loads(a.solver_opts)
 
@@ -234,21 +238,45 @@ def main():
     for _ in range(W):
         eng.step(st_d, xr_d, scenario=sc_t)
     sync_all()
-    # ---- timed region: device-resident inputs
-    L.check(eng.lib.ftmpc_profile_enable(eng.handle, 1))
+    # ---- timed region: device-resident inputs.  Step i runs on stream i % S with buffer set i % S; the timing events sit
+    # on the main stream, which every side stream waits for at the start and which waits for every side stream at the end.
+    S = max(1, a.streams)
+    side = [torch.cuda.Stream(device=devs) for _ in range(S)] if S > 1 else [stream]
+    for i in range(S):                                            # allocate the buffer sets outside the timed region
+        with torch.cuda.stream(side[i]):
+            eng.step(st_d, xr_d, scenario=sc_t, out=eng.buffers(hi - lo, i))
+    sync_all()
+
+    def fan_out(ev):
+        for s_ in side:
+            if s_ is not stream:
+                s_.wait_event(ev)
+
+    def fan_in():
+        for s_ in side:
+            if s_ is not stream:
+                ev = torch.cuda.Event()
+                ev.record(s_)
+                stream.wait_event(ev)
+
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         sync_all()
         e0.record(stream)
+        fan_out(e0)
         launches = 0
-        for _ in range(a.steps):
-            out = eng.step(st_d, xr_d, scenario=sc_t)
+        for i in range(a.steps):
+            with torch.cuda.stream(side[i % S]):
+                out = eng.step(st_d, xr_d, scenario=sc_t, out=eng.buffers(hi - lo, i % S))
             launches += eng.lib.ftmpc_last_launches(eng.handle)
+        fan_in()
         e1.record(stream)
         sync_all()
     ms_total = e0.elapsed_time(e1)
-    # device time of the two kernels of the LAST timed step (events recorded on the launching stream by ftmpc_step)
-    # and the solver kernel's own per-phase cycle profile
+    # one more step, alone and with the in-kernel profile switched on (per-handle counters and events, so not inside the
+    # pipelined region): device time of the two kernels and the solver kernel's per-phase cycle profile
+    L.check(eng.lib.ftmpc_profile_enable(eng.handle, 1))
+    out = eng.step(st_d, xr_d, scenario=sc_t)
     kms = (C.c_double * 2)(); cyc = (C.c_int64 * L.N_PHASES)()
     L.check(eng.lib.ftmpc_profile_read(eng.handle, C.c_void_p(stream.cuda_stream), kms, cyc, L.N_PHASES))
     kernel_ms = {"k_solve": float(kms[0]), "k_alloc": float(kms[1])}
@@ -275,23 +303,29 @@ def main():
     st_h = torch.tensor(states[lo:hi], dtype=f64).pin_memory()
     xr_h = torch.tensor(xref[lo:hi], dtype=f64).pin_memory()
     sc_h = torch.tensor(scen[lo:hi], dtype=torch.int64).pin_memory()
-    th_h = torch.empty(hi - lo, 16, dtype=f64).pin_memory()
-    stt_h = torch.empty(hi - lo, dtype=torch.int32).pin_memory()
+    th_h = [torch.empty(hi - lo, 16, dtype=f64).pin_memory() for _ in range(S)]
+    stt_h = [torch.empty(hi - lo, dtype=torch.int32).pin_memory() for _ in range(S)]
 
-    def e2e_step():
-        thrust = ctrl.step(st_h.to(devs, non_blocking=True), xr_h.to(devs, non_blocking=True), scenario=sc_h.to(devs, non_blocking=True))
-        th_h.copy_(thrust, non_blocking=True)
-        stt_h.copy_(ctrl.last["status"], non_blocking=True)
+    def e2e_step(slot):
+        with torch.cuda.stream(side[slot]):
+            thrust = ctrl.step(st_h.to(devs, non_blocking=True), xr_h.to(devs, non_blocking=True),
+                               scenario=sc_h.to(devs, non_blocking=True), slot=slot)
+            th_h[slot].copy_(thrust, non_blocking=True)
+            stt_h[slot].copy_(ctrl.last["status"], non_blocking=True)
 
-    e2e_steps = min(a.steps, 3)
-    e2e_step(); sync_all()
+    e2e_steps = a.steps
+    for i in range(S):
+        e2e_step(i)
+    sync_all()
     e0.record(stream)
-    for _ in range(e2e_steps):
-        e2e_step()
+    fan_out(e0)
+    for i in range(e2e_steps):
+        e2e_step(i % S)
+    fan_in()
     e1.record(stream)
     sync_all()
     ms_e2e = e0.elapsed_time(e1)
-    ok_e2e = float((stt_h.numpy() == 0).sum())
+    ok_e2e = float((stt_h[(e2e_steps - 1) % S].numpy() == 0).sum())
     te = torch.tensor([ms_e2e, ok_e2e], dtype=f64, device=devs)
     if world > 1:
         temax = te.clone(); dist.all_reduce(temax, op=dist.ReduceOp.MAX)
@@ -299,14 +333,16 @@ def main():
         ms_e2e, ok_e2e = float(temax[0]), float(tesum[1])
     e2e = {"value": ok_e2e * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
            "h2d_bytes_per_step": int((st_h.nbytes + xr_h.nbytes + sc_h.nbytes) * world),
-           "d2h_bytes_per_step": int((th_h.nbytes + stt_h.nbytes) * world), "steps": e2e_steps,
-           "api": "SpiralingController.step(state, ref, scenario=...) -> thrust (pinned host tensors in / out)"}
+           "d2h_bytes_per_step": int((th_h[0].nbytes + stt_h[0].nbytes) * world), "steps": e2e_steps,
+           "api": "SpiralingController.step(state, ref, scenario=..., slot=i) -> thrust (pinned host tensors in / out), step i on stream i % S"}
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         return 0
 
+    clocks_summary = clk.summary()
+    props = torch.cuda.get_device_properties(devs)
     # ---- roofline of the dominant kernel, k_solve (rank 0's shard, last timed step)
     fl = algorithmic_flops(N, iters[:, 0], iters[:, 1])
     peak = C.c_double()
@@ -330,7 +366,15 @@ def main():
                 "peak_source": "FP64 FMA probe run live on this device (ftmpc_fp64_peak); MEASURED_PEAKS.json has no fp64 figure",
                 "flops_model": "SURVEY.md 8d: K_sqp(F_lin+F_cond+F_chol)+K_qp F_iter+F_alloc with the kernel's own iteration counters",
                 "algorithmic_flops_per_launch": solve_flops, "kernel_ms": kernel_ms,
-                "kernel_share_of_step": kernel_ms["k_solve"] / (ms_total / a.steps),
+                # share of k_solve in the device time of the step's own kernels (solo profiled step; with pipelined steps the
+                # wall time per step is shorter than one launch, so the share is taken over the kernels, as the ncu list does)
+                "kernel_share_of_step": kernel_ms["k_solve"] / (kernel_ms["k_solve"] + kernel_ms["k_alloc"]),
+                "achieved_pipelined": solve_flops / (ms_total / a.steps * 1e-3) * 1e-12,
+                "kernel_ms_note": "one step alone on the main stream after the timed region, in-kernel phase profile on",
+                # cycles the persistent CTAs spent working (in-kernel clock64 marks, summed over CTAs) / (SMs x kernel time):
+                # below 1 = SMs idling at the end of the launch while the last, hardest instances finish
+                "sm_busy_frac": (float(cyc[:L.N_CYCLE_PHASES].sum()) / (props.multi_processor_count * kernel_ms["k_solve"] * 1e-3 * clocks_summary.get("sm_mhz", 1965.0) * 1e6)
+                                 if cyc.sum() > 0 and clocks_summary.get("sm_mhz") else None),
                 "phase_share": {n: round(float(c / cyc[:L.N_CYCLE_PHASES].sum()), 4) for n, c in zip(L.PHASE_NAMES[:L.N_CYCLE_PHASES], cyc)} if cyc.sum() > 0 else None,
                 "phase_counters": {n: int(c) for n, c in zip(L.PHASE_NAMES[L.N_CYCLE_PHASES:], cyc[L.N_CYCLE_PHASES:])},
                 "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
@@ -374,7 +418,7 @@ def main():
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config, "converged_frac": ok_total / Btot,
             "sqp_iters_mean": float(iters[:, 0].mean()), "qp_iters_mean": float(iters[:, 1].mean()),
-            "status_hist": np.bincount(status, minlength=5).tolist(), "clocks": clk.summary(), "e2e": e2e,
+            "status_hist": np.bincount(status, minlength=5).tolist(), "clocks": clocks_summary, "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "latency": latency,
             "target": {"solves_per_s_8gpu": 1e6, "per_gpu": 125000.0}}
     _emit(line)

@@ -102,8 +102,11 @@ class BatchedMPC:
         except Exception:
             pass
 
-    def buffers(self, B):
-        b = self._bufs.get(B)
+    def buffers(self, B, slot=0):
+        """Output / workspace tensors for a batch of B (cached).  `slot` selects an independent set: steps that use
+        different sets may be in flight on different CUDA streams at the same time (the work queue of a launch lives in
+        its workspace), which lets the tail of one batch overlap the head of the next."""
+        b = self._bufs.get((B, slot))
         if b is None:
             nbytes = C.c_size_t()
             L.check(self.lib.ftmpc_workspace_bytes(self.handle, B, C.byref(nbytes)), "ftmpc_workspace_bytes")
@@ -116,7 +119,7 @@ class BatchedMPC:
                      status=torch.empty(B, dtype=torch.int32, device=dev),
                      iters=torch.empty(B, 2, dtype=torch.int32, device=dev),
                      cost=torch.empty(B, dtype=f64, device=dev))
-            self._bufs[B] = b
+            self._bufs[(B, slot)] = b
         return b
 
     def scenario_tensors(self, scenario):
@@ -291,12 +294,14 @@ class SpiralingController:
         return thrust
 
     # ---- batched API -------------------------------------------------------------------------------------
-    def step(self, state, ref, uref=None, scenario=None, warm=False):
+    def step(self, state, ref, uref=None, scenario=None, warm=False, slot=0):
         """state [B,13] robot states, ref [B,N+1,9] reference windows -> thrust [B,16] (CUDA tensor).
-        Other outputs of the solve are in `self.last` (u0, active, status, iters, cost, z)."""
+        Other outputs of the solve are in `self.last` (u0, active, status, iters, cost, z).  Work is enqueued on the
+        current CUDA stream; steps issued with different `slot`s use independent output / workspace buffers and may
+        therefore overlap on different streams (a warm start continues the `z` of its own slot)."""
         state = torch.as_tensor(state, dtype=torch.float64, device=self.device).contiguous()
         ref = torch.as_tensor(ref, dtype=torch.float64, device=self.device).contiguous()
-        self.last = self.engine.step(state, ref, uref, scenario, warm)
+        self.last = self.engine.step(state, ref, uref, scenario, warm, out=self.engine.buffers(state.shape[0], slot))
         return self.last["thrust"]
 
 

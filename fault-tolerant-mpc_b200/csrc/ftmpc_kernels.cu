@@ -409,6 +409,8 @@ int ftmpc_workspace_bytes(ftmpc_handle h, int batch, size_t* out) {
     size_t b = align_up(h->L.stride * sizeof(double) * (size_t)grid, 256);
     const size_t need = solve_smem_bytes(h->cfg.horizon);
     if (need > h->smem_optin) b += align_up(need, 256) * (size_t)grid;
+    b += 256;      // work-queue head of the launch: it lives in the caller's workspace, so steps with different workspaces
+                   // may be in flight on different streams at the same time (pipelined batches)
     *out = b;
     return FTMPC_OK;
 }
@@ -434,16 +436,17 @@ int ftmpc_step(ftmpc_handle h, int batch, const double* state, const double* xre
     const size_t sdoubles = align_up(smem, 256) / sizeof(double);
     // the attribute is per function, not per handle: handles with different horizons share k_solve
     if (!use_global) CU(cudaFuncSetAttribute(k_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaMemsetAsync(h->d_queue, 0, sizeof(int), stream));
+    int* queue = (int*)((char*)workspace + need_ws - 256);
+    CU(cudaMemsetAsync(queue, 0, sizeof(int), stream));
     if (h->profile) {
         CU(cudaMemsetAsync(h->d_prof, 0, PH_COUNT * sizeof(long long), stream));
         CU(cudaEventRecord(h->ev[0], stream));
     }
     if (use_global)
-        k_solve<true><<<grid, FTMPC_QP_THREADS, 0, stream>>>(h->cfg, L, io, h->d_queue, gscratch, sdoubles,
+        k_solve<true><<<grid, FTMPC_QP_THREADS, 0, stream>>>(h->cfg, L, io, queue, gscratch, sdoubles,
                                                              h->profile ? h->d_prof : nullptr);
     else
-        k_solve<false><<<grid, FTMPC_QP_THREADS, smem, stream>>>(h->cfg, L, io, h->d_queue, nullptr, 0,
+        k_solve<false><<<grid, FTMPC_QP_THREADS, smem, stream>>>(h->cfg, L, io, queue, nullptr, 0,
                                                                  h->profile ? h->d_prof : nullptr);
     if (h->profile) CU(cudaEventRecord(h->ev[1], stream));
     k_alloc<<<(batch + 63) / 64, 64, 0, stream>>>(h->cfg, L, io);
