@@ -174,3 +174,57 @@ def test_infeasible_instance_is_flagged(port, golden):
                     masks[[0]], ffs[[0]], np.zeros(1, np.int32))
     assert out["status"][0] != 0
     assert np.isfinite(out["thrust"]).all() and (out["thrust"] >= 0).all() and (out["thrust"] <= 3.4 + 1e-12).all()
+
+
+def _bench_sample(port, n, offset=0, **opts):
+    """first n instances (from `offset`) of bench.py's workload through the CPU checker with ftmpc_config overrides"""
+    import bench
+    import ftmpc_import
+    ftmpc_import.load()
+    from ft_mpc_b200 import _lib as L
+    from ft_mpc_b200.controllers.spiraling_mpc import DEFAULT_Q, DEFAULT_R, hull_table_entry
+    from ft_mpc_b200.controllers.tools.spiral_parameters import SpiralParameters
+    from ft_mpc_b200.models import SystemModel
+    cells, states, scen, xref = bench.make_workload(8192, 20, 1)        # the bench batch (instance numbers refer to it)
+    model = SystemModel(0.1)
+    sp = SpiralParameters(model)
+    table = np.ascontiguousarray(np.stack([hull_table_entry(c["A"], c["b"]) for c in cells]))
+    cfg = L.make_config(20, DEFAULT_Q, DEFAULT_R, dt=model.dt, mass=model.mass, inertia=model.inertia, r=sp.r, f_virt=sp.f_virt,
+                        max_thrust=model.max_thrust, D=model.D, n_hull_sets=len(cells), **opts)
+    masks = np.zeros(len(cells), np.uint16)
+    ffs = np.zeros((len(cells), 16))
+    for k, c in enumerate(cells):
+        for i, a in c["faults"]:
+            masks[k] |= np.uint16(1 << i)
+            ffs[k, i] = a * model.max_thrust
+    s = slice(offset, offset + n)
+    return port.step(cfg, table, states[s], xref[s], None, masks[scen[s]], ffs[scen[s]], scen[s])
+
+
+def test_early_stop_in_the_quadratic_regime_changes_nothing_but_the_count(port):
+    """ftmpc_config.fast_dmax: skipping the QP that only confirms convergence saves iterations and moves the answer by less
+    than the termination tolerance (u0 1e-8 relative here; the parity bar is 1e-5), active sets unchanged"""
+    fast = _bench_sample(port, 96)
+    full = _bench_sample(port, 96, fast_dmax=0.0)
+    ok = (fast["status"] == 0) & (full["status"] == 0)
+    assert ok.sum() >= 95 and np.array_equal(fast["status"] == 0, full["status"] == 0)
+    assert fast["iters"][ok, 0].sum() < full["iters"][ok, 0].sum()
+    assert (fast["iters"][:, 0] <= full["iters"][:, 0]).all()
+    du = np.abs(fast["u0"] - full["u0"]).max(axis=1) / np.maximum(1.0, np.abs(full["u0"]).max(axis=1))
+    assert du[ok].max() < 1e-8
+    assert np.array_equal(fast["active"][ok], full["active"][ok])
+    assert np.abs(fast["thrust"] - full["thrust"])[ok].max() < 1e-7
+
+
+def test_stall_detector_only_stops_hopeless_instances(port):
+    """ftmpc_config.stall_window: instance 249 of the bench workload creeps along a flat non-convex valley (step ~2e-4,
+    objective moving by 1e-11 relative per iteration) and is given up after 30 iterations instead of 60; every instance
+    that converges without the detector still converges with it, to the same point"""
+    on = _bench_sample(port, 64, offset=224)
+    off = _bench_sample(port, 64, offset=224, stall_window=0)
+    k = 249 - 224
+    assert off["status"][k] == 1 and off["iters"][k, 0] == 60
+    assert on["status"][k] == 1 and on["iters"][k, 0] <= 30
+    conv = off["status"] == 0
+    assert conv.sum() == 63 and np.array_equal(on["status"] == 0, conv)
+    assert np.array_equal(on["iters"][conv], off["iters"][conv]) and np.array_equal(on["u0"][conv], off["u0"][conv])
