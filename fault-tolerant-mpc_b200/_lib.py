@@ -132,6 +132,7 @@ def lib() -> C.CDLL:
     L.ftmpc_num_var.argtypes = [vp]
     L.ftmpc_num_ineq.argtypes = [vp]
     L.ftmpc_step.argtypes = [vp, C.c_int, dp, dp, dp, ip, dp, ip, C.c_int, dp, dp, dp, ip, ip, ip, dp, vp, C.c_size_t, vp]
+    L.ftmpc_hull_facets.argtypes = [vp, C.c_int, ip, dp, dp, ip, ip, vp]
     L.ftmpc_rk4_jac.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp, vp]
     L.ftmpc_robot_to_center.argtypes = [vp, C.c_int, dp, dp, vp]
     L.ftmpc_terminal.argtypes = [vp, C.c_int, dp, dp, dp, dp, vp]

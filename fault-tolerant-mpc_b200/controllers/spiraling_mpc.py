@@ -156,6 +156,29 @@ class BatchedMPC:
                                           int(bool(normalize)), _ptr(nxt), C.c_void_p(stream)), "ftmpc_plant_step")
         return nxt
 
+    def hull_facets(self, fault_sets):
+        """Input-bound polytopes of arbitrary fault sets built on the device (ftmpc_hull_facets; analytic facet enumeration,
+        SURVEY.md section 8 row f-2).  fault_sets: list of [(thruster, intensity), ...].  Returns (table [n, HULL_STRIDE],
+        n_rows [n], status [n]) as CUDA tensors; the table rows are what ftmpc_create takes."""
+        n = len(fault_sets)
+        mask = np.zeros(n, np.int16)
+        ff = np.zeros((n, L.NTHR))
+        for k, fs in enumerate(fault_sets):
+            m = 0
+            for i, a in fs:
+                m |= 1 << int(i)
+                ff[k, int(i)] = float(a) * self.model.max_thrust
+            mask[k] = np.array(m, dtype=np.uint16).view(np.int16)
+        mask_d = torch.tensor(mask, device=self.device)
+        ff_d = torch.tensor(ff, dtype=torch.float64, device=self.device)
+        table = torch.empty(n, L.HULL_STRIDE, dtype=torch.float64, device=self.device)
+        nrows = torch.empty(n, dtype=torch.int32, device=self.device)
+        status = torch.empty(n, dtype=torch.int32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        L.check(self.lib.ftmpc_hull_facets(self.handle, n, _ptr(mask_d), _ptr(ff_d), _ptr(table), _ptr(nrows), _ptr(status),
+                                           C.c_void_p(stream)), "ftmpc_hull_facets")
+        return table, nrows, status
+
     def closed_loop(self, state0, trajectory, scenario=None, steps=1, noise=None, start_step=0, nominal_input=None):
         """`steps` x (ftmpc_step -> ftmpc_plant_step) entirely on the device: SimulationEnvironment.run_simulation
         (sim_env.py:77-112) for a batch.  trajectory: [T,9] device reference table (assign_trajectory), shared by

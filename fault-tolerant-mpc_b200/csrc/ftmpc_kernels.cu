@@ -18,6 +18,7 @@
 #include "ftmpc.h"
 #include "ftmpc_alloc.cuh"
 #include "ftmpc_plant.cuh"
+#include "ftmpc_hull.cuh"
 
 using namespace ftmpc;
 
@@ -452,6 +453,14 @@ int ftmpc_step(ftmpc_handle h, int batch, const double* state, const double* xre
     k_alloc<<<(batch + 63) / 64, 64, 0, stream>>>(h->cfg, L, io);
     if (h->profile) CU(cudaEventRecord(h->ev[2], stream));
     h->last_launches = 2;
+    CU(cudaGetLastError());
+    return FTMPC_OK;
+}
+
+int ftmpc_hull_facets(ftmpc_handle h, int n_sets, const uint16_t* fault_mask, const double* fault_force, double* table,
+                      int32_t* n_rows, int32_t* status, void* stream) {
+    if (!h || n_sets < 1 || !fault_mask || !fault_force || !table || !n_rows || !status) return FTMPC_ERR_ARG;
+    k_hull_facets<<<n_sets, 256, 0, (cudaStream_t)stream>>>(h->d_cfg, n_sets, fault_mask, fault_force, table, n_rows, status);
     CU(cudaGetLastError());
     return FTMPC_OK;
 }

@@ -162,6 +162,15 @@ int ftmpc_plant_step(ftmpc_handle h, int batch, const double* state, const doubl
                      const uint16_t* fault_mask, const double* fault_force, const double* noise, int normalize,
                      double* next, void* stream);
 
+/* Input-bound polytope of n_sets fault sets on the device (analytic replacement of InputBounds.calc_input_bounds,
+ *     input_bounds.py:43-76: zonotope facet enumeration instead of Qhull on 2^14 corner wrenches).
+ *     fault_mask [n_sets], fault_force [n_sets,16] (intensity * max_thrust at failed thrusters) ->
+ *     table [n_sets, FTMPC_HULL_STRIDE] in the layout ftmpc_create takes (A_h 26x6 then b_h 26, padding rows 0 / 1e30),
+ *     n_rows [n_sets], status [n_sets] (0 ok, 1 = rank-deficient fault set or too many facets: use the host routine).
+ *     Rows come in a canonical order (lexicographic on [A | -b]); the reference's order follows Qhull's rounding noise. */
+int ftmpc_hull_facets(ftmpc_handle h, int n_sets, const uint16_t* fault_mask, const double* fault_force, double* table,
+                      int32_t* n_rows, int32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

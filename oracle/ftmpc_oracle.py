@@ -9,7 +9,9 @@ PARITY: pinned for the problem definition, UNPINNED for the NLP solve.
     ft_mpc.models.sys_model / spiral_model, SpiralParameters, InputBounds and get_trajectory in the build
     container (numeric stand-in for the few CasADi calls they make) and tests/test_reference_fixtures.py
     checks every model function below against those outputs (tests/golden/ref_fixtures.npz) -- including the
-    ROW ORDER of the input-bound hull, i.e. the numbering of the constraints.  The stored terminal
+    ROW ORDER of the input-bound hull, i.e. the numbering of the constraints -- and, likewise executed from the
+    reference, SpiralingController.assign_trajectory / get_next_trajectory_part (reference window + nominal wrench)
+    and the CSV written by ControllerDebug.export.  The stored terminal
     ingredients (config/terminal.yaml) are pinned through sympy evaluation (tools/gen_terminal_data.py).
   * Unpinned: the reference ships no tests or golden vectors for solve_mpc, and casadi 3.6.7 / IPOPT and
     cvxpy 1.6.4 / OSQP are not installable here, so the optimiser outputs (KKT point, active set, thrust)

@@ -521,6 +521,52 @@ def test_closed_loop_on_circle_matches_get_control_loop(L, oracle, accel_golden)
     assert np.abs(xh.cpu().numpy()[0] - x).max() > 1e-4
 
 
+def test_hull_facets_kernel_vs_host_enumeration(L, eng6):
+    """row f-2 on the device: ftmpc_hull_facets == the host facet enumeration (itself checked against the Qhull table of the
+    reference's InputBounds in tests/test_abi_host.py) for tabulated cells, arbitrary intensities and the healthy vehicle;
+    a rank-deficient pair is flagged; a controller built from the device table solves like one built from the host table"""
+    from ft_mpc_b200 import _lib as LL
+    from ft_mpc_b200.controllers.tools.input_bounds import zonotope_facets
+    from ft_mpc_b200.models import SystemModel
+    from ft_mpc_b200.util import scenarios
+    m = SystemModel(0.1)
+    cells = scenarios.load_cells(kinds=("single", "double"))
+    rng = np.random.default_rng(5)
+    sets = [c["faults"] for c in cells[::4]] + [[]] + [[(int(i), float(a))] for i, a in zip(rng.integers(0, 12, 6), rng.uniform(0, 1, 6))]
+    sets += [[(2, 0.31), (9, 0.0)], [(12, 0.0), (13, 0.0)]]
+    table, nrows, status = eng6.hull_facets(sets)
+    torch.cuda.synchronize()
+    table, nrows, status = table.cpu().numpy(), nrows.cpu().numpy(), status.cpu().numpy()
+    assert status[-1] == 1                                          # pair (12,13): flat zonotope (Qhull raises for it)
+    for k, fs in enumerate(sets[:-1]):
+        A, b, r = zonotope_facets(m.D, m.max_thrust, fs)
+        assert status[k] == 0 and r == 6 and nrows[k] == len(b), (fs, status[k], nrows[k], len(b))
+        Ad = table[k, :LL.NH * LL.NU].reshape(LL.NH, LL.NU)
+        bd = table[k, LL.NH * LL.NU:]
+        assert np.allclose(Ad[:len(b)], A, atol=1e-12) and np.allclose(bd[:len(b)], b, atol=1e-11), fs
+        assert np.all(Ad[len(b):] == 0) and np.all(bd[len(b):] == 1e30)
+    # same KKT point from a controller that uses the device-built table (row order differs from Qhull's, the set does not)
+    N = 15
+    fs = [(10, 1.0), (11, 1.0)]
+    ref = make_engine([fs], N)
+    alt = make_engine([fs], N)
+    t2, _, st2 = alt.hull_facets([fs])
+    assert int(st2[0]) == 0
+    import ctypes as C
+    host_table = np.ascontiguousarray(t2.cpu().numpy())
+    LL.lib().ftmpc_destroy(alt.handle)
+    alt.handle = C.c_void_p()
+    LL.check(LL.lib().ftmpc_create(C.byref(alt.handle), C.byref(alt.cfg), host_table.ctypes.data_as(C.POINTER(C.c_double))), "ftmpc_create")
+    st = dev(scenarios.random_states(5, 3))
+    xr = dev(scenarios.hover_reference(5, N))
+    o1 = {k: v.clone() for k, v in ref.step(st, xr).items() if k != "ws"}
+    o2 = alt.step(st, xr)
+    torch.cuda.synchronize()
+    ok = (o1["status"] == 0) & (o2["status"] == 0)
+    assert int(ok.sum()) >= 4
+    assert torch.allclose(o1["u0"][ok], o2["u0"][ok], atol=1e-7) and torch.allclose(o1["thrust"][ok], o2["thrust"][ok], atol=1e-6)
+
+
 def test_concurrent_steps_on_two_streams(L):
     """steps issued with different buffer slots on different CUDA streams (bench.py pipelines consecutive batches that
     way: the work queue of a launch lives in its own workspace) give exactly the results of the same steps run one
