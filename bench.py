@@ -9,11 +9,16 @@ shard is fixed at 65,536 / 8 = 8,192 instances): Monte-Carlo fault scenarios -- 
 double thruster failures (dead / stuck-on), seeded random initial robot states, hover reference, horizon
 N = 20, cold start.  One "step" = one ftmpc_step over the rank's shard = B complete get_control equivalents
 (state -> SQP on the reference NLP -> 16 thrusts).  Only converged instances (status 0) count as solves.
+Consecutive steps are independent batches; they are enqueued on `--streams` (default 2) alternating CUDA streams, each
+with its own output / workspace buffers, so the SMs that run out of instances at the tail of one launch start on the next
+batch (`--streams 1`: strictly serial steps).  The timing events sit on the main stream, which all side streams wait
+for at the start and which waits for all of them at the end.
 
 One JSON line on stdout (rank 0).  `value` is device-resident throughput, `e2e` goes through the public
 SpiralingController.step with pinned HOST buffers (H2D of the inputs and D2H of thrust/status inside the timed
-region), `roofline` compares the dominant kernel with the measured FP64 FMA peak of the device (the solve is
-FP64-compute/latency bound) and reports the HBM side too, `cpu_baseline` / `--impl reference`
+region), `roofline` compares the dominant kernel -- timed in one more step run alone, with the in-kernel phase profile
+on -- with the measured FP64 FMA peak of the device (the solve is FP64-compute/latency bound) and reports
+the HBM side too, `cpu_baseline` / `--impl reference`
 time the same algorithm on the host cores (oracle/cpu_port -- the reference's own casadi/IPOPT stack is not
 installable offline).
 """
