@@ -406,11 +406,12 @@ def test_qp_warm_start_gives_identical_results(L, golden):
         assert np.abs(out1["u0"][j] - u0).max() <= 1e-5 * max(1.0, np.abs(u0).max())
 
 
-def test_long_horizon_global_scratch_path(L, built):
+@pytest.mark.parametrize("N,B", [(30, 6), (100, 3)])
+def test_long_horizon_global_scratch_path(L, built, N, B):
     """N = 30: the QP scratch (275 KB) no longer fits in shared memory -> k_solve<true> keeps it in a per-CTA global
-    slice and the generic condensing / factorisation routines run; results must agree with the CPU port"""
+    slice and the generic condensing / factorisation routines run; results must agree with the CPU port.
+    N = 100 is the horizon of BASELINE configs[4] (600 decision variables, 2.9 MB of scratch per CTA)."""
     from ft_mpc_b200.util import scenarios
-    N, B = 30, 6
     cells = scenarios.load_cells(kinds=("single",))[:3]
     eng = make_engine(cells, N)
     st = scenarios.random_states(B, 21)
