@@ -434,20 +434,7 @@ FT_HD int gi_solve(Blk& blk, const Cons& cons, const GiWork& w, int nv, int ne, 
 #if defined(__CUDACC__)
 // Register-blocked row kernels.  A CTA runs 8 warps (2 per scheduler), so a dependent load -> FMA -> store chain
 // is bound by latency; these load eight operands of each stream before touching them.
-__device__ __forceinline__ double dot_ilp(const double* __restrict__ a, const double* __restrict__ b, int k0, int k1) {
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int k = k0;
-    for (; k + 7 < k1; k += 8) {
-        double x[8], y[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { x[j] = a[k + j]; y[j] = b[k + j]; }
-        s0 += x[0] * y[0]; s1 += x[1] * y[1]; s2 += x[2] * y[2]; s3 += x[3] * y[3];
-        s0 += x[4] * y[4]; s1 += x[5] * y[5]; s2 += x[6] * y[6]; s3 += x[7] * y[7];
-    }
-    for (; k < k1; ++k) s0 += a[k] * b[k];
-    return (s0 + s1) + (s2 + s3);
-}
-// The same two row kernels for a LANE PAIR per row: lane `part` of the pair owns the columns of its parity (k, k + 2, ...).
+// Row kernels for a LANE PAIR per row: lane `part` of the pair owns the columns of its parity (k, k + 2, ...).
 // With rows 2 apart inside a half-warp (see gi_pair_row) the 16 lanes of a shared-memory phase hit 16 distinct 8-byte
 // banks for any odd row stride, so the pair split costs no extra wavefronts, every thread of the block works, and the
 // dependent chain per thread is half as long.
@@ -492,18 +479,6 @@ __device__ __forceinline__ void axpy_stride2(double* __restrict__ e, const doubl
 __device__ __forceinline__ int gi_pair_row(int tid) {
     const int hw = tid >> 4, j = (tid & 15) >> 1;
     return ((hw >> 1) << 4) + (hw & 1) + (j << 1);
-}
-// e[k] -= wv * d[k], k in [k0, k1)
-__device__ __forceinline__ void axpy_ilp(double* __restrict__ e, const double* __restrict__ d, double wv, int k0, int k1) {
-    int k = k0;
-    for (; k + 7 < k1; k += 8) {
-        double x[8], y[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { x[j] = e[k + j]; y[j] = d[k + j]; }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) e[k + j] = x[j] - wv * y[j];
-    }
-    for (; k < k1; ++k) e[k] -= wv * d[k];
 }
 #endif
 

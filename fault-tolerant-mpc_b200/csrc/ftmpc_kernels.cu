@@ -32,7 +32,6 @@ struct ftmpc_ctx {
     ftmpc_config cfg;          // host copy
     ftmpc_config* d_cfg;       // device copy
     double* d_hull;            // device hull table
-    int* d_queue;              // device work-queue head
     long long* d_prof;         // per-phase cycle accumulators (PH_COUNT) of the last profiled step
     int device, num_sms;
     size_t smem_optin;
@@ -345,7 +344,6 @@ int ftmpc_create(ftmpc_handle* out, const ftmpc_config* cfg, const double* hull_
     const size_t hb = (size_t)cfg->n_hull_sets * FTMPC_HULL_STRIDE * sizeof(double);
     CU(cudaMalloc(&h->d_hull, hb));
     CU(cudaMemcpy(h->d_hull, hull_table, hb, cudaMemcpyHostToDevice));
-    CU(cudaMalloc(&h->d_queue, sizeof(int)));
     CU(cudaMalloc(&h->d_prof, PH_COUNT * sizeof(long long)));
     CU(cudaMemset(h->d_prof, 0, PH_COUNT * sizeof(long long)));
     for (int i = 0; i < 3; ++i) CU(cudaEventCreate(&h->ev[i]));
@@ -385,7 +383,6 @@ void ftmpc_destroy(ftmpc_handle h) {
     for (int i = 0; i < 3; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     cudaFree(h->d_cfg);
     cudaFree(h->d_hull);
-    cudaFree(h->d_queue);
     cudaFree(h->d_prof);
     delete h;
 }

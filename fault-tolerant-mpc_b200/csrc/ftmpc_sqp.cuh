@@ -329,41 +329,6 @@ __device__ __forceinline__ LsScratch ls_carve(double* buf, int N) {
     return s;
 }
 
-// forward rollout at U + alpha d (all operands in shared memory): states -> Xs, stage wrenches -> Ws,
-// returns the running cost (the terminal cost is added term-parallel afterwards)
-__device__ __noinline__ double rollout_states(const ftmpc_config& cfg, int N, const double* xref, const double* uref,
-                                              const double* U, const double* d, double alpha, const double* x0,
-                                              double* Xs, double* Ws, double* Uconv_s = nullptr, double* Uconv_g = nullptr) {
-    const DynConsts k = dyn_consts(cfg);
-    double x[FTMPC_NX], xn[FTMPC_NX], u[FTMPC_NU], Wr[FTMPC_NU], rho[FTMPC_NU] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int i = 0; i < FTMPC_NX; ++i) { x[i] = x0[i]; Xs[i] = x[i]; }
-    double f = 0.0;
-    for (int t = 0; t < N; ++t) {
-#pragma unroll
-        for (int j = 0; j < FTMPC_NU; ++j) u[j] = U[t * FTMPC_NU + j] + alpha * d[t * FTMPC_NU + j];
-        if (uref) {                                   // U holds u~ = u + rho(q_t), see FTMPC_CQ
-            nominal_rot(x + 9, uref + t * FTMPC_NU, rho);
-            if (Uconv_s) {                            // first rollout: U still holds u
-#pragma unroll
-                for (int j = 0; j < FTMPC_NU; ++j) { u[j] += rho[j]; Uconv_s[t * FTMPC_NU + j] = u[j]; Uconv_g[t * FTMPC_NU + j] = u[j]; }
-            }
-        }
-        stage_wrench(cfg, u, nullptr, x + 9, Wr);
-#pragma unroll
-        for (int j = 0; j < FTMPC_NE; ++j) {
-            const double e = x[j] - xref[t * FTMPC_NE + j];
-            f += cfg.Q[j] * e * e;
-        }
-#pragma unroll
-        for (int j = 0; j < FTMPC_NU; ++j) { f += cfg.R[j] * (u[j] - rho[j]) * (u[j] - rho[j]); Ws[t * FTMPC_NU + j] = Wr[j]; }
-        rk4_step(k, x, Wr, xn);
-#pragma unroll
-        for (int i = 0; i < FTMPC_NX; ++i) { x[i] = xn[i]; Xs[(t + 1) * FTMPC_NX + i] = xn[i]; }
-    }
-    return f;
-}
-
 // ---- split rollout --------------------------------------------------------------------------------------
 // The attitude (omega, q) of the centre state evolves on its own (torque in, no dependence on p, v), and the translation
 // is a quadrature over the attitude stages:  v_{t+1} = v_t + dv_t,  p_{t+1} = p_t + dt v_t + cp_t  with
