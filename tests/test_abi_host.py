@@ -225,3 +225,19 @@ def test_analytic_zonotope_facets_match_qhull_table(ft):
     assert r == 5 and np.isfinite(A).all()
     flat = [(i, j) for i in range(len(A)) for j in range(i) if np.allclose(A[i], -A[j], atol=1e-9) and abs(b[i] + b[j]) < 1e-9]
     assert len(flat) == 1
+
+
+def test_bench_reference_arm_prints_one_json_line(built):
+    """`bench.py --impl reference` (the driver's CPU arm): exactly one line on stdout, the contract's keys, no GPU needed"""
+    import json
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-sample", "8"], capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "solves/s" and d["value"] > 0 and d["dtype"] == "f64"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
