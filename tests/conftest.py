@@ -63,3 +63,10 @@ def accel_golden():
     """oracle KKT points for accelerating (circle) references: non-zero nominal wrench (tools/gen_golden.py --accel)"""
     import numpy as np
     return np.load(ROOT / "tests" / "golden" / "nlp_cases_accel.npz")
+
+
+@pytest.fixture(scope="session")
+def bench_golden():
+    """oracle KKT points of 32 instances of bench.py's own workload (BASELINE configs[3]; tools/gen_golden.py --more)"""
+    import numpy as np
+    return np.load(ROOT / "tests" / "golden" / "nlp_cases_bench.npz")

@@ -148,6 +148,26 @@ def test_accelerating_reference_vs_golden(port, accel_golden, N):
         assert np.allclose(out["thrust"][j], g["thrust"][k], atol=2e-5), g["name"][k]
 
 
+def test_bench_workload_instances_vs_golden(port, bench_golden):
+    """32 instances of the bench workload (single / double faults, dead / stuck-on): the solver that bench.py times lands on
+    the oracle's KKT point for every one of them"""
+    g = bench_golden
+    N = 20
+    ks = H.cases_with_horizon(g, N)
+    assert len(ks) == 32
+    sets, scen = H.gather_cases(g, ks)
+    cfg, table, masks, ffs, _ = H.host_tables(sets, N)
+    out = port.step(cfg, table, g["x0"][ks], g["xref"][ks][:, :N + 1], None, masks[scen], ffs[scen], scen)
+    assert (out["status"] == 0).all(), out["status"]
+    nbits = 26 * N + 72
+    for j, k in enumerate(ks):
+        u0 = g["U"][k, 0]
+        assert out["cost"][j] == pytest.approx(g["f"][k], rel=1e-9), g["name"][k]
+        assert np.abs(out["u0"][j] - u0).max() <= 1e-5 * max(1.0, np.abs(u0).max()), g["name"][k]
+        assert H.active_bits(out["active"][j], nbits) == H.active_bits(g["active"][k], nbits), g["name"][k]
+        assert np.allclose(out["thrust"][j], g["thrust"][k], atol=2e-5), g["name"][k]
+
+
 def test_warm_start_closed_loop_vs_golden(port, oracle, golden):
     """warm start = previous solution shifted one stage (spiraling_mpc.py:324-331); closed-loop steps 1..4"""
     N = 15

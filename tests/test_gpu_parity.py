@@ -285,6 +285,24 @@ def test_step_accelerating_reference_vs_golden(L, oracle, accel_golden, N):
 
 
 @pytest.mark.gpu
+def test_step_on_bench_workload_vs_golden(L, oracle, bench_golden):
+    """32 instances of bench.py's own workload against the oracle: u0 1e-5 relative, active sets bit-exact, thrust 2e-5"""
+    g = bench_golden
+    N = 20
+    ks = H.cases_with_horizon(g, N)
+    assert len(ks) == 32
+    eng, out = run_cases(g, ks, N)
+    assert (out["status"] == 0).all(), out["status"]
+    nbits = 26 * N + 72
+    for j, k in enumerate(ks):
+        name, u0 = g["name"][k], g["U"][k, 0]
+        assert out["cost"][j] == pytest.approx(g["f"][k], rel=1e-9), name
+        assert np.abs(out["u0"][j] - u0).max() <= 1e-5 * max(1.0, np.abs(u0).max()), name
+        assert H.active_bits(out["active"][j].view(np.uint32), nbits) == H.active_bits(g["active"][k], nbits), name
+        assert np.allclose(out["thrust"][j], g["thrust"][k], atol=2e-5), name
+
+
+@pytest.mark.gpu
 def test_get_control_tracks_circle_reference(L, oracle, accel_golden):
     """the reference-facing call with an accelerating trajectory: load_trajectory("generate_circle") + get_control(x, t)
     reproduces the oracle's thrust for the golden window (circle0_N15 starts at step 5, t = 0.5), and the debug

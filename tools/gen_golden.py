@@ -165,7 +165,35 @@ def main_accel():
     print("wrote", dst, "cases", len(cases), "max |uref|", np.abs(out["uref"]).max())
 
 
-if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "--accel":
+def make_more_cases():
+    """(7) a wider sample of the bench workload itself (BASELINE configs[3]): 32 instances of bench.make_workload at N = 20,
+    i.e. single and double faults, dead and stuck-on thrusters, the bench's state distribution -- cold start, hover."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    cells, states, scen, xref = bench.make_workload(8192, 20, 1)
+    cases = []
+    for k in list(range(0, 4096, 128)):
+        cases.append(dict(name=f"bench_{k}", faults=cells[scen[k]]["faults"], N=20, x0=states[k], xref=xref[k], uref=np.zeros((21, 6))))
+    return cases
+
+
+def main_more():
+    cases = make_more_cases()
+    with Pool(7) as p:
+        results = {}
+        for name, res, dt in p.imap_unordered(solve_case, cases):
+            results[name] = res
+            print(f"{name}: f={res['f']:.6f} kkt={res['kkt_stat']:.1e} viol={res['kkt_viol']:.1e} polished={res['polished']} "
+                  f"nact={len(res['active'])} {dt:.0f}s", flush=True)
+    out = pack(cases, [results[c["name"]] for c in cases])
+    dst = ROOT / "tests" / "golden" / "nlp_cases_bench.npz"
+    np.savez_compressed(dst, **out)
+    print("wrote", dst, "cases", len(cases), "with KKT point", int((out["kkt_viol"] < 1e-8).sum()))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "--more":
+    main_more()
+elif __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "--accel":
     main_accel()
 elif __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1].startswith("--")):
     main()
