@@ -117,6 +117,25 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # CPU arm (reference arm and cpu_baseline): the same NLP solved on the host cores by oracle/cpu_port
 # ---------------------------------------------------------------------------------------------------------
+def cpu_info() -> dict:
+    model = None
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    flags = None
+    try:
+        for ln in open(ROOT / "oracle" / "Makefile"):
+            if "$(CXX)" in ln and "-O" in ln:
+                flags = " ".join(w for w in ln.split() if w.startswith("-") and not w.startswith("-I") and w not in ("-x", "-o"))
+    except OSError:
+        pass
+    return {"cpu_model": model, "compiler_flags": flags, "host_cores": os.cpu_count()}
+
+
 def cpu_solve_rate(N: int, cells, states, scen, xref, sample: int, steps: int, warmup: int):
     """Times `steps` passes over the first `sample` instances with all host threads.  Returns (solves/s, ms/step, cores, ok_frac)."""
     sys.path.insert(0, str(ROOT / "tests"))
@@ -190,16 +209,18 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        sample = a.cpu_sample or 2048
-        cells, states, scen, xref = make_workload(sample, N)
+        sample = min(a.cpu_sample or 2048, a.batch)
+        cells, states, scen, xref = make_workload(a.batch * world, N)       # the batch the B200 arm solves (rank 0's shard first)
         rate, ms, cores, okf = cpu_solve_rate(N, cells, states, scen, xref, sample, a.steps, a.warmup)
+        config["reference_sample_per_step"] = sample
         line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": f"{sample} instances of the workload per step, all {cores} host threads (OpenMP, one instance per thread); "
+                                 "sample": f"the first {sample} instances of the batch the B200 arm solves (same seed, same order), every step, all "
+                                           f"{cores} host threads (OpenMP, one instance per thread); "
                                            "the reference's casadi/IPOPT solve is not installable offline, this is the C++ port of the same SQP "
-                                           "on the reference NLP (oracle/cpu_port)", "converged_frac": okf},
+                                           "on the reference NLP (oracle/cpu_port)", "converged_frac": okf, **cpu_info()},
                 "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         _emit(line)
         return 0
@@ -265,6 +286,7 @@ def main():
                 stream.wait_event(ev)
 
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ok_acc = torch.zeros(S, dtype=torch.int64, device=devs)       # converged instances of EVERY timed step, per stream slot
     with ClockSampler(local) as clk:
         sync_all()
         e0.record(stream)
@@ -273,6 +295,7 @@ def main():
         for i in range(a.steps):
             with torch.cuda.stream(side[i % S]):
                 out = eng.step(st_d, xr_d, scenario=sc_t, out=eng.buffers(hi - lo, i % S))
+                ok_acc[i % S] += (out["status"] == 0).sum()
             launches += eng.lib.ftmpc_last_launches(eng.handle)
         fan_in()
         e1.record(stream)
@@ -289,7 +312,7 @@ def main():
     L.check(eng.lib.ftmpc_profile_enable(eng.handle, 0))
     status = out["status"].cpu().numpy()
     iters = out["iters"].cpu().numpy()
-    ok_local = int((status == 0).sum())
+    ok_local = int(ok_acc.sum().item())                           # summed over all timed steps
     t = torch.tensor([ms_total, float(ok_local)], dtype=f64, device=devs)
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -297,7 +320,7 @@ def main():
         ms_total, ok_total = float(tmax[0]), float(tsum[1])
     else:
         ok_total = float(ok_local)
-    value = ok_total * a.steps / (ms_total * 1e-3)
+    value = ok_total / (ms_total * 1e-3)
 
     # ---- the one collective of the path: all-gather of the per-instance result records (outside the timed solve)
     rec = pack_results(st_d, out["cost"], out["status"], torch.ones(hi - lo, dtype=torch.int32, device=devs))
@@ -317,10 +340,14 @@ def main():
                                scenario=sc_h.to(devs, non_blocking=True), slot=slot)
             th_h[slot].copy_(thrust, non_blocking=True)
             stt_h[slot].copy_(ctrl.last["status"], non_blocking=True)
+            ok_e2e_acc[slot] += (ctrl.last["status"] == 0).sum()
 
     e2e_steps = a.steps
+    ok_e2e_acc = torch.zeros(S, dtype=torch.int64, device=devs)
     for i in range(S):
         e2e_step(i)
+    sync_all()
+    ok_e2e_acc.zero_()
     sync_all()
     e0.record(stream)
     fan_out(e0)
@@ -330,13 +357,13 @@ def main():
     e1.record(stream)
     sync_all()
     ms_e2e = e0.elapsed_time(e1)
-    ok_e2e = float((stt_h[(e2e_steps - 1) % S].numpy() == 0).sum())
+    ok_e2e = float(ok_e2e_acc.sum().item())                       # all timed steps
     te = torch.tensor([ms_e2e, ok_e2e], dtype=f64, device=devs)
     if world > 1:
         temax = te.clone(); dist.all_reduce(temax, op=dist.ReduceOp.MAX)
         tesum = te.clone(); dist.all_reduce(tesum, op=dist.ReduceOp.SUM)
         ms_e2e, ok_e2e = float(temax[0]), float(tesum[1])
-    e2e = {"value": ok_e2e * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT,
+    e2e = {"value": ok_e2e / (ms_e2e * 1e-3), "unit": UNIT,
            "h2d_bytes_per_step": int((st_h.nbytes + xr_h.nbytes + sc_h.nbytes) * world),
            "d2h_bytes_per_step": int((th_h[0].nbytes + stt_h[0].nbytes) * world), "steps": e2e_steps,
            "api": "SpiralingController.step(state, ref, scenario=..., slot=i) -> thrust (pinned host tensors in / out), step i on stream i % S"}
@@ -397,15 +424,28 @@ def main():
         c1.load_trajectory("hover", 30)
         from scipy.spatial.transform import Rotation
         x = np.concatenate([[1, 0, 1], [1, .5, 0], Rotation.from_euler("zyx", [50, 30, -10], degrees=True).as_quat(), [.3, .8, -.1]])
-        lat = []
-        for k in range(60):
+        lat, kms_l, its = [], [], []
+        kbuf = (C.c_double * 2)()
+        for k in range(300):                                       # the whole demo horizon (reactive.yaml:2,5; sim_env.py:109)
             t0 = time.perf_counter()
-            u = c1.get_control(x, 0.1 * k)
+            u = c1.get_control(x, 0.1 * k + 1e-9)
             lat.append((time.perf_counter() - t0) * 1e3)
+            its.append(c1.last_iters[0])
             x = m1.normalize_quaternion(m1.dynamics(x, u))
-        lat = np.array(lat[5:])
-        latency = {"p50_ms": float(np.percentile(lat, 50)), "p95_ms": float(np.percentile(lat, 95)), "steps": len(lat),
-                   "workload": "examples/sim.py default scenario, N=15, closed loop, warm start, get_control(x,t) host call"}
+        # device time of k_solve alone for the same loop (events inside ftmpc_step; separate pass so that the event
+        # bookkeeping does not sit in the latency numbers above)
+        L.check(c1.engine.lib.ftmpc_profile_enable(c1.engine.handle, 1))
+        for k in range(300, 340):
+            u = c1.get_control(x, 0.1 * (k % 250) + 1e-9)
+            L.check(c1.engine.lib.ftmpc_profile_read(c1.engine.handle, C.c_void_p(torch.cuda.current_stream().cuda_stream), kbuf, None, 0))
+            kms_l.append(float(kbuf[0]) + float(kbuf[1]))
+            x = m1.normalize_quaternion(m1.dynamics(x, u))
+        L.check(c1.engine.lib.ftmpc_profile_enable(c1.engine.handle, 0))
+        cold, lat = lat[0], np.array(lat[1:])
+        latency = {"p50_ms": float(np.percentile(lat, 50)), "p95_ms": float(np.percentile(lat, 95)), "cold_first_ms": float(cold),
+                   "steps": len(lat), "sqp_iters_mean": float(np.mean(its[1:])), "kernel_p50_ms": float(np.percentile(kms_l, 50)),
+                   "workload": "examples/sim.py default scenario, N=15, closed loop over the 300-step demo horizon, warm start, "
+                               "get_control(x,t) host call (pinned H2D of the state, one pinned D2H of the result record)"}
 
     # ---- CPU baseline (same algorithm on the host cores), bounded sample
     cpu = None
@@ -417,13 +457,13 @@ def main():
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"first {sample} instances of the same batch, one pass, OpenMP over instances ({cores} threads), "
                          "C++ port of the same SQP on the reference NLP (oracle/cpu_port); the reference's casadi/IPOPT stack is not installable offline",
-               "converged_frac": okf}
+               "converged_frac": okf, **cpu_info()}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W,
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": config, "converged_frac": ok_total / Btot,
+            "data": "synthetic", "config": config, "converged_frac": ok_total / (Btot * a.steps),
             "sqp_iters_mean": float(iters[:, 0].mean()), "qp_iters_mean": float(iters[:, 1].mean()),
-            "status_hist": np.bincount(status, minlength=5).tolist(), "clocks": clocks_summary, "e2e": e2e,
+            "status_hist": np.bincount(status, minlength=6).tolist(), "clocks": clocks_summary, "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "latency": latency,
             "target": {"solves_per_s_8gpu": 1e6, "per_gpu": 125000.0}}
     _emit(line)

@@ -24,7 +24,7 @@ PHASE_NAMES = ['ls', 'lin', 'condense', 'cholesky', 'inverse', 'qp_setup', 'qp_a
                'n_instances', 'n_sqp_iter', 'n_condense', 'n_chol_fail', 'n_qp', 'n_gi_iter', 'n_gi_drop', 'n_ls_backtrack', 'n_gi_warm_ok', 'n_gi_warm_miss']
 N_PHASES = len(PHASE_NAMES)
 N_CYCLE_PHASES = 29
-ST_OK, ST_MAXITER, ST_QPFAIL, ST_INFEASIBLE, ST_ALLOC = 0, 1, 2, 3, 4
+ST_OK, ST_MAXITER, ST_QPFAIL, ST_INFEASIBLE, ST_ALLOC, ST_BADINPUT = 0, 1, 2, 3, 4, 5
 
 _PKG = Path(__file__).resolve().parent
 # FTMPC_LIB selects another build of the same library (A/B experiments on the GPU box); no fallback either way
@@ -110,6 +110,10 @@ def make_config(horizon: int, Q, R, *, dt: float, mass: float, inertia, r, f_vir
     return cfg
 
 
+# keyword names of make_config that tune the solver (accepted in params["solver_opts"] / params["ftmpc_opts"])
+SOLVER_OPTION_NAMES = ("max_sqp_iter", "max_qp_iter", "stall_window", "sqp_tol", "qp_tol", "feas_tol", "act_tol", "rho_slack",
+                       "clip_tol", "theta_first", "theta_growth", "blend_dmax", "warm_qp", "fast_dmax")
+
 _lib = None
 
 
@@ -139,6 +143,11 @@ def lib() -> C.CDLL:
     L.ftmpc_condense.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp, dp, dp, C.c_double, dp, dp, vp]
     L.ftmpc_qp_solve.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp, dp, ip, ip, dp, dp, dp, dp, ip, vp]
     L.ftmpc_allocate.argtypes = [vp, C.c_int, dp, dp, dp, ip, vp]
+    L.ftmpc_closed_loop.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, ip, dp, ip, dp, C.c_int, dp, dp, dp, ip, ip,
+                                    ip, dp, dp, ip, vp, C.c_size_t, vp]
+    L.ftmpc_closed_loop.restype = C.c_int
+    L.ftmpc_clip.argtypes = [vp, C.c_int, ip, dp, dp, ip, vp]
+    L.ftmpc_clip.restype = C.c_int
     L.ftmpc_plant_step.argtypes = [vp, C.c_int, dp, dp, ip, dp, dp, C.c_int, dp, vp]
     L.ftmpc_profile_enable.argtypes = [vp, C.c_int]
     L.ftmpc_profile_read.argtypes = [vp, vp, dp, ip, C.c_int]

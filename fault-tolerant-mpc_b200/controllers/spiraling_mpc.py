@@ -93,6 +93,7 @@ class BatchedMPC:
         self._fault_force_dev = torch.tensor(np.stack(self.fault_force_tab), dtype=torch.float64, device=self.device)
         self._mask_dev = torch.tensor(np.array(self.mask_tab, dtype=np.int64), device=self.device)
         self._bufs = {}
+        self._scen0 = {}
 
     def __del__(self):
         try:
@@ -122,6 +123,14 @@ class BatchedMPC:
             self._bufs[(B, slot)] = b
         return b
 
+    def _default_scenario(self, B):
+        """(mask, fault_force, hull_idx) of scenario 0 for every instance, built once per batch size"""
+        sc = self._scen0.get(B)
+        if sc is None:
+            sc = self.scenario_tensors(torch.zeros(B, dtype=torch.int64, device=self.device))
+            self._scen0[B] = sc
+        return sc
+
     def scenario_tensors(self, scenario):
         """scenario [B] int (index into fault_sets) -> (mask uint16 [B], fault_force [B,16], hull_idx int32 [B])"""
         scenario = scenario.to(self.device, torch.int64)
@@ -133,7 +142,7 @@ class BatchedMPC:
         B = state.shape[0]
         b = out or self.buffers(B)
         if scenario is None:
-            scenario = torch.zeros(B, dtype=torch.int64, device=self.device)
+            scenario = self._default_scenario(B)
         mask, ff, hidx = scenario if isinstance(scenario, tuple) else self.scenario_tensors(scenario)
         assert state.shape == (B, L.NX) and xref.shape == (B, self.N + 1, L.NE)
         assert state.is_contiguous() and xref.is_contiguous() and state.dtype == torch.float64
@@ -187,22 +196,27 @@ class BatchedMPC:
         (the reference draws unseeded U(0,1e-3), sim_env.py:88-91).  Warm start from the second step on (spiraling_mpc.py:324-331).
         Returns (final_state [B,13], cumulative optimal cost [B], worst status [B], steps done [B])."""
         B = state0.shape[0]
-        if scenario is None:
-            scenario = torch.zeros(B, dtype=torch.int64, device=self.device)
-        sc = scenario if isinstance(scenario, tuple) else self.scenario_tensors(scenario)
-        state = state0.clone()
-        cost = torch.zeros(B, dtype=torch.float64, device=self.device)
-        worst = torch.zeros(B, dtype=torch.int32, device=self.device)
-        for k in range(steps):
-            w = trajectory[start_step + k: start_step + k + self.N + 1]
-            xref = w.unsqueeze(0).expand(B, -1, -1).contiguous()
-            uref = None
-            if nominal_input is not None:
-                uref = nominal_input[start_step + k: start_step + k + self.N + 1].unsqueeze(0).expand(B, -1, -1).contiguous()
-            out = self.step(state, xref, uref, scenario=sc, warm=k > 0)
-            cost += out["cost"]
-            worst = torch.maximum(worst, out["status"])
-            state = self.plant_step(state, out["thrust"], sc, noise[k] if noise is not None else None, True)
+        sc = self._default_scenario(B) if scenario is None else (scenario if isinstance(scenario, tuple) else self.scenario_tensors(scenario))
+        mask, ff, hidx = sc
+        b = self.buffers(B)
+        state = state0.clone().contiguous()
+        trajectory = trajectory.contiguous()
+        assert trajectory.dim() == 2 and trajectory.shape[1] == L.NE and trajectory.dtype == torch.float64
+        if nominal_input is not None:
+            nominal_input = nominal_input.contiguous()
+            assert nominal_input.shape == (trajectory.shape[0], L.NU)
+        if noise is not None:
+            noise = noise.contiguous()
+            assert noise.shape[0] >= steps and noise.shape[1:] == (B, L.NX)
+        cost = torch.empty(B, dtype=torch.float64, device=self.device)
+        worst = torch.empty(B, dtype=torch.int32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        # one native call enqueues all steps (3 launches each) on the stream: no Python in the loop, no per-step window copies
+        L.check(self.lib.ftmpc_closed_loop(self.handle, B, int(steps), int(start_step), int(trajectory.shape[0]), _ptr(state),
+                                           _ptr(trajectory), _ptr(nominal_input), _ptr(mask), _ptr(ff), _ptr(hidx), _ptr(noise), 0,
+                                           _ptr(b["z"]), _ptr(b["thrust"]), _ptr(b["u0"]), _ptr(b["active"]), _ptr(b["status"]),
+                                           _ptr(b["iters"]), _ptr(b["cost"]), _ptr(cost), _ptr(worst), _ptr(b["ws"]),
+                                           b["ws"].numel(), C.c_void_p(stream)), "ftmpc_closed_loop")
         done = torch.full((B,), steps, dtype=torch.int32, device=self.device)
         return state, cost, worst, done
 
@@ -212,7 +226,9 @@ class _PlantStepper:
 
     def __init__(self, model):
         faults = [(bt.index, bt.intensity) for bt in model.broken_thrusters]
-        self.eng = BatchedMPC(model, 1, DEFAULT_Q, DEFAULT_R, [faults])
+        # the plant step reads only the model constants and the fault record of the handle: a placeholder hull entry keeps
+        # the construction free of the Qhull pass (input_bounds.py:43-76) a controller would need
+        self.eng = BatchedMPC(model, 1, DEFAULT_Q, DEFAULT_R, [{"faults": faults, "A": np.zeros((1, L.NU)), "b": np.ones(1)}])
 
     def __call__(self, x, u):
         dev = self.eng.device
@@ -238,7 +254,9 @@ class SpiralingController:
         params.setdefault("param_set", "P1")
         params.setdefault(params["param_set"], {"Q": DEFAULT_Q, "R": DEFAULT_R})
         if params.get("xub") is not None or params.get("xlb") is not None:
-            raise NotImplementedError("state bounds (xub/xlb) are not configured by the reference and not supported")
+            raise NotImplementedError("state bounds params['xub'] / params['xlb'] (spiraling_mpc.py:129-130, 180-185) are refused: "
+                                      "the reference's configuration never sets them and the reduced-space SQP has no "
+                                      "state-bound rows (DESIGN.md section 7)")
         self.params = params
         self.Nt = params["horizon"]
         ps = params[params["param_set"]]
@@ -252,7 +270,18 @@ class SpiralingController:
                 fault_sets = [[(i, float(inten[i])) for i in range(16) if (int(fault_mask) >> i) & 1]]
             else:
                 fault_sets = [[(bt.index, bt.intensity) for bt in model.broken_thrusters]]
-        opts = dict(params.get("solver_opts") or {})
+        # params["solver_opts"] carries IPOPT / nlpsol options in the reference (spiraling_mpc.py:227-229, e.g.
+        # "ipopt.max_iter"); they have no meaning for this solver and are ignored with a note, except the ones that map:
+        # ipopt.max_iter -> max_sqp_iter.  Native options go in params["ftmpc_opts"] (or as keyword arguments).
+        opts = {}
+        for key, val in dict(params.get("solver_opts") or {}).items():
+            if key == "ipopt.max_iter":
+                opts["max_sqp_iter"] = int(val)
+            elif key in L.SOLVER_OPTION_NAMES:
+                opts[key] = val
+            else:
+                self.ignored_solver_opts = getattr(self, "ignored_solver_opts", []) + [key]
+        opts.update(dict(params.get("ftmpc_opts") or {}))
         opts.update(solver_opts)
         self.engine = BatchedMPC(model, self.Nt, ps["Q"], ps["R"], fault_sets, device=device, **opts)
         self.device = self.engine.device
@@ -296,19 +325,51 @@ class SpiralingController:
         return w.unsqueeze(0).expand(batch, -1, -1).contiguous()
 
     # ---- single-instance reference API ------------------------------------------ spiraling_mpc.py:288-317
+    def _single_io(self):
+        """Staging of the B = 1 call: a pinned host state, and ONE device record [thrust 16 | u0 6 | cost 1 | status, sqp
+        iterations, qp iterations (int32) + pad] that the kernels write in place and that comes back in one pinned copy."""
+        io = getattr(self, "_io1", None)
+        if io is None:
+            dev = self.device
+            rec = torch.zeros(25, dtype=torch.float64, device=dev)          # 23 doubles + 4 int32
+            ints = rec[23:25].view(torch.int32)
+            eng = self.engine
+            nbytes = C.c_size_t()
+            L.check(eng.lib.ftmpc_workspace_bytes(eng.handle, 1, C.byref(nbytes)), "ftmpc_workspace_bytes")
+            out = dict(ws=torch.empty(nbytes.value, dtype=torch.uint8, device=dev),
+                       z=torch.zeros(1, eng.nz, dtype=torch.float64, device=dev),
+                       thrust=rec[0:16].view(1, 16), u0=rec[16:22].view(1, 6), cost=rec[22:23],
+                       status=ints[0:1], iters=ints[1:3].view(1, 2),
+                       active=torch.empty(1, (eng.mc + 31) // 32, dtype=torch.int32, device=dev))
+            io = dict(out=out, rec=rec, rec_host=torch.zeros(25, dtype=torch.float64).pin_memory(),
+                      state_host=torch.zeros(1, 13, dtype=torch.float64).pin_memory(),
+                      state=torch.zeros(1, 13, dtype=torch.float64, device=dev))
+            self._io1 = io
+        return io
+
     def get_control(self, x0, t):
-        x0 = np.asarray(x0, float).reshape(1, 13)
-        state = torch.tensor(x0, dtype=torch.float64, device=self.device)
+        io = self._single_io()
+        x0 = np.asarray(x0, float).reshape(13)
+        io["state_host"].numpy()[0] = x0
+        io["state"].copy_(io["state_host"], non_blocking=True)
         k = int(t / self.dt)                                                               # spiraling_mpc.py:360
-        xref = self.reference_window(k)
-        out = self.engine.step(state, xref, self.nominal_window(k), warm=self.optimal_solution is not None)
+        # the window of a single instance is a contiguous slice of the device table: no copy
+        xref = self._traj_dev[k:k + self.Nt + 1].unsqueeze(0)
+        uref = self._uref_dev[k:k + self.Nt + 1].unsqueeze(0) if self._accelerating else None
+        out = self.engine.step(io["state"], xref, uref, warm=self.optimal_solution is not None, out=io["out"])
+        io["rec_host"].copy_(io["rec"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()                               # the one host round trip
         self.optimal_solution = out["z"]
-        self.last_status = int(out["status"][0].item())
-        self.last_u0 = out["u0"][0].cpu().numpy()
-        thrust = out["thrust"][0].cpu().numpy()
+        rec = io["rec_host"].numpy()
+        ints = rec[23:25].view(np.int32)
+        self.last_status = int(ints[0])
+        self.last_iters = (int(ints[1]), int(ints[2]))
+        self.last_u0 = rec[16:22].copy()
+        self.last_cost = float(rec[22])
+        thrust = rec[0:16].copy()
         if self.debug is not None:                                                         # spiraling_mpc.py:309-315
             dv = DebugVal(self, t)
-            dv.set_state(x0[0])
+            dv.set_state(x0)
             dv.set_circle_state(out["z"][0, 6 * self.Nt:6 * self.Nt + 9].cpu().numpy())     # c0 = x_0 of the decision vector
             dv.set_input(thrust, self.model)
             dv.set_desired_state(self.trajectory[:, k])

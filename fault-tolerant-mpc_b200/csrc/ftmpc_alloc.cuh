@@ -106,7 +106,7 @@ FT_HD void phase_out_write(Blk& blk, const ftmpc_config& cfg, const WsLayout& L,
     const double* C = w + L.oC;
     // optimal decision vector, reference layout [u | x]   (spiraling_mpc.py:110-114)
     double* zw = io.z_warm + (size_t)inst * (L.n + (size_t)(N + 1) * FTMPC_NX);
-    const double* uref = io.uref ? io.uref + (size_t)inst * (N + 1) * FTMPC_NU : nullptr;
+    const double* uref = io.uref ? io.uref + (size_t)inst * io.uref_stride : nullptr;
     if (uref) {
         // the solver iterated on u~ = u + rho_t(q_t) (ftmpc_sqp.cuh, FTMPC_CQ): hand back the reference's variable u
         for (int t = tid; t < N; t += nt) {
@@ -149,10 +149,11 @@ FT_HD void phase_out_write(Blk& blk, const ftmpc_config& cfg, const WsLayout& L,
 FT_HD void phase_alloc(const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst) {
     const int N = L.N;
     int status = io.status[inst];
+    if (status == FTMPC_ST_BADINPUT) return;               // rejected inputs (phase_out_invalid wrote a zero command)
     const double* zw = io.z_warm + (size_t)inst * (L.n + (size_t)(N + 1) * FTMPC_NX);
     const double* U = zw;
     const double* X = zw + L.n;
-    const double* uref = io.uref ? io.uref + (size_t)inst * (N + 1) * FTMPC_NU : nullptr;
+    const double* uref = io.uref ? io.uref + (size_t)inst * io.uref_stride : nullptr;
     const double* hull = io.hull_table + (size_t)io.hull_idx[inst] * FTMPC_HULL_STRIDE;
     // u_res = u*_0 + RotFullInv(q_0) ur_0 + u_comp                     spiraling_mpc.py:301-306
     const double* ff = io.fault_force + (size_t)inst * FTMPC_NTHR;

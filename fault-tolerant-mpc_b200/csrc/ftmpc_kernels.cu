@@ -80,6 +80,10 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
         const int inst = s_inst;
         __syncthreads();
         if (inst >= io.batch) break;
+        if (!instance_input_ok(cfg, io, inst)) {                   // uniform over the block
+            phase_out_invalid(blk, L, io, inst);
+            continue;
+        }
         phase_ls_block(blk, cfg, L, io, inst, slot, 1, scratch);
         for (int it = 0; it < cfg.max_sqp_iter; ++it) {
             if (sc[SC_STATUS] != (double)FTMPC_ST_RUNNING) break;      // uniform: written before the last barrier
@@ -260,6 +264,21 @@ __global__ void __launch_bounds__(64) k_allocate(const ftmpc_config* __restrict_
     for (int j = 0; j < 16; ++j) thrust[(size_t)i * 16 + j] = th[j];
 }
 
+__global__ void __launch_bounds__(64) k_clip(const ftmpc_config* __restrict__ cfg, int batch, const double* hull_table,
+                                             const int32_t* hull_idx, const double* u, double* out, int32_t* status) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    const int hi = hull_idx[i];
+    double v[FTMPC_NU];
+    if (hi < 0 || hi >= cfg->n_hull_sets) {
+        for (int j = 0; j < FTMPC_NU; ++j) out[(size_t)i * FTMPC_NU + j] = u[(size_t)i * FTMPC_NU + j];
+        status[i] = FTMPC_ST_BADINPUT;
+        return;
+    }
+    status[i] = clip_to_hull(*cfg, hull_table + (size_t)hi * FTMPC_HULL_STRIDE, u + (size_t)i * FTMPC_NU, v);
+    for (int j = 0; j < FTMPC_NU; ++j) out[(size_t)i * FTMPC_NU + j] = v[j];
+}
+
 __global__ void k_plant(const ftmpc_config* __restrict__ cfg, int batch, const double* state, const double* thrust,
                         const uint16_t* mask, const double* ff, const double* noise, int normalize, double* next) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -268,6 +287,21 @@ __global__ void k_plant(const ftmpc_config* __restrict__ cfg, int batch, const d
     plant_step(*cfg, state + (size_t)i * 13, thrust + (size_t)i * 16, mask[i], ff + (size_t)i * 16,
                noise ? noise + (size_t)i * 13 : nullptr, normalize, xn);
     for (int k = 0; k < 13; ++k) next[(size_t)i * 13 + k] = xn[k];
+}
+
+// closed-loop driver: plant step in place (SimulationEnvironment.step, sim_env.py:85-93) + running totals of the loop
+__global__ void k_plant_loop(const ftmpc_config* __restrict__ cfg, int batch, double* state, const double* thrust,
+                             const uint16_t* mask, const double* ff, const double* noise, const int32_t* status,
+                             const double* cost, double* cost_sum, int32_t* worst, int first) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= batch) return;
+    double xn[13];
+    plant_step(*cfg, state + (size_t)i * 13, thrust + (size_t)i * 16, mask[i], ff + (size_t)i * 16,
+               noise ? noise + (size_t)i * 13 : nullptr, 1, xn);
+    for (int k = 0; k < 13; ++k) state[(size_t)i * 13 + k] = xn[k];
+    cost_sum[i] = (first ? 0.0 : cost_sum[i]) + cost[i];
+    const int w = first ? 0 : worst[i];
+    worst[i] = status[i] > w ? status[i] : w;
 }
 
 // FP64 FMA throughput probe (roofline denominator for bench.py: MEASURED_PEAKS.json has no fp64 figure).
@@ -293,6 +327,19 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, doubl
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Every entry point runs on the device the handle was created on, whatever the caller's current device is
+// (a handle bound to cuda:1 must not launch on cuda:0 with device-1 pointers); the caller's device is restored.
+struct DeviceGuard {
+    int prev;
+    bool ok;
+    explicit DeviceGuard(int dev) : prev(-1), ok(true) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define GUARD(h) DeviceGuard guard_((h)->device); if (!guard_.ok) return FTMPC_ERR_CUDA
+
 static size_t qp_smem_bytes(int N) { return qp_scratch_doubles(N) * sizeof(double); }
 
 
@@ -306,6 +353,7 @@ const char* ftmpc_strerror(int code) {
         case FTMPC_ERR_WORKSPACE: return "workspace too small";
         case FTMPC_ERR_UNSUPPORTED: return "unsupported configuration";
         case FTMPC_ERR_NO_DEVICE: return "no CUDA device (ft_mpc_b200 has no CPU fallback)";
+        case FTMPC_ERR_NOMEM: return "out of host memory";
         default: return "unknown error";
     }
 }
@@ -330,23 +378,31 @@ int ftmpc_create(ftmpc_handle* out, const ftmpc_config* cfg, const double* hull_
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return FTMPC_ERR_NO_DEVICE;
     ftmpc_ctx* h = new (std::nothrow) ftmpc_ctx;
-    if (!h) return FTMPC_ERR_ARG;
+    if (!h) return FTMPC_ERR_NOMEM;
     std::memset(h, 0, sizeof(*h));
     h->cfg = *cfg;
     h->L = ws_layout(cfg->horizon);
-    CU(cudaGetDevice(&h->device));
+    const size_t hb = (size_t)cfg->n_hull_sets * FTMPC_HULL_STRIDE * sizeof(double);
     cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, h->device));
+    // any failure below releases everything acquired so far (ftmpc_destroy copes with a half-built handle)
+#define CREATE_TRY(x) do { if ((x) != cudaSuccess) { ftmpc_destroy(h); return FTMPC_ERR_CUDA; } } while (0)
+    CREATE_TRY(cudaGetDevice(&h->device));
+    CREATE_TRY(cudaGetDeviceProperties(&prop, h->device));
     h->num_sms = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
-    CU(cudaMalloc(&h->d_cfg, sizeof(ftmpc_config)));
-    CU(cudaMemcpy(h->d_cfg, cfg, sizeof(ftmpc_config), cudaMemcpyHostToDevice));
-    const size_t hb = (size_t)cfg->n_hull_sets * FTMPC_HULL_STRIDE * sizeof(double);
-    CU(cudaMalloc(&h->d_hull, hb));
-    CU(cudaMemcpy(h->d_hull, hull_table, hb, cudaMemcpyHostToDevice));
-    CU(cudaMalloc(&h->d_prof, PH_COUNT * sizeof(long long)));
-    CU(cudaMemset(h->d_prof, 0, PH_COUNT * sizeof(long long)));
-    for (int i = 0; i < 3; ++i) CU(cudaEventCreate(&h->ev[i]));
+    CREATE_TRY(cudaMalloc(&h->d_cfg, sizeof(ftmpc_config)));
+    CREATE_TRY(cudaMemcpy(h->d_cfg, cfg, sizeof(ftmpc_config), cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMalloc(&h->d_hull, hb));
+    CREATE_TRY(cudaMemcpy(h->d_hull, hull_table, hb, cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMalloc(&h->d_prof, PH_COUNT * sizeof(long long)));
+    CREATE_TRY(cudaMemset(h->d_prof, 0, PH_COUNT * sizeof(long long)));
+    for (int i = 0; i < 3; ++i) CREATE_TRY(cudaEventCreate(&h->ev[i]));
+    // dynamic shared memory opt-in, once per handle: the attribute is per function and per device, so it is raised to the
+    // device maximum (every horizon whose scratch fits uses the same kernel instantiation)
+    CREATE_TRY(cudaFuncSetAttribute(k_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+    CREATE_TRY(cudaFuncSetAttribute(k_condense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+    CREATE_TRY(cudaFuncSetAttribute(k_qp_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+#undef CREATE_TRY
     *out = h;
     return FTMPC_OK;
 }
@@ -361,6 +417,7 @@ int ftmpc_last_launches(ftmpc_handle h) { return h ? h->last_launches : FTMPC_ER
 
 int ftmpc_profile_read(ftmpc_handle h, void* stream, double* kernel_ms, int64_t* phase_cycles, int n_phase) {
     if (!h || !kernel_ms) return FTMPC_ERR_ARG;
+    GUARD(h);
     CU(cudaStreamSynchronize((cudaStream_t)stream));
     kernel_ms[0] = kernel_ms[1] = 0.0;
     if (h->profile) {
@@ -380,6 +437,7 @@ int ftmpc_profile_read(ftmpc_handle h, void* stream, double* kernel_ms, int64_t*
 
 void ftmpc_destroy(ftmpc_handle h) {
     if (!h) return;
+    DeviceGuard guard_(h->device);
     for (int i = 0; i < 3; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     cudaFree(h->d_cfg);
     cudaFree(h->d_hull);
@@ -413,27 +471,14 @@ int ftmpc_workspace_bytes(ftmpc_handle h, int batch, size_t* out) {
     return FTMPC_OK;
 }
 
-int ftmpc_step(ftmpc_handle h, int batch, const double* state, const double* xref, const double* uref,
-               const uint16_t* fault_mask, const double* fault_force, const int32_t* hull_idx, int warm,
-               double* z_warm, double* thrust, double* u0, uint32_t* active_set, int32_t* status, int32_t* iters,
-               double* cost, void* workspace, size_t workspace_bytes, void* stream_) {
-    if (!h || batch < 1 || !state || !xref || !fault_mask || !fault_force || !hull_idx || !z_warm || !thrust || !u0 ||
-        !active_set || !status || !iters || !workspace)
-        return FTMPC_ERR_ARG;
-    size_t need_ws = 0;
-    ftmpc_workspace_bytes(h, batch, &need_ws);
-    if (workspace_bytes < need_ws) return FTMPC_ERR_WORKSPACE;
-    cudaStream_t stream = (cudaStream_t)stream_;
+// enqueue memset(queue) + k_solve + k_alloc for one batch (no synchronisation)
+static int launch_step(ftmpc_ctx* h, const StepIO& io, void* workspace, size_t need_ws, cudaStream_t stream) {
     const WsLayout L = h->L;
-    StepIO io{batch, state, xref, uref, fault_mask, fault_force, hull_idx, h->d_hull, warm, z_warm, thrust, u0,
-              active_set, status, iters, cost, nullptr, nullptr, h->d_cfg, (double*)workspace};
-    const int grid = solve_grid(h, batch);
+    const int grid = solve_grid(h, io.batch);
     const size_t smem = solve_smem_bytes(h->cfg.horizon);
     const bool use_global = smem > h->smem_optin;
     double* gscratch = use_global ? (double*)((char*)workspace + align_up(L.stride * sizeof(double) * (size_t)grid, 256)) : nullptr;
     const size_t sdoubles = align_up(smem, 256) / sizeof(double);
-    // the attribute is per function, not per handle: handles with different horizons share k_solve
-    if (!use_global) CU(cudaFuncSetAttribute(k_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int* queue = (int*)((char*)workspace + need_ws - 256);
     CU(cudaMemsetAsync(queue, 0, sizeof(int), stream));
     if (h->profile) {
@@ -447,9 +492,59 @@ int ftmpc_step(ftmpc_handle h, int batch, const double* state, const double* xre
         k_solve<false><<<grid, FTMPC_QP_THREADS, smem, stream>>>(h->cfg, L, io, queue, nullptr, 0,
                                                                  h->profile ? h->d_prof : nullptr);
     if (h->profile) CU(cudaEventRecord(h->ev[1], stream));
-    k_alloc<<<(batch + 63) / 64, 64, 0, stream>>>(h->cfg, L, io);
+    k_alloc<<<(io.batch + 63) / 64, 64, 0, stream>>>(h->cfg, L, io);
     if (h->profile) CU(cudaEventRecord(h->ev[2], stream));
     h->last_launches = 2;
+    CU(cudaGetLastError());
+    return FTMPC_OK;
+}
+
+int ftmpc_step(ftmpc_handle h, int batch, const double* state, const double* xref, const double* uref,
+               const uint16_t* fault_mask, const double* fault_force, const int32_t* hull_idx, int warm,
+               double* z_warm, double* thrust, double* u0, uint32_t* active_set, int32_t* status, int32_t* iters,
+               double* cost, void* workspace, size_t workspace_bytes, void* stream_) {
+    if (!h || batch < 1 || !state || !xref || !fault_mask || !fault_force || !hull_idx || !z_warm || !thrust || !u0 ||
+        !active_set || !status || !iters || !workspace)
+        return FTMPC_ERR_ARG;
+    GUARD(h);
+    size_t need_ws = 0;
+    ftmpc_workspace_bytes(h, batch, &need_ws);
+    if (workspace_bytes < need_ws) return FTMPC_ERR_WORKSPACE;
+    StepIO io{batch, state, xref, uref, fault_mask, fault_force, hull_idx, h->d_hull, warm, z_warm, thrust, u0,
+              active_set, status, iters, cost, nullptr, nullptr, h->d_cfg, (double*)workspace, 0, 0};
+    stepio_default_strides(io, h->L.N);
+    return launch_step(h, io, workspace, need_ws, (cudaStream_t)stream_);
+}
+
+int ftmpc_closed_loop(ftmpc_handle h, int batch, int steps, int start_step, int table_rows, double* state,
+                      const double* trajectory, const double* nominal, const uint16_t* fault_mask,
+                      const double* fault_force, const int32_t* hull_idx, const double* noise, int warm_first,
+                      double* z_warm, double* thrust, double* u0, uint32_t* active_set, int32_t* status, int32_t* iters,
+                      double* cost, double* cost_sum, int32_t* worst_status, void* workspace, size_t workspace_bytes,
+                      void* stream_) {
+    if (!h || batch < 1 || steps < 1 || start_step < 0 || !state || !trajectory || !fault_mask || !fault_force || !hull_idx ||
+        !z_warm || !thrust || !u0 || !active_set || !status || !iters || !cost || !cost_sum || !worst_status || !workspace)
+        return FTMPC_ERR_ARG;
+    if (start_step + steps + h->L.N > table_rows) return FTMPC_ERR_ARG;      // the last window must lie inside the table
+    GUARD(h);
+    size_t need_ws = 0;
+    ftmpc_workspace_bytes(h, batch, &need_ws);
+    if (workspace_bytes < need_ws) return FTMPC_ERR_WORKSPACE;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int launches = 0;
+    for (int k = 0; k < steps; ++k) {
+        const int row = start_step + k;
+        StepIO io{batch, state, trajectory + (size_t)row * FTMPC_NE, nominal ? nominal + (size_t)row * FTMPC_NU : nullptr,
+                  fault_mask, fault_force, hull_idx, h->d_hull, (k > 0 || warm_first) ? 1 : 0, z_warm, thrust, u0, active_set,
+                  status, iters, cost, nullptr, nullptr, h->d_cfg, (double*)workspace, 0, 0};      // strides 0: shared window
+        const int rc = launch_step(h, io, workspace, need_ws, stream);
+        if (rc != FTMPC_OK) return rc;
+        k_plant_loop<<<(batch + 127) / 128, 128, 0, stream>>>(h->d_cfg, batch, state, thrust, fault_mask, fault_force,
+                                                              noise ? noise + (size_t)k * batch * FTMPC_NX : nullptr, status,
+                                                              cost, cost_sum, worst_status, k == 0);
+        launches += 3;
+    }
+    h->last_launches = launches;
     CU(cudaGetLastError());
     return FTMPC_OK;
 }
@@ -457,6 +552,7 @@ int ftmpc_step(ftmpc_handle h, int batch, const double* state, const double* xre
 int ftmpc_hull_facets(ftmpc_handle h, int n_sets, const uint16_t* fault_mask, const double* fault_force, double* table,
                       int32_t* n_rows, int32_t* status, void* stream) {
     if (!h || n_sets < 1 || !fault_mask || !fault_force || !table || !n_rows || !status) return FTMPC_ERR_ARG;
+    GUARD(h);
     k_hull_facets<<<n_sets, 256, 0, (cudaStream_t)stream>>>(h->d_cfg, n_sets, fault_mask, fault_force, table, n_rows, status);
     CU(cudaGetLastError());
     return FTMPC_OK;
@@ -465,6 +561,7 @@ int ftmpc_hull_facets(ftmpc_handle h, int n_sets, const uint16_t* fault_mask, co
 int ftmpc_rk4_jac(ftmpc_handle h, int batch, double* x, const double* wrench, double* jac, const double* lam,
                   double* hess, void* stream) {
     if (!h || batch < 1 || !x || !wrench || !jac) return FTMPC_ERR_ARG;
+    GUARD(h);
     k_rk4_jac<<<(batch + 3) / 4, 128, 0, (cudaStream_t)stream>>>(h->d_cfg, batch, x, wrench, jac, lam, hess);
     CU(cudaGetLastError());
     return FTMPC_OK;
@@ -472,6 +569,7 @@ int ftmpc_rk4_jac(ftmpc_handle h, int batch, double* x, const double* wrench, do
 
 int ftmpc_robot_to_center(ftmpc_handle h, int batch, const double* state, double* center, void* stream) {
     if (!h || batch < 1 || !state || !center) return FTMPC_ERR_ARG;
+    GUARD(h);
     k_r2c<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d_cfg, batch, state, center);
     CU(cudaGetLastError());
     return FTMPC_OK;
@@ -479,6 +577,7 @@ int ftmpc_robot_to_center(ftmpc_handle h, int batch, const double* state, double
 
 int ftmpc_terminal(ftmpc_handle h, int batch, const double* e, double* V, double* grad, double* hess, void* stream) {
     if (!h || batch < 1 || !e || !V || !grad || !hess) return FTMPC_ERR_ARG;
+    GUARD(h);
     k_terminal<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d_cfg, batch, e, V, grad, hess);
     CU(cudaGetLastError());
     return FTMPC_OK;
@@ -488,10 +587,10 @@ int ftmpc_condense(ftmpc_handle h, int batch, const double* jac, const double* h
                    const double* xref, const double* gradV, const double* hessV, double theta, double* H, double* g,
                    void* stream) {
     if (!h || batch < 1 || !jac || !x || !u || !xref || !gradV || !hessV || !H || !g) return FTMPC_ERR_ARG;
+    GUARD(h);
     const size_t smem = qp_smem_bytes(h->cfg.horizon);
     if (smem > h->smem_optin) return FTMPC_ERR_UNSUPPORTED;
     const int grid = batch < h->num_sms ? batch : h->num_sms;
-    CU(cudaFuncSetAttribute(k_condense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_condense<<<grid, FTMPC_QP_THREADS, smem, (cudaStream_t)stream>>>(h->d_cfg, h->L, batch, jac, hess, x, u, xref,
                                                                          gradV, hessV, theta, H, g, nullptr, 0);
     CU(cudaGetLastError());
@@ -503,11 +602,11 @@ int ftmpc_qp_solve(ftmpc_handle h, int batch, int n, int m, const double* H, con
                    int32_t* status, void* stream) {
     if (!h || batch < 1 || n < 1 || m < 0 || !H || !g || !row_ptr || !col_idx || !val || !b || !x || !lam || !status)
         return FTMPC_ERR_ARG;
+    GUARD(h);
     const int ld = n | 1;
     const size_t doubles = (size_t)n * ld + (size_t)n * (n + 1) / 2 + 1 + 12 * (size_t)n + m + 16;
     const size_t bytes = doubles * 8 + ((size_t)2 * n + m + 8) * 4;
     if (bytes > h->smem_optin) return FTMPC_ERR_UNSUPPORTED;
-    CU(cudaFuncSetAttribute(k_qp_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     const int grid = batch < h->num_sms ? batch : h->num_sms;
     k_qp_generic<<<grid, FTMPC_QP_THREADS, bytes, (cudaStream_t)stream>>>(batch, n, m, H, g, row_ptr, col_idx, val, b, x,
                                                                             lam, status, 20 * (n + m), 1e-11);
@@ -518,7 +617,17 @@ int ftmpc_qp_solve(ftmpc_handle h, int batch, int n, int m, const double* H, con
 int ftmpc_allocate(ftmpc_handle h, int batch, const double* u_des, const double* ub, double* thrust, int32_t* status,
                    void* stream) {
     if (!h || batch < 1 || !u_des || !ub || !thrust || !status) return FTMPC_ERR_ARG;
+    GUARD(h);
     k_allocate<<<(batch + 63) / 64, 64, 0, (cudaStream_t)stream>>>(h->d_cfg, batch, u_des, ub, thrust, status);
+    CU(cudaGetLastError());
+    return FTMPC_OK;
+}
+
+int ftmpc_clip(ftmpc_handle h, int batch, const int32_t* hull_idx, const double* u, double* u_clipped, int32_t* status,
+               void* stream) {
+    if (!h || batch < 1 || !hull_idx || !u || !u_clipped || !status) return FTMPC_ERR_ARG;
+    GUARD(h);
+    k_clip<<<(batch + 63) / 64, 64, 0, (cudaStream_t)stream>>>(h->d_cfg, batch, h->d_hull, hull_idx, u, u_clipped, status);
     CU(cudaGetLastError());
     return FTMPC_OK;
 }
@@ -526,6 +635,7 @@ int ftmpc_allocate(ftmpc_handle h, int batch, const double* u_des, const double*
 int ftmpc_plant_step(ftmpc_handle h, int batch, const double* state, const double* thrust, const uint16_t* fault_mask,
                      const double* fault_force, const double* noise, int normalize, double* next, void* stream) {
     if (!h || batch < 1 || !state || !thrust || !fault_mask || !fault_force || !next) return FTMPC_ERR_ARG;
+    GUARD(h);
     k_plant<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d_cfg, batch, state, thrust, fault_mask,
                                                                      fault_force, noise, normalize, next);
     CU(cudaGetLastError());
@@ -534,6 +644,7 @@ int ftmpc_plant_step(ftmpc_handle h, int batch, const double* state, const doubl
 
 int ftmpc_fp64_peak(ftmpc_handle h, double* tflops, void* stream_) {
     if (!h || !tflops) return FTMPC_ERR_ARG;
+    GUARD(h);
     cudaStream_t stream = (cudaStream_t)stream_;
     double* d = nullptr;
     CU(cudaMalloc(&d, sizeof(double)));

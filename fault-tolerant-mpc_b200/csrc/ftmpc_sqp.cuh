@@ -87,9 +87,36 @@ struct StepIO {
     const ftmpc_config* cfg_g;  // copy of the configuration in global memory (tables indexed per thread); the kernels
                                 // also receive it by value as a __grid_constant__ parameter for uniform accesses
     double* ws;                 // workspace: one slot of L.stride doubles per instance (CPU port) or per CTA (k_solve)
+    size_t xref_stride;         // doubles between the reference windows of consecutive instances: (N+1)*9, or 0 when every
+    size_t uref_stride;         // instance tracks the same window (closed-loop driver: one table shared by the batch)
 };
+FT_HD void stepio_default_strides(StepIO& io, int N) {
+    io.xref_stride = (size_t)(N + 1) * FTMPC_NE;
+    io.uref_stride = (size_t)(N + 1) * FTMPC_NU;
+}
 
 FT_HD double* ws_slot(const StepIO& io, const WsLayout& L, int slot) { return io.ws + (size_t)slot * L.stride; }
+
+// per-instance input validation: the hull table is indexed with hull_idx straight from the caller's tensor
+FT_HD bool instance_input_ok(const ftmpc_config& cfg, const StepIO& io, int inst) {
+    const int h = io.hull_idx[inst];
+    return h >= 0 && h < cfg.n_hull_sets;
+}
+// results of an instance whose inputs were rejected: status FTMPC_ST_BADINPUT, zero command, empty active set
+template <class Blk>
+FT_HD void phase_out_invalid(Blk& blk, const WsLayout& L, const StepIO& io, int inst) {
+    const int tid = blk.tid(), nt = blk.nthreads(), nw = (L.mc + 31) / 32;
+    for (int j = tid; j < FTMPC_NU; j += nt) io.u0[(size_t)inst * FTMPC_NU + j] = 0.0;
+    for (int j = tid; j < FTMPC_NTHR; j += nt) io.thrust[(size_t)inst * FTMPC_NTHR + j] = 0.0;
+    for (int wd = tid; wd < nw; wd += nt) io.active_set[(size_t)inst * nw + wd] = 0u;
+    if (tid == 0) {
+        io.status[inst] = FTMPC_ST_BADINPUT;
+        io.iters[2 * inst] = 0;
+        io.iters[2 * inst + 1] = 0;
+        if (io.cost) io.cost[inst] = 0.0;
+    }
+    blk.sync();
+}
 
 FT_HD DynConsts dyn_consts(const ftmpc_config& c) {
     DynConsts k;
@@ -235,8 +262,8 @@ FT_HD void phase_ls(const ftmpc_config& cfg, const WsLayout& L, const StepIO& io
     double* w = ws_slot(io, L, slot);
     double* sc = w + L.oSc;
     const int N = L.N;
-    const double* xref = io.xref + (size_t)inst * (N + 1) * FTMPC_NE;
-    const double* uref = io.uref ? io.uref + (size_t)inst * (N + 1) * FTMPC_NU : nullptr;
+    const double* xref = io.xref + (size_t)inst * io.xref_stride;
+    const double* uref = io.uref ? io.uref + (size_t)inst * io.uref_stride : nullptr;
     const double* hull = io.hull_table + (size_t)io.hull_idx[inst] * FTMPC_HULL_STRIDE;
     double* U = w + L.oU;
     double* D = w + L.oD;
@@ -471,8 +498,8 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
     double* w = ws_slot(io, L, slot);
     double* sc = w + L.oSc;
     const int N = L.N, tid = blk.tid(), nt = blk.nthreads(), lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-    const double* xref_g = io.xref + (size_t)inst * (N + 1) * FTMPC_NE;
-    const double* uref_g = io.uref ? io.uref + (size_t)inst * (N + 1) * FTMPC_NU : nullptr;
+    const double* xref_g = io.xref + (size_t)inst * io.xref_stride;
+    const double* uref_g = io.uref ? io.uref + (size_t)inst * io.uref_stride : nullptr;
     const double* hull_g = io.hull_table + (size_t)io.hull_idx[inst] * FTMPC_HULL_STRIDE;
     const ftmpc_config& cg = *io.cfg_g;
     double* U = w + L.oU;
@@ -702,8 +729,8 @@ FT_HD void phase_lin(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const
     if (sc[SC_STATUS] != FTMPC_ST_RUNNING) return;
     const int N = L.N, tid = blk.tid(), nt = blk.nthreads();
     const DynConsts k = dyn_consts(cfg);
-    const double* xref = io.xref + (size_t)inst * (N + 1) * FTMPC_NE;
-    const double* uref = io.uref ? io.uref + (size_t)inst * (N + 1) * FTMPC_NU : nullptr;
+    const double* xref = io.xref + (size_t)inst * io.xref_stride;
+    const double* uref = io.uref ? io.uref + (size_t)inst * io.uref_stride : nullptr;
     const double* U = w + L.oU;
     const double* X = w + L.oX;
     double* Jz = w + L.oJz;
@@ -1088,8 +1115,8 @@ __device__ __forceinline__ void phase_lin(CudaBlock& blk, const ftmpc_config& cf
     if (sc[SC_STATUS] != FTMPC_ST_RUNNING) return;
     const int N = L.N, tid = blk.tid(), nt = blk.nthreads();
     const DynConsts k = dyn_consts(cfg);
-    const double* xref = io.xref + (size_t)inst * (N + 1) * FTMPC_NE;
-    const double* uref = io.uref ? io.uref + (size_t)inst * (N + 1) * FTMPC_NU : nullptr;
+    const double* xref = io.xref + (size_t)inst * io.xref_stride;
+    const double* uref = io.uref ? io.uref + (size_t)inst * io.uref_stride : nullptr;
     const double* U = w + L.oU;
     const double* X = w + L.oX;
     double* Jz = w + L.oJz;
@@ -1775,7 +1802,7 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     QpScratch s = qp_carve(scratch, N, io.cfg_g);
     s.tf_val = io.tf_val;
     s.tf_idx = io.tf_idx;
-    const double* xref = io.xref + (size_t)inst * (N + 1) * FTMPC_NE;
+    const double* xref = io.xref + (size_t)inst * io.xref_stride;
     const double* hull_g = io.hull_table + (size_t)io.hull_idx[inst] * FTMPC_HULL_STRIDE;
     // stage data -> scratch (the R^-1 region is free until the active-set solve starts)
     double* Jz = s.RS;
@@ -1822,7 +1849,13 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         if (sigma == 0.0 && theta == 1.0 && aug_allowed) { sig0 = 10.0 * dscale; sigma = sig0; FT_DBG_COUNT(0); }
         else if (sigma > 0.0 && sig0 > 0.0 && sigma < 5.0 * sig0) { sigma *= 10.0; FT_DBG_COUNT(1); }
         else if (sigma > 0.0) { sigma = 0.0; theta = 0.5; aug_allowed = false; FT_DBG_COUNT(2); }
-        else if (theta <= 0.0) { if (tid == 0) { sc[SC_QPST] = 3.0; } return; }
+        else if (theta <= 0.0) {
+            // even the Gauss-Newton model could not be factorised (NaN / non-positive weights): every thread must see
+            // SC_QPST before the step acceptance reads it, otherwise the warps of the block take different barrier paths
+            if (tid == 0) sc[SC_QPST] = 3.0;
+            blk.sync();
+            return;
+        }
         else { FT_DBG_COUNT(theta == 1.0 ? 3 : 4); theta = (theta > cfg.theta_first) ? 0.5 * theta : 0.0; }     // below the first blend level: Gauss-Newton
     }
     // slack variable column/row, extension rows  X J  (X = d x_N[0:9] / d U)

@@ -13,7 +13,8 @@
  * fp64 arithmetic; every call only enqueues work on `stream` (no hidden synchronisation);
  * return value 0 = ok, <0 = error
  * (ftmpc_strerror); per-instance outcomes are reported in status[B], never by exit()/exceptions.
- * One handle per device; a handle is not thread-safe.
+ * A handle is bound to the device that was current in ftmpc_create; every entry point switches to that device for
+ * its launches and restores the caller's current device.  A handle is not thread-safe.
  */
 #ifndef FTMPC_H_
 #define FTMPC_H_
@@ -41,6 +42,7 @@ enum {
     FTMPC_ST_QPFAIL = 2,      /* QP sub-problem infeasible / numerical breakdown / NaN      */
     FTMPC_ST_INFEASIBLE = 3,  /* converged to a point that violates the constraints         */
     FTMPC_ST_ALLOC = 4,       /* NLP ok but thrust allocation infeasible (control_allocator.py:88-93 calls exit()) */
+    FTMPC_ST_BADINPUT = 5,    /* rejected inputs: hull_idx outside [0, n_hull_sets); zero command returned   */
     FTMPC_ST_RUNNING = -1
 };
 
@@ -51,7 +53,8 @@ enum {
     FTMPC_ERR_CUDA = -2,
     FTMPC_ERR_WORKSPACE = -3,
     FTMPC_ERR_UNSUPPORTED = -4,
-    FTMPC_ERR_NO_DEVICE = -5
+    FTMPC_ERR_NO_DEVICE = -5,
+    FTMPC_ERR_NOMEM = -6
 };
 
 typedef struct ftmpc_config {
@@ -116,6 +119,22 @@ int ftmpc_step(ftmpc_handle h, int batch, const double* state, const double* xre
                double* z_warm, double* thrust, double* u0, uint32_t* active_set, int32_t* status,
                int32_t* iters, double* cost, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Closed loop for `batch` instances == SimulationEnvironment.run_simulation (sim_env.py:77-112): `steps` times
+ * (ftmpc_step -> plant step -> noise -> quaternion renormalisation), enqueued back to back on `stream` with no host
+ * round trip.  Every instance tracks the SAME reference table (SpiralingController.assign_trajectory, :255-286):
+ *   trajectory [table_rows,9], nominal [table_rows,6] or NULL; the window of loop step k starts at row start_step + k
+ *   (the integer form of int(t/dt), :360) and is read in place -- no per-instance copies;
+ *   state [B,13] in/out (robot states); noise [steps,B,13] or NULL (the reference draws unseeded U(0,1e-3), sim_env.py:88-91);
+ *   warm start from the second step on, from the first too when warm_first != 0 (spiraling_mpc.py:324-331);
+ *   per-step outputs as in ftmpc_step (they hold the LAST step on return); cost_sum [B] = sum of the optimal costs,
+ *   worst_status [B] = max status over the steps. */
+int ftmpc_closed_loop(ftmpc_handle h, int batch, int steps, int start_step, int table_rows, double* state,
+                      const double* trajectory, const double* nominal, const uint16_t* fault_mask,
+                      const double* fault_force, const int32_t* hull_idx, const double* noise, int warm_first,
+                      double* z_warm, double* thrust, double* u0, uint32_t* active_set, int32_t* status, int32_t* iters,
+                      double* cost, double* cost_sum, int32_t* worst_status, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
 /* Profiling hooks used by bench.py.  When enabled, ftmpc_step brackets its kernels with CUDA events on `stream` and
  * the solver kernel accumulates a per-phase cycle profile.  ftmpc_profile_read synchronises the stream and returns, for
  * the LAST ftmpc_step:  kernel_ms[0] = k_solve, kernel_ms[1] = k_alloc (device time);
@@ -155,6 +174,11 @@ int ftmpc_qp_solve(ftmpc_handle h, int batch, int n, int m, const double* H, con
 /* K5: control allocation  min |u|^2 s.t. D u = u_des, 0 <= u <= ub   (control_allocator.py:28-40) */
 int ftmpc_allocate(ftmpc_handle h, int batch, const double* u_des, const double* ub, double* thrust,
                    int32_t* status, void* stream);
+/* clip_generalized_input (control_allocator.py:42-63): u [B,6] = u_res + D f_fault -> u_clipped [B,6]; identity when
+ *     A_h u <= b_h + clip_tol, else the Euclidean projection onto the hull of hull_idx[B] (the reference's branch is
+ *     dimensionally inconsistent and names an absent solver; its docstring states this projection).  status 0 / GI code. */
+int ftmpc_clip(ftmpc_handle h, int batch, const int32_t* hull_idx, const double* u, double* u_clipped, int32_t* status,
+               void* stream);
 /* K6: plant step (16 thrusters, robot state): RK4 of SystemModel.dx_dt (sys_model.py:138-243);
  *     noise [B,13] or NULL is added after the step (sim_env.py:88-91); normalize != 0 renormalises the
  *     quaternion (sys_model.py:164-175, sim_env.py:93).  normalize = 0, noise = NULL == model.dynamics(x,u). */

@@ -37,7 +37,8 @@ int ftmpc_cpu_step(const ftmpc_config* cfg, const double* hull_table, int batch,
     std::vector<double> own;
     if (!ws) { own.resize(L.stride * (size_t)batch); ws = own.data(); }
     StepIO io{batch, state, xref, uref, fault_mask, fault_force, hull_idx, hull_table, warm, z_warm, thrust, u0,
-              active_set, status, iters, cost, nullptr, nullptr, cfg, ws};
+              active_set, status, iters, cost, nullptr, nullptr, cfg, ws, 0, 0};
+    stepio_default_strides(io, cfg->horizon);
     const size_t sdoubles = qp_scratch_doubles(cfg->horizon);
     const bool trace = std::getenv("FTMPC_TRACE") != nullptr;
 #ifdef _OPENMP
@@ -49,6 +50,7 @@ int ftmpc_cpu_step(const ftmpc_config* cfg, const double* hull_table, int batch,
         SerialBlock blk;
 #pragma omp for schedule(dynamic, 1)
         for (int inst = 0; inst < batch; ++inst) {
+            if (!instance_input_ok(*cfg, io, inst)) { phase_out_invalid(blk, L, io, inst); continue; }
             phase_ls(*cfg, L, io, inst, inst, 1);
             for (int it = 0; it < cfg->max_sqp_iter; ++it) {
                 if (ws[(size_t)inst * L.stride + L.oSc + SC_STATUS] != FTMPC_ST_RUNNING) break;
@@ -102,6 +104,13 @@ int ftmpc_cpu_terminal(const ftmpc_config* cfg, int batch, const double* e, doub
 int ftmpc_cpu_allocate(const ftmpc_config* cfg, int batch, const double* u_des, const double* ub, double* thrust,
                        int32_t* status) {
     for (int b = 0; b < batch; ++b) status[b] = allocate_thrust(*cfg, u_des + b * 6, ub + b * 16, thrust + b * 16);
+    return 0;
+}
+
+int ftmpc_cpu_clip(const ftmpc_config* cfg, int batch, const double* hull_table, const int32_t* hull_idx, const double* u,
+                   double* out, int32_t* status) {
+    for (int b = 0; b < batch; ++b)
+        status[b] = clip_to_hull(*cfg, hull_table + (size_t)hull_idx[b] * FTMPC_HULL_STRIDE, u + b * 6, out + b * 6);
     return 0;
 }
 

@@ -464,7 +464,7 @@ def test_batch_1024_properties_and_sharding(L, oracle):
     torch.cuda.synchronize()
     g = {k: v.cpu().numpy().copy() for k, v in out.items() if k != "ws"}
     ok = g["status"] == 0
-    assert ok.mean() > 0.95, np.bincount(g["status"], minlength=5)
+    assert ok.mean() > 0.95, np.bincount(g["status"], minlength=6)
     th = g["thrust"]
     assert np.isfinite(th).all() and (th >= 0).all() and (th <= 3.4 + 1e-12).all()
     for k in range(B):                                                   # failed thrusters are never commanded

@@ -1,0 +1,350 @@
+"""Round-2 parity cases (VERDICT r01 "next round" item 1 and the advisor's findings):
+  * closed loop of the examples/sim.py default scenario over the demo horizon (sim_env.py:102-112, 300 steps) against
+    the oracle's closed loop (tests/golden/closed_loop_N15.npz, tools/gen_closed_loop_golden.py), noise off and with
+    the recorded default_rng(0) noise tensor, oracle-KKT-certified every 25th step;
+  * the projection branch of clip_generalized_input (control_allocator.py:42-63) on points outside the hull;
+  * long horizons (N = 30, N = 100) certified by the oracle's KKT residual instead of the CPU port;
+  * rejected inputs (hull_idx out of range), a forced factorisation failure, a handle bound to a non-current device.
+CPU variants run the same checks on the CPU port (same per-instance headers) where that finishes in seconds."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+ROOT = Path(__file__).resolve().parent.parent
+DEFAULT_FAULTS = [(10, 1.0), (11, 1.0)]
+
+
+@pytest.fixture(scope="module")
+def loop_golden():
+    return np.load(ROOT / "tests" / "golden" / "closed_loop_N15.npz")
+
+
+def _noise(steps):
+    return np.random.default_rng(0).uniform(0.0, 1e-3, (300, 13))[:steps]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# closed loop
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["clean", "noisy"])
+def test_cpu_port_closed_loop_vs_oracle(oracle, built, loop_golden, kind):
+    """30 steps of get_control -> plant -> (noise) -> normalise on the CPU port track the oracle's loop within 1e-6"""
+    port = H.CpuPort()
+    N = 15
+    cfg, table, masks, ffs, _ = H.host_tables([DEFAULT_FAULTS], N)
+    fs = oracle.FaultSet(DEFAULT_FAULTS)
+    traj, _ = oracle.assign_trajectory(oracle.hover_trajectory(30, 0.1), N, 0.1)
+    gx, gth = loop_golden[f"{kind}::x"], loop_golden[f"{kind}::thrust"]
+    steps = gth.shape[0]
+    noise = _noise(steps) if kind == "noisy" else None
+    x = gx[0].copy()
+    z = None
+    for k in range(steps):
+        assert np.abs(x - gx[k]).max() <= 1e-6, (k, np.abs(x - gx[k]).max())
+        xr = traj[:, k:k + N + 1].T[None].copy()
+        out = port.step(cfg, table, x[None], xr, None, masks[:1], ffs[:1], np.zeros(1, np.int32), warm=int(k > 0), z=z)
+        assert int(out["status"][0]) == 0, k
+        assert np.allclose(out["thrust"][0], gth[k], atol=2e-5), k
+        u0 = loop_golden[f"{kind}::U"][k, 0]
+        assert np.abs(out["u0"][0] - u0).max() <= 1e-5 * max(1.0, np.abs(u0).max()), k
+        z = out["z"]
+        x = oracle.plant_rk4(x, out["thrust"][0], fs, 0.1)
+        if noise is not None:
+            x = x + noise[k]
+        x = oracle.normalize_quaternion_robot(x)
+    assert np.abs(x - gx[steps]).max() <= 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["clean", "noisy"])
+def test_gpu_closed_loop_300_steps(ft, oracle, built, loop_golden, kind):
+    """The reference-facing loop of examples/sim.py (SystemModel -> SpiralModel -> SpiralingController.get_control ->
+    model.dynamics -> noise -> normalize_quaternion, sim_env.py:77-99) over the full 300-step demo horizon on the GPU:
+    states within 1e-6 of the oracle's closed loop for its 30 recorded steps, every solve status 0, and the KKT
+    conditions of the reference NLP re-checked by the oracle at every 25th step up to step 300."""
+    import torch
+    from ft_mpc_b200.controllers import SpiralingController
+    from ft_mpc_b200.models import SpiralModel, SystemModel
+    from ft_mpc_b200.util import BrokenThruster
+    N, STEPS = 15, 300
+    model = SystemModel(0.1)
+    for i, a in DEFAULT_FAULTS:
+        model.set_fault(BrokenThruster(i, a))
+    ctrl = SpiralingController(SpiralModel.from_system_model(model), {"horizon": N}, None)
+    ctrl.load_trajectory("hover", 30)
+    fs = oracle.FaultSet(DEFAULT_FAULTS)
+    traj, nom = oracle.assign_trajectory(oracle.hover_trajectory(30, 0.1), N, 0.1)
+    gx, gth = loop_golden[f"{kind}::x"], loop_golden[f"{kind}::thrust"]
+    noise = np.random.default_rng(0).uniform(0.0, 1e-3, (300, 13)) if kind == "noisy" else None
+    x = gx[0].copy()
+    worst_kkt = 0.0
+    for k in range(STEPS):
+        if k < gth.shape[0]:
+            assert np.abs(x - gx[k]).max() <= 1e-6, (k, np.abs(x - gx[k]).max())
+        u = ctrl.get_control(x, 0.1 * k + 1e-9)                      # +1e-9: int(t/dt) must not round an exact multiple down
+        assert ctrl.last_status == 0, (k, ctrl.last_status)
+        if k < gth.shape[0]:
+            assert np.allclose(u, gth[k], atol=2e-5), k
+        if k % 25 == 0 or k == STEPS - 1:
+            xr, ur = oracle.window(traj, nom, k, N)
+            prob = oracle.Problem(fs, N, oracle.robot_to_center(x), xr, ur)
+            r = oracle.kkt_residual(prob, ctrl.optimal_solution[0, :6 * N].cpu().numpy())
+            assert r["stat"] < 1e-4 and r["viol"] < 1e-7, (k, r["stat"], r["viol"])
+            worst_kkt = max(worst_kkt, r["stat"])
+        x = model.dynamics(x, u)                                     # sim_env.py:85
+        if noise is not None:
+            x = x + noise[k]                                         # sim_env.py:88-91
+        x = model.normalize_quaternion(x)                            # sim_env.py:93
+    assert np.isfinite(x).all()
+    # noise off: the loop has converged onto the micro-orbit around the hover point (centre error -> 0)
+    if kind == "clean":
+        c = oracle.robot_to_center(x)
+        assert np.abs(c[0:6]).max() < 5e-2, c[0:6]
+
+
+@pytest.mark.gpu
+def test_gpu_native_closed_loop_matches_get_control_loop(ft, oracle, built, loop_golden):
+    """ftmpc_closed_loop (one native call: steps x (solve -> plant), shared reference table read in place, noise tensor
+    injected on the device) == the oracle's recorded loop, noise off and on, for a batch of identical instances"""
+    import torch
+    from ft_mpc_b200.controllers.spiraling_mpc import DEFAULT_Q, DEFAULT_R, BatchedMPC
+    from ft_mpc_b200.models import SystemModel
+    N, B = 15, 3
+    eng = BatchedMPC(SystemModel(0.1), N, DEFAULT_Q, DEFAULT_R, [DEFAULT_FAULTS])
+    traj, _ = oracle.assign_trajectory(oracle.hover_trajectory(30, 0.1), N, 0.1)
+    d = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
+    for kind in ("clean", "noisy"):
+        gx = loop_golden[f"{kind}::x"]
+        steps = gx.shape[0] - 1
+        noise = d(np.repeat(_noise(steps)[:, None, :], B, axis=1)) if kind == "noisy" else None
+        xf, cost, worst, done = eng.closed_loop(d(np.repeat(gx[:1], B, axis=0)), d(traj.T.copy()), steps=steps, noise=noise)
+        torch.cuda.synchronize()
+        assert int(worst.max()) == 0 and int(done[0]) == steps
+        assert np.abs(xf.cpu().numpy() - gx[steps]).max() <= 1e-6
+        assert float(cost[0]) == pytest.approx(float(loop_golden[f"{kind}::f"].sum()), rel=1e-8)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clip_generalized_input: the projection branch
+# ---------------------------------------------------------------------------------------------------------
+def _clip_cases(oracle, faults, seed=3, K=24):
+    fs = oracle.FaultSet(faults)
+    A, b = oracle.input_bounds(fs)
+    rng = np.random.default_rng(seed)
+    ctr = fs.generalized + oracle.D_ALLOC @ (0.5 * fs.ub)                    # a point well inside the hull
+    u = ctr + rng.normal(0, 1.0, (K, 6)) * np.array([6, 4, 4, 0.5, 0.4, 1.2]) * rng.uniform(0.2, 2.5, (K, 1))
+    return fs, A, b, u
+
+
+def _check_projection(oracle, fs, A, b, u, out, status):
+    prob = oracle.Problem(fs, 5, np.r_[np.zeros(12), 1.0], np.zeros((6, 9)), np.zeros((6, 6)))
+    n_out = 0
+    for k in range(len(u)):
+        assert status[k] == 0
+        inside = np.all(A @ u[k] <= b + 1e-9)
+        if inside:
+            assert np.array_equal(out[k], u[k])
+            continue
+        n_out += 1
+        x = out[k]
+        assert np.all(A @ x <= b + 1e-9)                                        # feasible
+        act = np.where(A @ x >= b - 1e-8)[0]
+        assert len(act) >= 1
+        from scipy.optimize import nnls
+        lam, res = nnls(A[act].T, u[k] - x)                                     # u - x in the normal cone of the face
+        assert res <= 1e-8 * max(1.0, np.linalg.norm(u[k] - x)), (k, res)
+        want = oracle.clip_generalized_input(prob, u[k])                        # control_allocator.py:42-63 restated
+        assert np.allclose(x, want, atol=2e-6), (k, np.abs(x - want).max())
+    assert n_out >= 8                                                           # the branch was really exercised
+
+
+@pytest.mark.parametrize("faults", [DEFAULT_FAULTS, [(3, 0.0)], [(0, 0.0), (5, 0.0)]])
+def test_cpu_port_clip_projection_vs_oracle(oracle, built, faults):
+    port = H.CpuPort()
+    cfg, table, *_ = H.host_tables([faults], 5)
+    fs, A, b, u = _clip_cases(oracle, faults)
+    out, st = np.zeros_like(u), np.zeros(len(u), np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    port.lib.ftmpc_cpu_clip(C.byref(cfg), len(u), p(table), p(np.zeros(len(u), np.int32)), p(np.ascontiguousarray(u)), p(out), p(st))
+    _check_projection(oracle, fs, A, b, u, out, st)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("faults", [DEFAULT_FAULTS, [(3, 0.0)], [(0, 0.0), (5, 0.0)]])
+def test_gpu_clip_projection_vs_oracle(ft, oracle, built, faults):
+    import torch
+    from ft_mpc_b200 import _lib as L
+    from ft_mpc_b200.controllers.spiraling_mpc import DEFAULT_Q, DEFAULT_R, BatchedMPC
+    from ft_mpc_b200.models import SystemModel
+    eng = BatchedMPC(SystemModel(0.1), 5, DEFAULT_Q, DEFAULT_R, [faults])
+    fs, A, b, u = _clip_cases(oracle, faults)
+    ud = torch.tensor(u, dtype=torch.float64, device="cuda")
+    out = torch.empty_like(ud)
+    st = torch.empty(len(u), dtype=torch.int32, device="cuda")
+    hidx = torch.zeros(len(u), dtype=torch.int32, device="cuda")
+    pp = lambda t: C.c_void_p(t.data_ptr())
+    L.check(L.lib().ftmpc_clip(eng.handle, len(u), pp(hidx), pp(ud), pp(out), pp(st), None))
+    torch.cuda.synchronize()
+    _check_projection(oracle, fs, A, b, u, out.cpu().numpy(), st.cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_gpu_step_takes_projection_branch_consistently(ft, oracle, built):
+    """end to end: an instance whose u_res lies outside the hull cannot come out of a converged solve (the hull rows are
+    constraints of the NLP), so the branch is driven through the allocator stage: clip -> allocate reproduces
+    oracle.get_control's u_des / thrust for an outside point"""
+    import torch
+    from ft_mpc_b200 import _lib as L
+    from ft_mpc_b200.controllers.spiraling_mpc import DEFAULT_Q, DEFAULT_R, BatchedMPC
+    from ft_mpc_b200.models import SystemModel
+    eng = BatchedMPC(SystemModel(0.1), 5, DEFAULT_Q, DEFAULT_R, [DEFAULT_FAULTS])
+    fs, A, b, u = _clip_cases(oracle, DEFAULT_FAULTS, seed=9, K=12)
+    prob = oracle.Problem(fs, 5, np.r_[np.zeros(12), 1.0], np.zeros((6, 9)), np.zeros((6, 6)))
+    pp = lambda t: C.c_void_p(t.data_ptr())
+    ud = torch.tensor(u, dtype=torch.float64, device="cuda")
+    clipped = torch.empty_like(ud)
+    st = torch.empty(len(u), dtype=torch.int32, device="cuda")
+    L.check(L.lib().ftmpc_clip(eng.handle, len(u), pp(torch.zeros(len(u), dtype=torch.int32, device="cuda")), pp(ud), pp(clipped), pp(st), None))
+    udes = (clipped - torch.tensor(fs.generalized, device="cuda")).contiguous()                  # control_allocator.py:79
+    ub = torch.tensor(np.tile(fs.ub, (len(u), 1)), dtype=torch.float64, device="cuda")
+    th = torch.empty(len(u), 16, dtype=torch.float64, device="cuda")
+    st2 = torch.empty(len(u), dtype=torch.int32, device="cuda")
+    L.check(L.lib().ftmpc_allocate(eng.handle, len(u), pp(udes), pp(ub), pp(th), pp(st2), None))
+    torch.cuda.synchronize()
+    for k in range(len(u)):
+        want_des = oracle.clip_generalized_input(prob, u[k]) - fs.generalized
+        want, ok = oracle.allocate(want_des, fs.ub)
+        assert ok and int(st2[k]) == 0
+        assert np.allclose(th[k].cpu().numpy(), want, atol=2e-5), k
+
+
+# ---------------------------------------------------------------------------------------------------------
+# long horizons: certified by the oracle, not by the CPU port
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,B", [(30, 8), (100, 8)])
+def test_long_horizon_oracle_kkt(ft, oracle, built, N, B):
+    """BASELINE configs[4] horizon (N = 100) and the first horizon beyond the register-tiled path (N = 30): the GPU's
+    decision vector is a KKT point of the oracle's restatement of the reference NLP (independent derivatives)"""
+    import torch
+    from ft_mpc_b200.controllers.spiraling_mpc import DEFAULT_Q, DEFAULT_R, BatchedMPC
+    from ft_mpc_b200.models import SystemModel
+    from ft_mpc_b200.util import scenarios
+    cells = scenarios.load_cells(kinds=("single",))[:4]
+    eng = BatchedMPC(SystemModel(0.1), N, DEFAULT_Q, DEFAULT_R, cells)
+    st = scenarios.random_states(B, 21)
+    scen = np.arange(B) % len(cells)
+    xref = scenarios.hover_reference(B, N)
+    d = lambda a, t=torch.float64: torch.tensor(np.ascontiguousarray(a), dtype=t, device="cuda")
+    out = eng.step(d(st), d(xref), scenario=d(scen, torch.int64))
+    torch.cuda.synchronize()
+    g = {k: v.cpu().numpy() for k, v in out.items() if k != "ws"}
+    assert (g["status"] == 0).sum() >= B - 1, g["status"]
+    for k in np.where(g["status"] == 0)[0]:
+        fs = oracle.FaultSet(cells[scen[k]]["faults"])
+        prob = oracle.Problem(fs, N, oracle.robot_to_center(st[k]), xref[k], np.zeros((N + 1, 6)))
+        r = oracle.kkt_residual(prob, g["z"][k, :6 * N])
+        assert r["stat"] < 1e-4 and r["viol"] < 1e-7, (N, k, r["stat"], r["viol"])
+        assert np.allclose(g["z"][k, 6 * N:].reshape(N + 1, 13), r["X"], atol=1e-9)              # states = the oracle's rollout
+        want = [int(i) for i in r["active"]]
+        nh = prob.n_h
+        bits = [26 * (i // nh) + i % nh if i < nh * N else 26 * N + i - nh * N for i in want]
+        assert H.active_bits(g["active"][k].view(np.uint32), 26 * N + 72) == bits
+
+
+# ---------------------------------------------------------------------------------------------------------
+# robustness (advisor findings)
+# ---------------------------------------------------------------------------------------------------------
+def test_cpu_port_rejects_bad_hull_index(built):
+    from ft_mpc_b200.util import scenarios
+    port = H.CpuPort()
+    N, B = 6, 4
+    cfg, table, masks, ffs, _ = H.host_tables([[(3, 0.0)]], N)
+    st = scenarios.random_states(B, 1)
+    hidx = np.array([0, 7, -1, 0], np.int32)
+    out = port.step(cfg, table, st, scenarios.hover_reference(B, N), None, np.repeat(masks[:1], B), np.repeat(ffs[:1], B, 0), hidx)
+    assert list(out["status"][[1, 2]]) == [5, 5] and np.all(out["thrust"][[1, 2]] == 0)
+    assert np.all(out["status"][[0, 3]] != 5)
+
+
+@pytest.mark.gpu
+def test_gpu_rejects_bad_hull_index_and_keeps_solving(ft, built):
+    import torch
+    from ft_mpc_b200.controllers.spiraling_mpc import DEFAULT_Q, DEFAULT_R, BatchedMPC
+    from ft_mpc_b200.models import SystemModel
+    from ft_mpc_b200.util import scenarios
+    N, B = 15, 16
+    eng = BatchedMPC(SystemModel(0.1), N, DEFAULT_Q, DEFAULT_R, [DEFAULT_FAULTS])
+    st = torch.tensor(scenarios.random_states(B, 2), dtype=torch.float64, device="cuda")
+    xr = torch.tensor(scenarios.hover_reference(B, N), dtype=torch.float64, device="cuda")
+    good = eng.step(st, xr)
+    torch.cuda.synchronize()
+    ref = {k: v.clone() for k, v in good.items() if k != "ws"}
+    mask, ff, hidx = eng.scenario_tensors(torch.zeros(B, dtype=torch.int64, device="cuda"))
+    hidx = hidx.clone()
+    hidx[3], hidx[9] = 5, -2
+    out = eng.step(st, xr, scenario=(mask, ff, hidx))
+    torch.cuda.synchronize()
+    stt = out["status"].cpu().numpy()
+    assert stt[3] == 5 and stt[9] == 5 and np.all(out["thrust"][[3, 9]].cpu().numpy() == 0)
+    keep = [i for i in range(B) if i not in (3, 9)]
+    assert torch.equal(out["thrust"][keep], ref["thrust"][keep]) and torch.equal(out["status"][keep], ref["status"][keep])
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(120)
+def test_gpu_factorisation_failure_is_reported_not_hung(ft, built):
+    """zero weights make even the Gauss-Newton Hessian singular: every instance must come back with FTMPC_ST_QPFAIL
+    (no hang, no garbage -- the failure path of phase_qp used to skip a barrier), and the device keeps working"""
+    import torch
+    from ft_mpc_b200.controllers.spiraling_mpc import DEFAULT_Q, DEFAULT_R, BatchedMPC
+    from ft_mpc_b200.models import SystemModel
+    from ft_mpc_b200.util import scenarios
+    N, B = 20, 300                                                   # two instances per CTA: the CTA survives a failure
+    bad = BatchedMPC(SystemModel(0.1), N, [0.0] * 9, [0.0] * 6, [DEFAULT_FAULTS])
+    st = torch.tensor(scenarios.random_states(B, 4), dtype=torch.float64, device="cuda")
+    xr = torch.tensor(scenarios.hover_reference(B, N), dtype=torch.float64, device="cuda")
+    out = bad.step(st, xr)
+    torch.cuda.synchronize()
+    assert np.all(out["status"].cpu().numpy() == 2)
+    assert torch.isfinite(out["thrust"]).all()
+    ok = BatchedMPC(SystemModel(0.1), N, DEFAULT_Q, DEFAULT_R, [DEFAULT_FAULTS])
+    out2 = ok.step(st, xr)
+    torch.cuda.synchronize()
+    assert (out2["status"].cpu().numpy() == 0).mean() > 0.9
+
+
+@pytest.mark.gpu
+def test_handle_bound_to_other_device(ft, built):
+    """a controller constructed with device='cuda:1' works while cuda:0 stays the current device"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from ft_mpc_b200.controllers.spiraling_mpc import DEFAULT_Q, DEFAULT_R, BatchedMPC
+    from ft_mpc_b200.models import SystemModel
+    from ft_mpc_b200.util import scenarios
+    torch.cuda.set_device(0)
+    N, B = 15, 8
+    e0 = BatchedMPC(SystemModel(0.1), N, DEFAULT_Q, DEFAULT_R, [DEFAULT_FAULTS], device="cuda:0")
+    e1 = BatchedMPC(SystemModel(0.1), N, DEFAULT_Q, DEFAULT_R, [DEFAULT_FAULTS], device="cuda:1")
+    st, xr = scenarios.random_states(B, 5), scenarios.hover_reference(B, N)
+    o0 = e0.step(torch.tensor(st, device="cuda:0"), torch.tensor(xr, device="cuda:0"))
+    o1 = e1.step(torch.tensor(st, device="cuda:1"), torch.tensor(xr, device="cuda:1"))
+    torch.cuda.synchronize(0); torch.cuda.synchronize(1)
+    assert torch.cuda.current_device() == 0
+    assert torch.equal(o0["thrust"].cpu(), o1["thrust"].cpu()) and torch.equal(o0["status"].cpu(), o1["status"].cpu())
+
+
+def test_reference_style_solver_opts_are_accepted(ft):
+    """params['solver_opts'] holds IPOPT options in the reference (spiraling_mpc.py:227-229): they must not break construction"""
+    import inspect
+    from ft_mpc_b200 import _lib as L
+    from ft_mpc_b200.controllers import SpiralingController
+    src = inspect.getsource(SpiralingController.__init__)
+    assert "ipopt.max_iter" in src and "ftmpc_opts" in src
+    sig = inspect.signature(L.make_config)
+    assert all(name in sig.parameters for name in L.SOLVER_OPTION_NAMES)
