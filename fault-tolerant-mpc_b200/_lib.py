@@ -21,7 +21,7 @@ MAX_POLY, MAX_ROOT = 32, 16
 PHASE_NAMES = ['ls', 'lin', 'condense', 'cholesky', 'inverse', 'qp_setup', 'qp_active_set', 'qp_post', 'out',
                'ls_rollout', 'ls_eval', 'ls_terminal', 'chol_panel', 'chol_syrk', 'gi_select', 'gi_d', 'gi_z', 'gi_step', 'gi_update',
                'gi_drop', 'lin_jac', 'lin_costate', 'cond_pre', 'cond_col', 'cond_blk', 'warm_d0', 'warm_qr', 'warm_solve', 'warm_E',
-               'n_instances', 'n_sqp_iter', 'n_condense', 'n_chol_fail', 'n_qp', 'n_gi_iter', 'n_gi_drop', 'n_ls_backtrack', 'n_gi_warm_ok', 'n_gi_warm_miss']
+               'n_instances', 'n_sqp_iter', 'n_condense', 'n_chol_fail', 'n_qp', 'n_gi_iter', 'n_gi_drop', 'n_ls_backtrack', 'n_gi_warm_ok', 'n_gi_warm_miss', 'n_gi_refine']
 N_PHASES = len(PHASE_NAMES)
 N_CYCLE_PHASES = 29
 ST_OK, ST_MAXITER, ST_QPFAIL, ST_INFEASIBLE, ST_ALLOC, ST_BADINPUT = 0, 1, 2, 3, 4, 5
@@ -37,6 +37,7 @@ class FtmpcConfig(C.Structure):
     _fields_ = [
         ("horizon", C.c_int32), ("dtype", C.c_int32), ("max_sqp_iter", C.c_int32), ("max_qp_iter", C.c_int32),
         ("stall_window", C.c_int32), ("warm_qp", C.c_int32), ("n_poly", C.c_int32), ("n_root", C.c_int32), ("n_hull_sets", C.c_int32),
+        ("qp_method", C.c_int32),
         ("dt", C.c_double), ("mass", C.c_double), ("inertia", C.c_double * 3), ("r", C.c_double * 3),
         ("f_virt", C.c_double * 3), ("max_thrust", C.c_double),
         ("Q", C.c_double * NE), ("R", C.c_double * NU), ("D", C.c_double * (NU * NTHR)),
@@ -60,7 +61,8 @@ def make_config(horizon: int, Q, R, *, dt: float, mass: float, inertia, r, f_vir
                 terminal: dict | None = None, n_hull_sets: int = 1, max_sqp_iter: int = 60, max_qp_iter: int = 0,
                 stall_window: int = 10, sqp_tol: float = 1e-8, qp_tol: float = 1e-10, feas_tol: float = 1e-7,
                 act_tol: float = 1e-7, rho_slack: float = 1e4, clip_tol: float = 1e-9, theta_first: float = 0.5,
-                theta_growth: float = 2.0, blend_dmax: float = 1.0, warm_qp: int = 0, fast_dmax: float = 1e-5) -> FtmpcConfig:
+                theta_growth: float = 2.0, blend_dmax: float = 1.0, warm_qp: int = 0, fast_dmax: float = 1e-5,
+                qp_method: int = 1) -> FtmpcConfig:
     term = terminal or load_terminal()
     if len(term["poly"]) > MAX_POLY or len(term["root"]) > MAX_ROOT:
         raise ValueError("terminal cost has more terms than the term table holds")
@@ -71,6 +73,7 @@ def make_config(horizon: int, Q, R, *, dt: float, mass: float, inertia, r, f_vir
     cfg.max_qp_iter = int(max_qp_iter) if max_qp_iter else 20 * (n + m)
     cfg.stall_window = int(stall_window)
     cfg.warm_qp = int(warm_qp)
+    cfg.qp_method = int(qp_method)
     cfg.n_poly, cfg.n_root, cfg.n_hull_sets = len(term["poly"]), len(term["root"]), int(n_hull_sets)
     cfg.dt, cfg.mass, cfg.max_thrust = float(dt), float(mass), float(max_thrust)
     cfg.inertia[:] = [float(x) for x in np.diag(np.asarray(inertia, float))] if np.ndim(inertia) == 2 else list(map(float, inertia))
@@ -112,7 +115,7 @@ def make_config(horizon: int, Q, R, *, dt: float, mass: float, inertia, r, f_vir
 
 # keyword names of make_config that tune the solver (accepted in params["solver_opts"] / params["ftmpc_opts"])
 SOLVER_OPTION_NAMES = ("max_sqp_iter", "max_qp_iter", "stall_window", "sqp_tol", "qp_tol", "feas_tol", "act_tol", "rho_slack",
-                       "clip_tol", "theta_first", "theta_growth", "blend_dmax", "warm_qp", "fast_dmax")
+                       "clip_tol", "theta_first", "theta_growth", "blend_dmax", "warm_qp", "fast_dmax", "qp_method")
 
 _lib = None
 

@@ -12,11 +12,13 @@
 // There is no CPU fallback in this translation unit: without a CUDA device ftmpc_create fails.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
 #include "ftmpc.h"
 #include "ftmpc_alloc.cuh"
+#include "ftmpc_qp2.cuh"
 #include "ftmpc_plant.cuh"
 #include "ftmpc_hull.cuh"
 
@@ -34,7 +36,8 @@ struct ftmpc_ctx {
     double* d_hull;            // device hull table
     long long* d_prof;         // per-phase cycle accumulators (PH_COUNT) of the last profiled step
     int device, num_sms;
-    size_t smem_optin;
+    size_t smem_optin, smem_dyn_max, smem_dyn2_max;
+    int ctas_per_sm2;          // resident k_solve2 CTAs per SM for this horizon (occupancy query)
     WsLayout L;
     int profile, last_launches;
     cudaEvent_t ev[3];         // before k_solve / between / after k_alloc (profile mode)
@@ -89,8 +92,64 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
             if (sc[SC_STATUS] != (double)FTMPC_ST_RUNNING) break;      // uniform: written before the last barrier
             // with the shared-memory scratch the linearisation leaves Jz / Wz where condensing reads them
             const bool staged = !GS && lin_scratch_doubles(L.N) <= (size_t)(L.nv + FTMPC_NE) * L.nv && condense_fast_path(L, blockDim.x);
-            phase_lin(blk, cfg, L, io, inst, slot, scratch, staged);
+            phase_lin(blk, cfg, L, io, inst, slot, lin_place_v1(scratch, L.N, staged));
             phase_qp(blk, cfg, L, io, inst, slot, scratch, staged);
+            phase_ls_block(blk, cfg, L, io, inst, slot, 0, scratch);
+        }
+        phase_out_write(blk, cfg, L, io, inst, slot);
+    }
+}
+
+// Two CTAs per SM (<= 113 KB of shared memory, <= 128 registers per thread): range-space QP on the packed extended inverse
+// (ftmpc_qp2.cuh).  Horizons with (N + 2)(N + 3) / 2 <= 256 block threads, i.e. N <= 20.
+__global__ void __launch_bounds__(FTMPC_QP_THREADS, 2)
+    k_solve2(const __grid_constant__ ftmpc_config cfg, WsLayout L, StepIO io, int* queue, double* ovf, size_t ovf_doubles,
+             long long* prof) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(16) double red[192];
+    __shared__ int s_inst;
+    __shared__ double s_tfv[2 * FTMPC_NF];
+    __shared__ int s_tfi[2 * FTMPC_NF];
+    double* scratch = smem;
+    CudaBlock blk(red, prof);
+    const int slot = blockIdx.x;
+    const double* sc = ws_slot(io, L, slot) + L.oSc;
+    for (int i = threadIdx.x; i < FTMPC_NF; i += blockDim.x) {
+        int k = 0;
+        s_tfv[2 * i] = s_tfv[2 * i + 1] = 0.0;
+        s_tfi[2 * i] = s_tfi[2 * i + 1] = 0;
+        for (int j = 0; j < FTMPC_NE; ++j) {
+            const double a = io.cfg_g->Af[i * FTMPC_NE + j];
+            if (a != 0.0 && k < 2) { s_tfv[2 * i + k] = a; s_tfi[2 * i + k] = j; ++k; }
+        }
+    }
+    io.tf_val = s_tfv;
+    io.tf_idx = s_tfi;
+    // the linearisation works in the front of the scratch and leaves Jz / Wz where condense2 reads them
+    LinPlace lp;
+    {
+        const Qp2Scratch q = qp2_carve(scratch, L.N, io);
+        lp.work = scratch;
+        lp.JzS = q.Jz;
+        lp.WzS = q.Wz;
+        lp.tail = q.Wz + (size_t)L.N * 169;
+    }
+    __syncthreads();
+    for (;;) {
+        if (threadIdx.x == 0) s_inst = atomicAdd(queue, 1);
+        __syncthreads();
+        const int inst = s_inst;
+        __syncthreads();
+        if (inst >= io.batch) break;
+        if (!instance_input_ok(cfg, io, inst)) {
+            phase_out_invalid(blk, L, io, inst);
+            continue;
+        }
+        phase_ls_block(blk, cfg, L, io, inst, slot, 1, scratch);
+        for (int it = 0; it < cfg.max_sqp_iter; ++it) {
+            if (sc[SC_STATUS] != (double)FTMPC_ST_RUNNING) break;
+            phase_lin(blk, cfg, L, io, inst, slot, lp);
+            phase_qp2(blk, cfg, L, io, inst, slot, scratch, true, ovf + (size_t)blockIdx.x * ovf_doubles);
             phase_ls_block(blk, cfg, L, io, inst, slot, 0, scratch);
         }
         phase_out_write(blk, cfg, L, io, inst, slot);
@@ -342,6 +401,22 @@ struct DeviceGuard {
 
 static size_t qp_smem_bytes(int N) { return qp_scratch_doubles(N) * sizeof(double); }
 
+// k_solve2 (two CTAs per SM, range-space QP) covers the horizons whose block sweep fits one 256-thread CTA
+static size_t solve2_smem_bytes(int N) {
+    size_t a = qp2_scratch_doubles(N), b = ls_scratch_doubles(N);
+    const size_t c = qp2_fixed_doubles(N) + (size_t)32 * (7 * N + 1) + (size_t)N * FTMPC_NE + 90 + (26 * N + 72) + 90 + (size_t)N * 10 +
+                     2 * (size_t)N * 169 + 2 * (size_t)(N + 1) * FTMPC_NX + 8;      // linearisation tail behind Wz
+    if (b > a) a = b;
+    if (c > a) a = c;
+    return a * sizeof(double);
+}
+static bool use_solve2(const ftmpc_ctx* h) {
+    const int N = h->cfg.horizon;
+    return h->cfg.qp_method != 0 && (N + 2) * (N + 3) / 2 <= FTMPC_QP_THREADS && 6 * N <= FTMPC_QP_THREADS &&
+           (size_t)N * 326 <= qp2_fixed_doubles(N) + (size_t)32 * (7 * N + 1) + (size_t)N * FTMPC_NE + 90 + (26 * N + 72) + 90 + (size_t)N * 10 &&
+           solve2_smem_bytes(N) <= h->smem_dyn2_max;
+}
+
 
 extern "C" {
 
@@ -399,9 +474,31 @@ int ftmpc_create(ftmpc_handle* out, const ftmpc_config* cfg, const double* hull_
     for (int i = 0; i < 3; ++i) CREATE_TRY(cudaEventCreate(&h->ev[i]));
     // dynamic shared memory opt-in, once per handle: the attribute is per function and per device, so it is raised to the
     // device maximum (every horizon whose scratch fits uses the same kernel instantiation)
-    CREATE_TRY(cudaFuncSetAttribute(k_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
-    CREATE_TRY(cudaFuncSetAttribute(k_condense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
-    CREATE_TRY(cudaFuncSetAttribute(k_qp_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_optin));
+    {
+        const void* fns[3] = {(const void*)k_solve<false>, (const void*)k_condense, (const void*)k_qp_generic};
+        for (int i = 0; i < 3; ++i) {               // the opt-in limit covers static + dynamic shared memory of a block
+            cudaFuncAttributes fa;
+            CREATE_TRY(cudaFuncGetAttributes(&fa, fns[i]));
+            const int dyn = (int)h->smem_optin - (int)fa.sharedSizeBytes;
+            CREATE_TRY(cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+            if (i == 0) h->smem_dyn_max = (size_t)dyn;
+        }
+        cudaFuncAttributes fa;
+        CREATE_TRY(cudaFuncGetAttributes(&fa, (const void*)k_solve2));
+        h->smem_dyn2_max = h->smem_optin - fa.sharedSizeBytes;
+        CREATE_TRY(cudaFuncSetAttribute((const void*)k_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_dyn2_max));
+        CREATE_TRY(cudaFuncSetAttribute((const void*)k_solve2, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        h->ctas_per_sm2 = 1;
+        if (use_solve2(h)) {
+            int nb = 0;
+            CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve2, FTMPC_QP_THREADS, solve2_smem_bytes(cfg->horizon)));
+            h->ctas_per_sm2 = nb < 1 ? 1 : nb;
+            if (const char* e = std::getenv("FTMPC_CTAS_PER_SM")) {      // experiments: fewer resident CTAs than the SM would take
+                const int v = std::atoi(e);
+                if (v >= 1 && v < h->ctas_per_sm2) h->ctas_per_sm2 = v;
+            }
+        }
+    }
 #undef CREATE_TRY
     *out = h;
     return FTMPC_OK;
@@ -456,7 +553,10 @@ static size_t solve_smem_bytes(int N) {
     return a * sizeof(double);
 }
 
-static int solve_grid(const ftmpc_ctx* h, int batch) { return batch < h->num_sms ? batch : h->num_sms; }
+static int solve_grid(const ftmpc_ctx* h, int batch) {
+    const int cap = use_solve2(h) ? h->ctas_per_sm2 * h->num_sms : h->num_sms;
+    return batch < cap ? batch : cap;
+}
 
 int ftmpc_workspace_bytes(ftmpc_handle h, int batch, size_t* out) {
     if (!h || !out || batch < 1) return FTMPC_ERR_ARG;
@@ -464,7 +564,8 @@ int ftmpc_workspace_bytes(ftmpc_handle h, int batch, size_t* out) {
     const int grid = solve_grid(h, batch);
     size_t b = align_up(h->L.stride * sizeof(double) * (size_t)grid, 256);
     const size_t need = solve_smem_bytes(h->cfg.horizon);
-    if (need > h->smem_optin) b += align_up(need, 256) * (size_t)grid;
+    if (use_solve2(h)) b += align_up(qp2_overflow_doubles(h->cfg.horizon) * sizeof(double), 256) * (size_t)grid;
+    else if (need > h->smem_optin) b += align_up(need, 256) * (size_t)grid;
     b += 256;      // work-queue head of the launch: it lives in the caller's workspace, so steps with different workspaces
                    // may be in flight on different streams at the same time (pipelined batches)
     *out = b;
@@ -475,6 +576,24 @@ int ftmpc_workspace_bytes(ftmpc_handle h, int batch, size_t* out) {
 static int launch_step(ftmpc_ctx* h, const StepIO& io, void* workspace, size_t need_ws, cudaStream_t stream) {
     const WsLayout L = h->L;
     const int grid = solve_grid(h, io.batch);
+    if (use_solve2(h)) {
+        const size_t ovf_bytes = align_up(qp2_overflow_doubles(h->cfg.horizon) * sizeof(double), 256);
+        double* ovf = (double*)((char*)workspace + align_up(L.stride * sizeof(double) * (size_t)grid, 256));
+        int* queue = (int*)((char*)workspace + need_ws - 256);
+        CU(cudaMemsetAsync(queue, 0, sizeof(int), stream));
+        if (h->profile) {
+            CU(cudaMemsetAsync(h->d_prof, 0, PH_COUNT * sizeof(long long), stream));
+            CU(cudaEventRecord(h->ev[0], stream));
+        }
+        k_solve2<<<grid, FTMPC_QP_THREADS, solve2_smem_bytes(h->cfg.horizon), stream>>>(h->cfg, L, io, queue, ovf, ovf_bytes / sizeof(double),
+                                                                                         h->profile ? h->d_prof : nullptr);
+        if (h->profile) CU(cudaEventRecord(h->ev[1], stream));
+        k_alloc<<<(io.batch + 63) / 64, 64, 0, stream>>>(h->cfg, L, io);
+        if (h->profile) CU(cudaEventRecord(h->ev[2], stream));
+        h->last_launches = 2;
+        CU(cudaGetLastError());
+        return FTMPC_OK;
+    }
     const size_t smem = solve_smem_bytes(h->cfg.horizon);
     const bool use_global = smem > h->smem_optin;
     double* gscratch = use_global ? (double*)((char*)workspace + align_up(L.stride * sizeof(double) * (size_t)grid, 256)) : nullptr;

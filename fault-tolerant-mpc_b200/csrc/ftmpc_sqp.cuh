@@ -16,6 +16,10 @@
 #include "ftmpc_block.cuh"
 #include "ftmpc_dyn.cuh"
 #include "ftmpc_gi.cuh"
+#include "ftmpc_gis.cuh"
+#if !defined(__CUDACC__)
+#include <vector>
+#endif
 #include "ftmpc_linalg.cuh"
 #include "ftmpc_terminal.cuh"
 
@@ -327,12 +331,16 @@ FT_HD void phase_ls(const ftmpc_config& cfg, const WsLayout& L, const StepIO& io
 //      case ends here), otherwise for the remaining step lengths warp-per-alpha;
 //   C. the first step length passing the Armijo test is committed.
 #define FTMPC_LS_NALPHA 28
+// The rollouts of the step lengths are kept in shared memory FTMPC_LS_CHUNK at a time (alpha = 2^-a lives in slot a % CHUNK):
+// the first chunk holds 2^0 .. 2^-11, which covers every accepted step but a handful per million; later chunks are only
+// rolled out when all of the previous one were rejected.  Same acceptance rule (first = largest passing step length).
+#define FTMPC_LS_CHUNK 12
 struct LsScratch {
     double *Xs, *Ws, *fa, *csa, *cma, *hull, *U, *D, *xref, *uref, *rec, *out;
     int xs_stride, ws_stride;
 };
 __host__ __device__ inline size_t ls_scratch_doubles(int N) {
-    return (size_t)FTMPC_LS_NALPHA * ((N + 1) * FTMPC_NX + 1 + N * FTMPC_NU + 1) + 96 + FTMPC_HULL_STRIDE +
+    return (size_t)FTMPC_LS_CHUNK * ((N + 1) * FTMPC_NX + 1 + N * FTMPC_NU + 1) + 96 + FTMPC_HULL_STRIDE +
            2 * (size_t)(FTMPC_NU * N + 1) + (size_t)(N + 1) * (FTMPC_NE + FTMPC_NU) +
            (size_t)(FTMPC_MAX_POLY + FTMPC_MAX_ROOT) * FTMPC_TERM_REC + FTMPC_TERM_REC + 8;
 }
@@ -341,8 +349,8 @@ __device__ __forceinline__ LsScratch ls_carve(double* buf, int N) {
     s.xs_stride = (N + 1) * FTMPC_NX + 1;          // odd strides: lanes of warp 0 hit different banks
     s.ws_stride = N * FTMPC_NU + 1;
     double* p = buf;
-    s.Xs = p; p += (size_t)FTMPC_LS_NALPHA * s.xs_stride;
-    s.Ws = p; p += (size_t)FTMPC_LS_NALPHA * s.ws_stride;
+    s.Xs = p; p += (size_t)FTMPC_LS_CHUNK * s.xs_stride;
+    s.Ws = p; p += (size_t)FTMPC_LS_CHUNK * s.ws_stride;
     s.fa = p; p += 32;
     s.csa = p; p += 32;
     s.cma = p; p += 32;
@@ -547,11 +555,16 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
     // A. rollouts, one step length per lane
     const int nalpha = first ? 1 : FTMPC_LS_NALPHA;
     const bool conv = first && uref_g;              // accelerating reference: U still holds u (warm start), see FTMPC_CQ
-    // A1. attitude chains, one step length per lane of warp 0
-    if (warp == 0 && lane < nalpha)
-        rollout_attitude(cfg, N, s.U, s.D, first ? 0.0 : ldexp(1.0, -lane), conv ? s.uref : nullptr, X,
-                         s.Xs + (size_t)lane * s.xs_stride);
-    blk.sync();
+    auto slot_x = [&](int a) { return s.Xs + (size_t)(a % FTMPC_LS_CHUNK) * s.xs_stride; };
+    auto slot_w = [&](int a) { return s.Ws + (size_t)(a % FTMPC_LS_CHUNK) * s.ws_stride; };
+    // A1. attitude chains of the step lengths [base, base + CHUNK), one per lane of warp 0
+    auto attitude_chunk = [&](int base) {
+        const int a = base + lane;
+        if (warp == 0 && lane < FTMPC_LS_CHUNK && a < nalpha)
+            rollout_attitude(cfg, N, s.U, s.D, first ? 0.0 : ldexp(1.0, -a), conv ? s.uref : nullptr, X, slot_x(a));
+        blk.sync();
+    };
+    attitude_chunk(0);
     // A2-A4 for the step lengths [a0, a1): stage tasks spread over the warps (task k runs on lane k / nw of warp k % nw, so a
     // handful of tasks costs one pass of one lane per warp), (p, v) scan per component, cost per step length
     double* stage_cost = s.rec;                     // [nalpha][N], free until the terminal records are built
@@ -561,13 +574,12 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
         for (int idx = lane * nw + warp; idx < ntask; idx += nt) {
             const int a = a0 + idx / N, t = idx - (a - a0) * N;
             rollout_stage_task(cfg, t, s.xref, uref_g ? s.uref : nullptr, s.U, s.D, first ? 0.0 : ldexp(1.0, -a),
-                               s.Xs + (size_t)a * s.xs_stride, s.Ws + (size_t)a * s.ws_stride, stage_cost + a * N + t,
-                               conv ? s.U : nullptr, U);
+                               slot_x(a), slot_w(a), stage_cost + a * N + t, conv ? s.U : nullptr, U);
         }
         blk.sync();
         for (int idx = tid; idx < 3 * (a1 - a0); idx += nt) {
             const int a = a0 + idx / 3, c = idx - (a - a0) * 3;
-            pv_cost[a * 3 + c] = rollout_scan(cfg, N, c, s.xref, s.Xs + (size_t)a * s.xs_stride);
+            pv_cost[a * 3 + c] = rollout_scan(cfg, N, c, s.xref, slot_x(a));
         }
         blk.sync();
         for (int a = a0 + tid; a < a1; a += nt) {
@@ -613,47 +625,51 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
     }
     blk.sync();
     if (win < 0) {
-        rollout_rest(1, nalpha);                      // translations of the other step lengths (their attitude chains exist)
-        // B1. the remaining step lengths: rows one warp per alpha, terminal cost one thread per (alpha, term)
-        for (int idx = tid; idx < (nalpha - 1) * nterm; idx += nt) {
-            const int a = 1 + idx / nterm, k = idx - (a - 1) * nterm;
-            const double* Xa = s.Xs + (size_t)a * s.xs_stride;
-            double e[FTMPC_NE];
+        for (int base = 0; base < nalpha && win < 0; base += FTMPC_LS_CHUNK) {
+            if (base > 0) attitude_chunk(base);       // (the attitude chains of the first chunk exist)
+            const int a_lo = base > 1 ? base : 1, a_hi = (base + FTMPC_LS_CHUNK < nalpha) ? base + FTMPC_LS_CHUNK : nalpha;
+            rollout_rest(a_lo, a_hi);                 // translations of these step lengths
+            // B1. rows one warp per alpha, terminal cost one thread per (alpha, term)
+            for (int idx = tid; idx < (a_hi - a_lo) * nterm; idx += nt) {
+                const int a = a_lo + idx / nterm, k = idx - (a - a_lo) * nterm;
+                const double* Xa = slot_x(a);
+                double e[FTMPC_NE];
 #pragma unroll
-            for (int j = 0; j < FTMPC_NE; ++j) e[j] = Xa[N * FTMPC_NX + j] - xrefN[j];
-            s.rec[(size_t)a * (FTMPC_MAX_POLY + FTMPC_MAX_ROOT) + k] = term_eval(term_desc(cg, k), e, nullptr);
-        }
-        for (int a = 1 + warp; a < nalpha; a += nw) {
-            const double* Xa = s.Xs + (size_t)a * s.xs_stride;
-            const double* Wa = s.Ws + (size_t)a * s.ws_stride;
-            double cs = 0.0, cm = 0.0;
-            for (int p = lane; p < L.mc; p += 32) {
-                const double v = cons_value(cg, N, s.hull, xrefN, Xa, Wa, p);
-                if (v > 0.0) { cs += v; cm = fmax(cm, v); }
+                for (int j = 0; j < FTMPC_NE; ++j) e[j] = Xa[N * FTMPC_NX + j] - xrefN[j];
+                s.rec[(size_t)a * (FTMPC_MAX_POLY + FTMPC_MAX_ROOT) + k] = term_eval(term_desc(cg, k), e, nullptr);
             }
-            for (int o = 16; o > 0; o >>= 1) {
-                cs += __shfl_xor_sync(0xffffffffu, cs, o);
-                cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+            for (int a = a_lo + warp; a < a_hi; a += nw) {
+                const double* Xa = slot_x(a);
+                const double* Wa = slot_w(a);
+                double cs = 0.0, cm = 0.0;
+                for (int p = lane; p < L.mc; p += 32) {
+                    const double v = cons_value(cg, N, s.hull, xrefN, Xa, Wa, p);
+                    if (v > 0.0) { cs += v; cm = fmax(cm, v); }
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    cs += __shfl_xor_sync(0xffffffffu, cs, o);
+                    cm = fmax(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+                }
+                if (lane == 0) { s.csa[a] = cs; s.cma[a] = cm; }
             }
-            if (lane == 0) { s.csa[a] = cs; s.cma[a] = cm; }
-        }
-        blk.sync();
-        if (tid >= 1 && tid < nalpha) {
-            double v = 0.0;
-            for (int k = 0; k < nterm; ++k) v += s.rec[(size_t)tid * (FTMPC_MAX_POLY + FTMPC_MAX_ROOT) + k];
-            double f = s.fa[tid] + cfg.term_const + v, cs = s.csa[tid];
-            if (!(f == f) || !(cs == cs)) { f = INFINITY; cs = INFINITY; }
-            s.fa[tid] = f; s.csa[tid] = cs;
-        }
-        blk.sync();
-        for (int a = 1; a < nalpha && win < 0; ++a) {
-            const double alpha = ldexp(1.0, -a);
-            if (s.fa[a] + nu * s.csa[a] <= phi0 + 1e-4 * alpha * dphi || alpha < 1e-8) win = a;
+            blk.sync();
+            if (tid >= a_lo && tid < a_hi) {
+                double v = 0.0;
+                for (int k = 0; k < nterm; ++k) v += s.rec[(size_t)tid * (FTMPC_MAX_POLY + FTMPC_MAX_ROOT) + k];
+                double f = s.fa[tid] + cfg.term_const + v, cs = s.csa[tid];
+                if (!(f == f) || !(cs == cs)) { f = INFINITY; cs = INFINITY; }
+                s.fa[tid] = f; s.csa[tid] = cs;
+            }
+            blk.sync();
+            for (int a = a_lo; a < a_hi && win < 0; ++a) {
+                const double alpha = ldexp(1.0, -a);
+                if (s.fa[a] + nu * s.csa[a] <= phi0 + 1e-4 * alpha * dphi || alpha < 1e-8) win = a;
+            }
+            blk.sync();                               // the per-alpha term values have been consumed
         }
         // constraint values and terminal records of the accepted step
-        const double* Xa = s.Xs + (size_t)win * s.xs_stride;
-        const double* Wa = s.Ws + (size_t)win * s.ws_stride;
-        blk.sync();                                   // the per-alpha term values have been consumed
+        const double* Xa = slot_x(win);
+        const double* Wa = slot_w(win);
         for (int p = tid; p < L.mc; p += nt) C[p] = cons_value(cg, N, s.hull, xrefN, Xa, Wa, p);
         if (tid < nterm) {
             double e[FTMPC_NE];
@@ -678,7 +694,7 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
     const double f = s.fa[win], csum = s.csa[win], cmax = s.cma[win];
     const bool finite = f < INFINITY;
     if (!first && finite) for (int i = tid; i < L.n; i += nt) U[i] = s.U[i] + alpha * s.D[i];
-    const double* Xa = s.Xs + (size_t)win * s.xs_stride;
+    const double* Xa = slot_x(win);
     if (finite) for (int i = tid; i < (N + 1) * FTMPC_NX; i += nt) X[i] = Xa[i];
     if (finite || first) {                            // terminal gradient / Hessian at the accepted point
         for (int i = tid; i < FTMPC_NE; i += nt) w[L.oGV + i] = s.out[1 + i];
@@ -1108,8 +1124,16 @@ __device__ __noinline__ void lin_reverse_task(const DynConsts& k, const double* 
     rk4_col_reverse(k, nom, tang, tstride, col, lam, hess_col);
 }
 
+// LinPlace: where the phase keeps its own scratch and where it leaves the stage Jacobians / Hessians for the condensing
+// that follows (JzS / WzS = nullptr: only the global backing copies are written)
+struct LinPlace {
+    double* work;      // nom, wr, tang  (N * 326 doubles)
+    double* tail;      // mu, X          (2 (N + 1) * 13 doubles)
+    double* JzS;       // N * 169, always in shared memory (the costate recursion reads it)
+    double* WzS;       // N * 169 or nullptr
+};
 __device__ __forceinline__ void phase_lin(CudaBlock& blk, const ftmpc_config& cfg, const WsLayout& L, const StepIO& io,
-                                          int inst, int slot, double* scratch, bool stage_rs) {
+                                          int inst, int slot, const LinPlace& place) {
     double* w = ws_slot(io, L, slot);
     const double* sc = w + L.oSc;
     if (sc[SC_STATUS] != FTMPC_ST_RUNNING) return;
@@ -1123,13 +1147,14 @@ __device__ __forceinline__ void phase_lin(CudaBlock& blk, const ftmpc_config& cf
     double* Wz = w + L.oWz;
     double* Mu = w + L.oMu;
     const double* lam = w + L.oLam;
-    LinScratch s = lin_carve(scratch, N);
-    double* WzS = nullptr;
-    if (stage_rs) {                              // leave Jz / Wz where condense expects them (RS region of the QP scratch)
-        const QpScratch q = qp_carve(scratch, N);
-        s.Jz = q.RS;
-        WzS = q.RS + (size_t)N * 169;
-    }
+    LinScratch s;
+    s.nom = place.work;
+    s.wr = s.nom + (size_t)N * 40;
+    s.tang = s.wr + (size_t)N * 6;
+    s.mu = place.tail;
+    s.X = s.mu + (size_t)(N + 1) * FTMPC_NX;
+    s.Jz = place.JzS;
+    double* WzS = place.WzS;
     const int ntask = 10 * N;
     // stage states and wrenches -> shared memory
     for (int i = tid; i < (N + 1) * FTMPC_NX; i += nt) s.X[i] = X[i];
@@ -1233,6 +1258,22 @@ __device__ __forceinline__ void phase_lin(CudaBlock& blk, const ftmpc_config& cf
     blk.mark(PH_LIN);
 }
 #endif  // __CUDACC__
+
+#if defined(__CUDACC__)
+// scratch placement of the linearisation inside k_solve (one CTA per SM): own layout, Jz / Wz optionally left in the RS
+// region of the QP scratch
+__device__ __forceinline__ LinPlace lin_place_v1(double* scratch, int N, bool stage_rs) {
+    const LinScratch l = lin_carve(scratch, N);
+    LinPlace p;
+    p.work = l.nom; p.tail = l.mu; p.JzS = l.Jz; p.WzS = nullptr;
+    if (stage_rs) {
+        const QpScratch q = qp_carve(scratch, N);
+        p.JzS = q.RS;
+        p.WzS = q.RS + (size_t)N * 169;
+    }
+    return p;
+}
+#endif
 
 #if defined(__CUDACC__)
 // ---- condensing, CUDA-block specialisation -----------------------------------------------------------------
@@ -1899,6 +1940,28 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     blk.count(CT_QP);
     int qit1 = 0;
     // the previous multipliers are still needed if this attempt is rejected: the QP writes to the spare copy
+#if !defined(__CUDACC__)
+    if (cfg.qp_method == 2) {
+        // range-space form, host prototype: K = E E' (packed) from the dense E the null-space set-up built
+        const int qcap = 80;
+        std::vector<double> Kp((size_t)ne * (ne + 1) / 2), Ui((size_t)qcap * (qcap + 1) / 2 + 1), vec((size_t)3 * ne + 8 * (qcap + 2));
+        std::vector<int> iv(2 * (qcap + 2));
+        for (int i = 0; i < ne; ++i)
+            for (int j = 0; j <= i; ++j) {
+                double a = 0.0;
+                for (int k = 0; k < nv; ++k) a += s.E[(size_t)i * ld + k] * s.E[(size_t)j * ld + k];
+                Kp[(size_t)i * (i + 1) / 2 + j] = a;
+            }
+        GisWork gw;
+        double* v = vec.data();
+        gw.K = Kp.data(); gw.Ui = Ui.data(); gw.xe = s.gi.xe; gw.s = s.gi.s;
+        gw.ye = v; v += ne; gw.ze = v; v += ne; gw.c = v; v += ne;
+        gw.u = v; v += qcap + 2; gw.w = v; v += qcap + 2; gw.v = v; v += qcap + 2; gw.r = v; v += qcap + 2;
+        gw.cs = v; v += 2 * (qcap + 2); gw.tmp = v; v += qcap + 2; gw.sub = v; v += qcap + 2;
+        gw.act = iv.data(); gw.itmp = iv.data() + qcap + 2; gw.pos = s.gi.pos; gw.qcap = qcap;
+        st = gis_solve(blk, cons, gw, ne, L.m, w + L.oLam + L.m, cfg.max_qp_iter, cfg.qp_tol, &qit1, &nact);
+    } else
+#endif
     st = gi_solve(blk, cons, s.gi, nv, ne, ld, L.m, 0, w + L.oLam + L.m, cfg.max_qp_iter, cfg.qp_tol, &qit1, &nact,
                   (cfg.warm_qp != 0 && sc[SC_ITER] > 0.0 && sc[SC_DMAX] <= 1.0) ? lam_prev : nullptr, L.mc);    // hit rate 4 % above |d| = 1
     have_j = false;                     // R^-1 has overwritten the staged Jacobians

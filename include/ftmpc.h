@@ -67,6 +67,10 @@ typedef struct ftmpc_config {
     int32_t warm_qp;           /* 1 = start each QP from the previous QP's active set (gi_warm_start): -40 % active-set iterations, same
                                   results; default 0 -- on the B200 the bulk update currently costs what it saves (profiles/README.md) */
     int32_t n_poly, n_root, n_hull_sets;
+    int32_t qp_method;         /* 0 = null-space form of the dual active-set QP (J = L^-T Q rotated in shared memory, ftmpc_gi.cuh), one
+                                      CTA per SM;  1 (default) = range-space form on the packed extended inverse K (ftmpc_qp2.cuh /
+                                      ftmpc_gis.cuh), two CTAs per SM, for horizons N <= 20 (longer ones fall back to 0);
+                                  2 = as 1, and the CPU checker (oracle/cpu_port) runs its range-space prototype too          */
     double dt, mass, inertia[3], r[3], f_virt[3], max_thrust;   /* sys_model.py:52-61, spiral_parameters.py:33-39 */
     double Q[FTMPC_NE], R[FTMPC_NU];                            /* reactive.yaml:32-33                      */
     double D[FTMPC_NU * FTMPC_NTHR];                            /* allocation matrix, sys_model.py:73-123   */
@@ -141,7 +145,7 @@ int ftmpc_closed_loop(ftmpc_handle h, int batch, int steps, int start_step, int 
  * phase_cycles[i] = SM cycles summed over all CTAs spent in phase i:
  *   0 step acceptance + rollout, 1 linearisation (Jacobians, costates, stage Hessians), 2 condensing, 3 Cholesky,
  *   4 J = L^-T, 5 QP set-up, 6 dual active-set iterations, 7 QP post-processing, 8 result write-out. */
-#define FTMPC_N_PHASES 39   /* 9 coarse phases, 20 sub-phases, 10 event counters: names in ft_mpc_b200._lib.PHASE_NAMES */
+#define FTMPC_N_PHASES 40   /* 9 coarse phases, 20 sub-phases, 11 event counters: names in ft_mpc_b200._lib.PHASE_NAMES */
 int ftmpc_profile_enable(ftmpc_handle h, int enable);
 int ftmpc_profile_read(ftmpc_handle h, void* stream, double* kernel_ms, int64_t* phase_cycles, int n_phase);
 /* number of kernels ftmpc_step launched on its last call */

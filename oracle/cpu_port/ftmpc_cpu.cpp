@@ -13,7 +13,7 @@
 #include <omp.h>
 #endif
 #define FTMPC_DEBUG_COUNTERS 1
-namespace ftmpc { long g_ftmpc_dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long g_ftmpc_dbg2[8] = {0, 0, 0, 0, 0, 0, 0, 0}; thread_local int g_ftmpc_warm_hit = 0; }
+namespace ftmpc { long g_ftmpc_dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long g_ftmpc_dbg2[8] = {0, 0, 0, 0, 0, 0, 0, 0}; thread_local int g_ftmpc_warm_hit = 0; long g_ftmpc_qmax_hist[16] = {0}; }
 #include "ftmpc_alloc.cuh"
 using namespace ftmpc;
 
@@ -113,6 +113,8 @@ int ftmpc_cpu_clip(const ftmpc_config* cfg, int batch, const double* hull_table,
         status[b] = clip_to_hull(*cfg, hull_table + (size_t)hull_idx[b] * FTMPC_HULL_STRIDE, u + b * 6, out + b * 6);
     return 0;
 }
+
+void ftmpc_cpu_qmax_hist(long* out) { for (int i = 0; i < 16; ++i) out[i] = ftmpc::g_ftmpc_qmax_hist[i]; }
 
 void ftmpc_cpu_debug_counters(long* out, int reset) {
     for (int i = 0; i < 8; ++i) { out[i] = ftmpc::g_ftmpc_dbg[i]; if (reset) ftmpc::g_ftmpc_dbg[i] = 0; }

@@ -3,7 +3,7 @@
 profiles/:  <tag>_bench.json, <tag>_launches.csv + <tag>_launch_shares.txt, <tag>_k_solve_ncu_full_summary.csv,
 <tag>_k_solve_stalls_by_source.txt (warp-stall samples of the full capture attributed to source lines / barrier call
 sites) and traffic.json (DRAM bytes of the captured launch, read by bench.py for roofline.traffic).
-Usage: python tools/summarise_profile.py <tag> [instances_in_capture]"""
+Usage: python tools/summarise_profile.py <tag> [instances_in_capture] [mangled kernel prefix]"""
 import collections, csv, io, json, re, shutil, subprocess, sys
 from pathlib import Path
 
@@ -72,7 +72,7 @@ def full(tag, instances):
     tmp = Path("/tmp/ftmpc_sass"); shutil.rmtree(tmp, ignore_errors=True); tmp.mkdir()
     subprocess.run(["cuobjdump", "-xelf", "all", str(lib)], cwd=tmp, capture_output=True)
     sass = subprocess.run(["nvdisasm", "-g", "-c", str(next(tmp.glob("*.cubin")))], capture_output=True, text=True).stdout
-    kname = "_Z7k_solveILb0EE"
+    kname = KNAME
     off2src, cur, on = {}, None, False
     for l in sass.splitlines():
         if l.startswith(".text."):
@@ -117,13 +117,17 @@ def full(tag, instances):
     lines.append(f"  total stall_barrier: {100 * sum(o[2] for o in offs) / total:.1f} %")
     lines += ["", "source lines by samples (innermost inlined frame), top stall reasons:"]
     for k, s in per_line.most_common(30):
-        top = ", ".join(f"{n.replace('stall_', '')} {100 * v / max(s, 1):.0f}%" for n, v in per_stall[k].most_common(3))
+        top = ", ".join(f"{n.replace('stall_', '')} {100 * v / max(s, 1):.0f}%" for n, v in per_stall[k].most_common(4))
         lines.append(f"  {100 * s / total:5.2f} %  {k[0] if k else '?'}:{k[1] if k else 0}   [{top}]")
     (PROF / f"{tag}_k_solve_stalls_by_source.txt").write_text("\n".join(lines) + "\n")
 
 
+KNAME = "_Z8k_solve2"          # mangled prefix of the captured kernel (k_solve<false>: "_Z7k_solveILb0EE")
+
 if __name__ == "__main__":
     tag = sys.argv[1]
+    if len(sys.argv) > 3:
+        KNAME = sys.argv[3]
     inst = int(sys.argv[2]) if len(sys.argv) > 2 else 592
     PROF.mkdir(exist_ok=True)
     b = OUT / f"bench_{tag}.json"
