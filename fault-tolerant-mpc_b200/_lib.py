@@ -62,7 +62,7 @@ def make_config(horizon: int, Q, R, *, dt: float, mass: float, inertia, r, f_vir
                 stall_window: int = 10, sqp_tol: float = 1e-8, qp_tol: float = 1e-10, feas_tol: float = 1e-7,
                 act_tol: float = 1e-7, rho_slack: float = 1e4, clip_tol: float = 1e-9, theta_first: float = 0.5,
                 theta_growth: float = 2.0, blend_dmax: float = 1.0, warm_qp: int = 0, fast_dmax: float = 1e-5,
-                qp_method: int = 1) -> FtmpcConfig:
+                qp_method: int = 0) -> FtmpcConfig:
     term = terminal or load_terminal()
     if len(term["poly"]) > MAX_POLY or len(term["root"]) > MAX_ROOT:
         raise ValueError("terminal cost has more terms than the term table holds")

@@ -68,7 +68,7 @@ typedef struct ftmpc_config {
                                   results; default 0 -- on the B200 the bulk update currently costs what it saves (profiles/README.md) */
     int32_t n_poly, n_root, n_hull_sets;
     int32_t qp_method;         /* 0 = null-space form of the dual active-set QP (J = L^-T Q rotated in shared memory, ftmpc_gi.cuh), one
-                                      CTA per SM;  1 (default) = range-space form on the packed extended inverse K (ftmpc_qp2.cuh /
+                                      CTA per SM (default);  1 = range-space form on the packed extended inverse K (ftmpc_qp2.cuh /
                                       ftmpc_gis.cuh), two CTAs per SM, for horizons N <= 20 (longer ones fall back to 0);
                                   2 = as 1, and the CPU checker (oracle/cpu_port) runs its range-space prototype too          */
     double dt, mass, inertia[3], r[3], f_virt[3], max_thrust;   /* sys_model.py:52-61, spiral_parameters.py:33-39 */

@@ -348,3 +348,55 @@ def test_reference_style_solver_opts_are_accepted(ft):
     assert "ipopt.max_iter" in src and "ftmpc_opts" in src
     sig = inspect.signature(L.make_config)
     assert all(name in sig.parameters for name in L.SOLVER_OPTION_NAMES)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# k_solve2 (qp_method = 1: two CTAs per SM, range-space QP on the packed extended inverse)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [15, 20])
+def test_range_space_kernel_vs_golden(ft, oracle, built, golden, bench_golden, N):
+    """same bar as test_step_vs_golden for the second solver kernel: u0 1e-5 relative, active-set bits identical,
+    thrust 2e-5 on every feasible cold-start golden of this horizon"""
+    import torch
+    from ft_mpc_b200.controllers.spiraling_mpc import DEFAULT_Q, DEFAULT_R, BatchedMPC
+    from ft_mpc_b200.models import SystemModel
+    for g in ([golden, bench_golden] if N == 20 else [golden]):
+        ks = [k for k in H.cases_with_horizon(g, N) if not g["warm"][k]]
+        sets, scen = H.gather_cases(g, ks)
+        eng = BatchedMPC(SystemModel(0.1), N, DEFAULT_Q, DEFAULT_R, sets, qp_method=1)
+        d = lambda a, t=torch.float64: torch.tensor(np.ascontiguousarray(a), dtype=t, device="cuda")
+        out = eng.step(d(g["x0"][ks]), d(g["xref"][ks][:, :N + 1]), scenario=d(scen, torch.int64))
+        torch.cuda.synchronize()
+        o = {k: v.cpu().numpy() for k, v in out.items() if k != "ws"}
+        assert (o["status"] == 0).all(), o["status"]
+        for j, k in enumerate(ks):
+            u0 = g["U"][k, 0]
+            assert np.abs(o["u0"][j] - u0).max() <= 1e-5 * max(1.0, np.abs(u0).max()), g["name"][k]
+            assert H.active_bits(o["active"][j].view(np.uint32), 26 * N + 72) == H.active_bits(g["active"][k], 26 * N + 72), g["name"][k]
+            assert np.allclose(o["thrust"][j], g["thrust"][k], atol=2e-5), g["name"][k]
+
+
+@pytest.mark.gpu
+def test_range_space_kernel_matches_null_space_kernel(ft, built):
+    """1024 bench-workload instances through both kernels: same statuses, same active sets, u0 / thrust to rounding"""
+    import sys
+    import torch
+    sys.path.insert(0, str(ROOT))
+    import bench
+    from ft_mpc_b200.controllers.spiraling_mpc import DEFAULT_Q, DEFAULT_R, BatchedMPC
+    from ft_mpc_b200.models import SystemModel
+    N, B = 20, 1024
+    cells, states, scen, xref = bench.make_workload(B, N)
+    d = lambda a, t=torch.float64: torch.tensor(np.ascontiguousarray(a), dtype=t, device="cuda")
+    res = []
+    for method in (0, 1):
+        eng = BatchedMPC(SystemModel(0.1), N, DEFAULT_Q, DEFAULT_R, cells, qp_method=method)
+        out = eng.step(d(states), d(xref), scenario=d(scen, torch.int64))
+        torch.cuda.synchronize()
+        res.append({k: v.cpu().numpy() for k, v in out.items() if k != "ws"})
+    a, b = res
+    ok = (a["status"] == 0) & (b["status"] == 0)
+    assert ok.mean() > 0.995 and (a["status"] == b["status"]).mean() > 0.998
+    assert np.abs(a["u0"] - b["u0"])[ok].max() < 5e-6 and np.abs(a["thrust"] - b["thrust"])[ok].max() < 5e-6
+    assert np.array_equal(a["active"][ok], b["active"][ok])
