@@ -104,6 +104,18 @@ FT_HD void phase_out_write(Blk& blk, const ftmpc_config& cfg, const WsLayout& L,
     const double* U = w + L.oU;
     const double* X = w + L.oX;
     const double* C = w + L.oC;
+    if ((int)sc[SC_STATUS] == FTMPC_ST_REDO && io.redo) {
+        // handed over to the null-space kernel: nothing is written (the warm-start input must stay intact), the id is queued
+        if (tid == 0) {
+#if defined(__CUDA_ARCH__)
+            const int k = atomicAdd(io.redo, 1);
+            io.redo[1 + k] = inst;
+#endif
+            io.status[inst] = FTMPC_ST_REDO;
+        }
+        blk.sync();
+        return;
+    }
     // optimal decision vector, reference layout [u | x]   (spiraling_mpc.py:110-114)
     double* zw = io.z_warm + (size_t)inst * (L.n + (size_t)(N + 1) * FTMPC_NX);
     const double* uref = io.uref ? io.uref + (size_t)inst * io.uref_stride : nullptr;
@@ -136,6 +148,7 @@ FT_HD void phase_out_write(Blk& blk, const ftmpc_config& cfg, const WsLayout& L,
     if (tid == 0) {
         int status = (int)sc[SC_STATUS];
         if (status == FTMPC_ST_RUNNING) status = FTMPC_ST_MAXITER;
+        if (status == FTMPC_ST_REDO) status = FTMPC_ST_QPFAIL;          // (no second pass configured)
         io.status[inst] = status;
         io.iters[2 * inst] = (int)sc[SC_ITER];
         io.iters[2 * inst + 1] = (int)sc[SC_QPIT];

@@ -78,11 +78,15 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
     io.tf_idx = s_tfi;
     __syncthreads();
     for (;;) {
-        if (threadIdx.x == 0) s_inst = atomicAdd(queue, 1);
+        if (threadIdx.x == 0) {
+            const int k = atomicAdd(queue, 1);
+            const int lim = io.batch_dev ? *io.batch_dev : io.batch;       // second pass behind k_solve2: device-side list
+            s_inst = (k < lim) ? (io.inst_list ? io.inst_list[k] : k) : -1;
+        }
         __syncthreads();
         const int inst = s_inst;
         __syncthreads();
-        if (inst >= io.batch) break;
+        if (inst < 0) break;
         if (!instance_input_ok(cfg, io, inst)) {                   // uniform over the block
             phase_out_invalid(blk, L, io, inst);
             continue;
@@ -103,8 +107,7 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
 // Two CTAs per SM (<= 113 KB of shared memory, <= 128 registers per thread): range-space QP on the packed extended inverse
 // (ftmpc_qp2.cuh).  Horizons with (N + 2)(N + 3) / 2 <= 256 block threads, i.e. N <= 20.
 __global__ void __launch_bounds__(FTMPC_QP_THREADS, 2)
-    k_solve2(const __grid_constant__ ftmpc_config cfg, WsLayout L, StepIO io, int* queue, double* ovf, size_t ovf_doubles,
-             long long* prof) {
+    k_solve2(const __grid_constant__ ftmpc_config cfg, WsLayout L, StepIO io, int* queue, long long* prof) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(16) double red[192];
     __shared__ int s_inst;
@@ -130,9 +133,9 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 2)
     {
         const Qp2Scratch q = qp2_carve(scratch, L.N, io);
         lp.work = scratch;
-        lp.JzS = q.Jz;
+        lp.JzS = scratch + (size_t)L.N * 326;
+        lp.tail = lp.JzS + (size_t)L.N * 169;
         lp.WzS = q.Wz;
-        lp.tail = q.Wz + (size_t)L.N * 169;
     }
     __syncthreads();
     for (;;) {
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 2)
         for (int it = 0; it < cfg.max_sqp_iter; ++it) {
             if (sc[SC_STATUS] != (double)FTMPC_ST_RUNNING) break;
             phase_lin(blk, cfg, L, io, inst, slot, lp);
-            phase_qp2(blk, cfg, L, io, inst, slot, scratch, true, ovf + (size_t)blockIdx.x * ovf_doubles);
+            phase_qp2(blk, cfg, L, io, inst, slot, scratch, true);
             phase_ls_block(blk, cfg, L, io, inst, slot, 0, scratch);
         }
         phase_out_write(blk, cfg, L, io, inst, slot);
@@ -404,16 +407,12 @@ static size_t qp_smem_bytes(int N) { return qp_scratch_doubles(N) * sizeof(doubl
 // k_solve2 (two CTAs per SM, range-space QP) covers the horizons whose block sweep fits one 256-thread CTA
 static size_t solve2_smem_bytes(int N) {
     size_t a = qp2_scratch_doubles(N), b = ls_scratch_doubles(N);
-    const size_t c = qp2_fixed_doubles(N) + (size_t)32 * (7 * N + 1) + (size_t)N * FTMPC_NE + 90 + (26 * N + 72) + 90 + (size_t)N * 10 +
-                     2 * (size_t)N * 169 + 2 * (size_t)(N + 1) * FTMPC_NX + 8;      // linearisation tail behind Wz
     if (b > a) a = b;
-    if (c > a) a = c;
     return a * sizeof(double);
 }
 static bool use_solve2(const ftmpc_ctx* h) {
     const int N = h->cfg.horizon;
     return h->cfg.qp_method != 0 && (N + 2) * (N + 3) / 2 <= FTMPC_QP_THREADS && 6 * N <= FTMPC_QP_THREADS &&
-           (size_t)N * 326 <= qp2_fixed_doubles(N) + (size_t)32 * (7 * N + 1) + (size_t)N * FTMPC_NE + 90 + (26 * N + 72) + 90 + (size_t)N * 10 &&
            solve2_smem_bytes(N) <= h->smem_dyn2_max;
 }
 
@@ -564,7 +563,7 @@ int ftmpc_workspace_bytes(ftmpc_handle h, int batch, size_t* out) {
     const int grid = solve_grid(h, batch);
     size_t b = align_up(h->L.stride * sizeof(double) * (size_t)grid, 256);
     const size_t need = solve_smem_bytes(h->cfg.horizon);
-    if (use_solve2(h)) b += align_up(qp2_overflow_doubles(h->cfg.horizon) * sizeof(double), 256) * (size_t)grid;
+    if (use_solve2(h)) b += align_up(sizeof(int) * ((size_t)batch + 2), 256);        // ids handed over to the null-space kernel
     else if (need > h->smem_optin) b += align_up(need, 256) * (size_t)grid;
     b += 256;      // work-queue head of the launch: it lives in the caller's workspace, so steps with different workspaces
                    // may be in flight on different streams at the same time (pipelined batches)
@@ -577,20 +576,29 @@ static int launch_step(ftmpc_ctx* h, const StepIO& io, void* workspace, size_t n
     const WsLayout L = h->L;
     const int grid = solve_grid(h, io.batch);
     if (use_solve2(h)) {
-        const size_t ovf_bytes = align_up(qp2_overflow_doubles(h->cfg.horizon) * sizeof(double), 256);
-        double* ovf = (double*)((char*)workspace + align_up(L.stride * sizeof(double) * (size_t)grid, 256));
+        // pass 1: k_solve2 (two CTAs per SM).  pass 2: the few instances whose working set outgrew its shared-memory capacity
+        // are solved from scratch by the null-space kernel (device-side list, usually empty: the launch then ends at once)
+        int* redo = (int*)((char*)workspace + align_up(L.stride * sizeof(double) * (size_t)grid, 256));
         int* queue = (int*)((char*)workspace + need_ws - 256);
-        CU(cudaMemsetAsync(queue, 0, sizeof(int), stream));
+        CU(cudaMemsetAsync(queue, 0, 2 * sizeof(int), stream));
+        CU(cudaMemsetAsync(redo, 0, sizeof(int), stream));
         if (h->profile) {
             CU(cudaMemsetAsync(h->d_prof, 0, PH_COUNT * sizeof(long long), stream));
             CU(cudaEventRecord(h->ev[0], stream));
         }
-        k_solve2<<<grid, FTMPC_QP_THREADS, solve2_smem_bytes(h->cfg.horizon), stream>>>(h->cfg, L, io, queue, ovf, ovf_bytes / sizeof(double),
-                                                                                         h->profile ? h->d_prof : nullptr);
+        StepIO io1 = io;
+        io1.redo = redo;
+        k_solve2<<<grid, FTMPC_QP_THREADS, solve2_smem_bytes(h->cfg.horizon), stream>>>(h->cfg, L, io1, queue, h->profile ? h->d_prof : nullptr);
+        StepIO io2 = io;
+        io2.inst_list = redo + 1;
+        io2.batch_dev = redo;
+        const int grid1 = io.batch < h->num_sms ? io.batch : h->num_sms;
+        k_solve<false><<<grid1 < grid ? grid1 : grid, FTMPC_QP_THREADS, solve_smem_bytes(h->cfg.horizon), stream>>>(
+            h->cfg, L, io2, queue + 1, nullptr, 0, h->profile ? h->d_prof : nullptr);
         if (h->profile) CU(cudaEventRecord(h->ev[1], stream));
         k_alloc<<<(io.batch + 63) / 64, 64, 0, stream>>>(h->cfg, L, io);
         if (h->profile) CU(cudaEventRecord(h->ev[2], stream));
-        h->last_launches = 2;
+        h->last_launches = 3;
         CU(cudaGetLastError());
         return FTMPC_OK;
     }
@@ -630,7 +638,7 @@ int ftmpc_step(ftmpc_handle h, int batch, const double* state, const double* xre
     ftmpc_workspace_bytes(h, batch, &need_ws);
     if (workspace_bytes < need_ws) return FTMPC_ERR_WORKSPACE;
     StepIO io{batch, state, xref, uref, fault_mask, fault_force, hull_idx, h->d_hull, warm, z_warm, thrust, u0,
-              active_set, status, iters, cost, nullptr, nullptr, h->d_cfg, (double*)workspace, 0, 0};
+              active_set, status, iters, cost, nullptr, nullptr, h->d_cfg, (double*)workspace, nullptr, nullptr, nullptr, 0, 0};
     stepio_default_strides(io, h->L.N);
     return launch_step(h, io, workspace, need_ws, (cudaStream_t)stream_);
 }
@@ -655,7 +663,7 @@ int ftmpc_closed_loop(ftmpc_handle h, int batch, int steps, int start_step, int 
         const int row = start_step + k;
         StepIO io{batch, state, trajectory + (size_t)row * FTMPC_NE, nominal ? nominal + (size_t)row * FTMPC_NU : nullptr,
                   fault_mask, fault_force, hull_idx, h->d_hull, (k > 0 || warm_first) ? 1 : 0, z_warm, thrust, u0, active_set,
-                  status, iters, cost, nullptr, nullptr, h->d_cfg, (double*)workspace, 0, 0};      // strides 0: shared window
+                  status, iters, cost, nullptr, nullptr, h->d_cfg, (double*)workspace, nullptr, nullptr, nullptr, 0, 0};      // strides 0: shared window
         const int rc = launch_step(h, io, workspace, need_ws, stream);
         if (rc != FTMPC_OK) return rc;
         k_plant_loop<<<(batch + 127) / 128, 128, 0, stream>>>(h->d_cfg, batch, state, thrust, fault_mask, fault_force,

@@ -35,13 +35,6 @@ __device__ __forceinline__ void q2_block_of(int tid, int& bi, int& bj) {
     while (bi * (bi + 1) / 2 > tid) --bi;
     bj = tid - bi * (bi + 1) / 2;
 }
-__device__ __forceinline__ int q2_blk(int bi, int bj) { return (bi * (bi + 1) / 2 + bj) * 36; }
-// K(r, c) in K coordinates (0..6N-1 decision variables, 6N..6N+8 extension rows); the diagonal blocks are stored full
-__device__ __forceinline__ double q2_K(const double* K, int r, int c) {
-    const int br = r / 6, bc = c / 6;
-    return (br >= bc) ? K[q2_blk(br, bc) + (r - 6 * br) * 6 + (c - 6 * bc)] : K[q2_blk(bc, br) + (c - 6 * bc) * 6 + (r - 6 * br)];
-}
-
 struct Qp2Scratch {
     // live for the whole phase
     double *cv, *hull, *g, *ga;
@@ -50,11 +43,11 @@ struct Qp2Scratch {
     // block sweep
     double *Lcol, *Xrow, *linv, *flag;
     // active-set iteration
-    double *K, *xe, *s, *ye, *ze, *c;
-    struct QVecs { double *Ui, *u, *w, *v, *r, *cs, *tmp, *sub; int *act, *itmp; int qcap; } qv;
+    double *K, *xe, *s, *ye, *ze;
+    // per member of the working set: aval[8 k + 0..5] normal values, [6] coefficient on the elastic variable, [7] = the six
+    // K coordinates of the values as bytes
+    struct QVecs { double *Ui, *u, *w, *v, *r, *cs, *tmp, *sub, *aval; int *act, *itmp; int qcap; } qv;
     short* pos;
-    unsigned* smask;      // [N] hull rows in the working set per stage, [3] terminal rows, [1] the two rows of the elastic variable
-    int* blist;           // blocks of K coordinates with a non-zero entry of c (uniform list), [NB + 1]
     const double* tf_val;
     const int* tf_idx;
     const ftmpc_config* cg;
@@ -64,17 +57,28 @@ __host__ __device__ inline size_t qp2_fixed_doubles(int N) {
     const WsLayout L = ws_layout(N);
     return (size_t)((L.mc + 1) & ~1) + ((FTMPC_HULL_STRIDE + 1) & ~1) + 2 * (size_t)((L.nv + 1) & ~1);
 }
+#define FTMPC_Q2_PROWS 26         /* panel rows: 0-12 G_t, 13-19 (W' G_t)[omega, q], 20-25 theta W_ux G_t; terminal stage: 0-8 G_N, 13-21 Ht G_N */
+// offset (doubles, from the start of the scratch) of the staged stage Hessians Wz: behind everything the condensing and the
+// linearisation (work 326 N, its shared-memory copy of the Jacobians 169 N, costates + states) keep in front of it
+__host__ __device__ inline size_t qp2_wz_offset(int N) {
+    const WsLayout L = ws_layout(N);
+    const int ldp = 7 * N + 1;
+    const size_t cond = qp2_fixed_doubles(N) + 2 * (size_t)FTMPC_Q2_PROWS * ldp + (size_t)N * FTMPC_NE + 90 + L.mc + 90 + (size_t)N * 10 + 8;
+    const size_t lin = (size_t)N * 326 + (size_t)N * 169 + 2 * (size_t)(N + 1) * FTMPC_NX + 8;
+    return ((cond > lin ? cond : lin) + 1) & ~(size_t)1;
+}
 __host__ __device__ inline size_t qp2_scratch_doubles(int N) {
     const WsLayout L = ws_layout(N);
-    const int NB = N + 2, ldp = 7 * N + 1, ne = L.nv + FTMPC_NE, qc = FTMPC_Q2_QCAP;
-    const size_t cond = (size_t)32 * ldp + 2 * (size_t)N * 169 + (size_t)N * FTMPC_NE + 90 + L.mc + 90 + (size_t)N * 10 + 8;
-    const size_t kblk = (size_t)NB * (NB + 1) / 2 * 36;
-    const size_t chol = kblk + 3 * (size_t)NB * FTMPC_Q2_BS + 8;
-    const size_t ints = ((size_t)2 * (qc + 2) + (L.m + 1) / 2 + (N + 4) + (NB + 2) + 1) / 2 + 1;
-    const size_t gi = kblk + (size_t)qc * (qc + 1) / 2 + 4 * (size_t)(ne + 1) + (L.m + 2) + 6 * (size_t)(qc + 2) + 2 * (size_t)(qc + 2) + ints + 8;
+    const int NB = N + 2, ne = L.nv + FTMPC_NE, qc = FTMPC_Q2_QCAP;
+    const size_t cond = qp2_wz_offset(N) + (size_t)N * 169;
+    const size_t kblk = (size_t)(ne - 1) * ne / 2 + 1;                 // row-packed K over the n + 9 K coordinates (ne - 1 = n + 9)
+    const size_t chol = qp2_fixed_doubles(N) + kblk + 3 * (size_t)NB * FTMPC_Q2_BS + 8;
+    const size_t ints = ((size_t)2 * (qc + 2) + (L.m + 1) / 2 + 1) / 2 + 1;
+    const size_t gi = qp2_fixed_doubles(N) + kblk + (size_t)qc * (qc + 1) / 2 + 3 * (size_t)(ne + 1) + (L.m + 2) + 6 * (size_t)(qc + 2) +
+                      2 * (size_t)(qc + 2) + 8 * (size_t)qc + ints + 8;
     size_t r = cond > chol ? cond : chol;
     if (gi > r) r = gi;
-    return qp2_fixed_doubles(N) + r;
+    return r;
 }
 __device__ __forceinline__ Qp2Scratch qp2_carve(double* buf, int N, const StepIO& io) {
     const WsLayout L = ws_layout(N);
@@ -88,17 +92,17 @@ __device__ __forceinline__ Qp2Scratch qp2_carve(double* buf, int N, const StepIO
     s.ga = p; p += (L.nv + 1) & ~1;
     double* R = p;
     // condensing
-    s.panel = p; p += (size_t)32 * ldp;
+    s.panel = p; p += 2 * (size_t)FTMPC_Q2_PROWS * ldp;       // double-buffered
     s.qe = p; p += (size_t)N * FTMPC_NE;
     s.Ht = p; p += 81;
     s.tgv = p; p += 9;
     s.lam_prev = p; p += L.mc;
     s.hv = p; p += 90;
     s.cqs = p; p += (size_t)N * 10;
-    s.Jz = p; p += (size_t)N * 169;          // last: phase_lin2 leaves the stage Jacobians / Hessians here
-    s.Wz = p; p += (size_t)N * 169;
+    s.Wz = buf + qp2_wz_offset(N);            // the linearisation leaves the stage Hessians here (the Jacobians are read
+    s.Jz = nullptr;                           // from the CTA's global slot: only the column role touches them)
     // block sweep: K first (written when the sweep has succeeded), the shared block column / row behind it
-    const size_t kblk = (size_t)NB * (NB + 1) / 2 * 36;
+    const size_t kblk = (size_t)(ne - 1) * ne / 2 + 1;
     p = R;
     s.K = p; p += kblk;
     s.Lcol = p; p += (size_t)NB * FTMPC_Q2_BS;
@@ -112,7 +116,6 @@ __device__ __forceinline__ Qp2Scratch qp2_carve(double* buf, int N, const StepIO
     s.xe = p; p += ne + 1;
     s.ye = p; p += ne + 1;
     s.ze = p; p += ne + 1;
-    s.c = p; p += ne + 1;
     s.s = p; p += L.m + 2;
     s.qv.u = p; p += qc + 2;
     s.qv.w = p; p += qc + 2;
@@ -121,38 +124,13 @@ __device__ __forceinline__ Qp2Scratch qp2_carve(double* buf, int N, const StepIO
     s.qv.tmp = p; p += qc + 2;
     s.qv.sub = p; p += qc + 2;
     s.qv.cs = p; p += 2 * (qc + 2);
+    s.qv.aval = p; p += 8 * (size_t)qc;
     int* ip = reinterpret_cast<int*>(p);
     s.qv.act = ip; ip += qc + 2;
     s.qv.itmp = ip; ip += qc + 2;
-    s.smask = reinterpret_cast<unsigned*>(ip); ip += N + 4;
-    s.blist = ip; ip += NB + 2;
     s.pos = reinterpret_cast<short*>(ip);
     s.total = qp2_scratch_doubles(N);
     return s;
-}
-
-// q-sized vectors of the overflow path (working sets beyond FTMPC_Q2_QCAP rows): capacity nv, global memory
-__host__ __device__ inline size_t qp2_overflow_doubles(int N) {
-    const size_t nv = 6 * (size_t)N + 1;
-    return nv * (nv + 1) / 2 + 8 * (nv + 2) + (nv + 2) + 8;
-}
-__device__ __forceinline__ Qp2Scratch::QVecs qp2_overflow_carve(double* g, int N) {
-    const int nv = 6 * N + 1;
-    Qp2Scratch::QVecs q;
-    double* p = g;
-    q.qcap = nv;
-    q.Ui = p; p += (size_t)nv * (nv + 1) / 2;
-    q.u = p; p += nv + 2;
-    q.w = p; p += nv + 2;
-    q.v = p; p += nv + 2;
-    q.r = p; p += nv + 2;
-    q.tmp = p; p += nv + 2;
-    q.sub = p; p += nv + 2;
-    q.cs = p; p += 2 * (nv + 2);
-    int* ip = reinterpret_cast<int*>(p);
-    q.act = ip; ip += nv + 2;
-    q.itmp = ip;
-    return q;
 }
 
 // =====================================================================================================================
@@ -160,13 +138,12 @@ __device__ __forceinline__ Qp2Scratch::QVecs qp2_overflow_carve(double* g, int N
 // block rows.  Same arithmetic as the register-tiled path of ftmpc_sqp.cuh::condense (see there for the derivation).
 // =====================================================================================================================
 __device__ __forceinline__ void condense2(CudaBlock& blk, const ftmpc_config& cfg, const WsLayout& L, const Qp2Scratch& s,
-                                          const double* X, const double* U, const double* xref, double theta, double sigma,
-                                          const double* Cq, double (&acc)[6][6], int bi, int bj) {
+                                          const double* Jz /* global: [N][13 cols][13] */, const double* X, const double* U,
+                                          const double* xref, double theta, double sigma, const double* Cq, double (&acc)[6][6],
+                                          int bi, int bj) {
     const int N = L.N, n = L.n, tid = blk.tid(), nt = blk.nthreads();
     const int ldp = 7 * N + 1;
-    double* buf = s.panel;                         // rows 0-12 G_t, 13-25 M_t G_t, 26-31 theta W_ux G_t
     double* Wp = s.Wz;
-    const double* Jz = s.Jz;
     double *qe = s.qe, *Ht = s.Ht, *tgv = s.tgv, *lam_prev = s.lam_prev, *hv = s.hv, *cqs = s.cqs;
     const double* Ah = s.hull;
     // ---- pre-pass: W' = theta * sym(W) (+ 2Q on the omega diagonal), qe, Ht           (hv, lam_prev staged by the caller)
@@ -238,12 +215,16 @@ __device__ __forceinline__ void condense2(CudaBlock& blk, const ftmpc_config& cf
         for (int j = 0; j < 6; ++j) acc[i][j] = 0.0;
     blk.sync();
     blk.mark(PH_COND_PRE);
-    for (int t = 0; t <= N; ++t) {
-        // ---------------- column phase of stage t: G_t[:, a] from G_{t-1}[:, a] (held in the panel), then publish
-        if (a >= 0 && ta < t) {
+    // software pipeline over two panels: interval tt runs the column phase of stage tt + 1 (reads its own column of G_tt from
+    // panel tt & 1, writes panel (tt + 1) & 1) and the block phase of stage tt (reads panel tt & 1); one barrier per stage
+    for (int tt = -1; tt <= N; ++tt) {
+        // ---------------- column phase of stage t = tt + 1
+        const int t = tt + 1;
+        if (a >= 0 && t <= N && ta < t) {
+            double* buf = s.panel + (size_t)(t & 1) * FTMPC_Q2_PROWS * ldp;
+            const double* jz = Jz + (size_t)(t - 1) * 169;
             double g[FTMPC_NX];
             if (ta == t - 1) {                     // birth: G_t[:, a] = B_{t-1} e_ja
-                const double* jz = Jz + (size_t)(t - 1) * 169;
 #pragma unroll
                 for (int r = 0; r < FTMPC_NX; ++r) g[r] = jz[(7 + ja) * 13 + r];
                 gs = 2.0 * cfg.R[ja] * (U[a] - (Cq ? cqs[(t - 1) * 10 + 4 + ja] : 0.0));
@@ -254,10 +235,10 @@ __device__ __forceinline__ void condense2(CudaBlock& blk, const ftmpc_config& cf
                     gaug = sigma * av;
                 }
             } else {                               // G_t[:, a] = A_{t-1} G_{t-1}[:, a]
-                const double* jz = Jz + (size_t)(t - 1) * 169;
+                const double* prev = s.panel + (size_t)((t - 1) & 1) * FTMPC_Q2_PROWS * ldp;
                 double gp[FTMPC_NX];
 #pragma unroll
-                for (int r = 0; r < FTMPC_NX; ++r) gp[r] = buf[r * ldp + pa_];
+                for (int r = 0; r < FTMPC_NX; ++r) gp[r] = prev[r * ldp + pa_];
 #pragma unroll
                 for (int r = 0; r < FTMPC_NX; ++r) {
                     double v = (r < 3) ? gp[r] + cfg.dt * gp[r + 3] : ((r < 6) ? gp[r] : 0.0);
@@ -271,20 +252,18 @@ __device__ __forceinline__ void condense2(CudaBlock& blk, const ftmpc_config& cf
 #pragma unroll
                 for (int r = 0; r < FTMPC_NX; ++r) buf[r * ldp + pa_] = g[r];
 #pragma unroll
-                for (int r = 0; r < 6; ++r) buf[(13 + r) * ldp + pa_] = 2.0 * cfg.Q[r] * g[r];
-#pragma unroll
                 for (int k = 0; k < 7; ++k) {
                     double v = 0.0;
 #pragma unroll
                     for (int l = 0; l < 7; ++l) v += wp[k * 13 + l] * g[6 + l];
-                    buf[(19 + k) * ldp + pa_] = v;
+                    buf[(13 + k) * ldp + pa_] = v;
                 }
 #pragma unroll
                 for (int i = 0; i < FTMPC_NU; ++i) {
                     double v = 0.0;
 #pragma unroll
                     for (int l = 0; l < 7; ++l) v += wp[(7 + i) * 13 + l] * g[6 + l];
-                    buf[(26 + i) * ldp + pa_] = v;
+                    buf[(20 + i) * ldp + pa_] = v;
                 }
 #pragma unroll
                 for (int kk = 0; kk < FTMPC_NE; ++kk) gs += qe[t * FTMPC_NE + kk] * g[kk];
@@ -310,63 +289,60 @@ __device__ __forceinline__ void condense2(CudaBlock& blk, const ftmpc_config& cf
                 s.ga[a] = gaug + gs + va;
             }
         }
-        blk.sync();
-        // ---------------- block phase of stage t
-        if (bi >= 0 && bi < N) {
-            if (bi < t) {
-                // rank-13 update (9 rows at the terminal stage).  The row loop stays ROLLED: unrolled it is 10 KB of
-                // straight-line code per stage, and the capture of the unrolled version showed the FMA lines stalled on
-                // instruction fetch (no_inst 45 %) with two CTAs sharing the instruction cache
-                const double* Pa = buf + 7 * bi;
-                const double* Tb = buf + (size_t)13 * ldp + 7 * bj;
-                const int nr = (t < N) ? FTMPC_NX : FTMPC_NE;
-                double pa[6], tb[6];
-#pragma unroll
-                for (int i = 0; i < 6; ++i) { pa[i] = Pa[i]; tb[i] = Tb[i]; }
+        // ---------------- block phase of stage tt
+        if (tt >= 0 && bi >= 0) {
+            const double* buf = s.panel + (size_t)(tt & 1) * FTMPC_Q2_PROWS * ldp;
+            if (bi < N) {
+                if (bi < tt) {
+                    // rank-13 update (9 rows at the terminal stage): G_t[:, bi]' (M_t G_t)[:, bj].  Rows 0-5 of M_t G_t are the
+                    // rows of G_t scaled by 2 Q_r (scaled on the fly: six panel rows less).  The row loop stays ROLLED:
+                    // unrolled it is 10 KB of straight-line code, and two CTAs share the instruction cache
+                    const double* Pa = buf + 7 * bi;
+                    const double* Pb = buf + 7 * bj;
+                    const bool term = (tt == N);
+                    const int nr = term ? FTMPC_NE : FTMPC_NX;
 #pragma unroll 1
-                for (int r = 0; r < nr; ++r) {
-                    double pn[6], tn[6];
-                    const int rn = (r + 1 < nr) ? r + 1 : r;       // operands of the next row in flight during the FMAs
+                    for (int r = 0; r < nr; ++r) {
+                        const int rb = term ? 13 + r : ((r < 6) ? r : r + 7);
+                        const double sc = (!term && r < 6) ? 2.0 * cfg.Q[r] : 1.0;
+                        double pa[6], tb[6];
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) { pn[i] = Pa[(size_t)rn * ldp + i]; tn[i] = Tb[(size_t)rn * ldp + i]; }
+                        for (int i = 0; i < 6; ++i) { pa[i] = Pa[(size_t)r * ldp + i]; tb[i] = sc * Pb[(size_t)rb * ldp + i]; }
 #pragma unroll
-                    for (int i = 0; i < 6; ++i)
+                        for (int i = 0; i < 6; ++i)
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) acc[i][j] += pa[i] * tb[j];
+                            for (int j = 0; j < 6; ++j) acc[i][j] += pa[i] * tb[j];
+                    }
+                } else if (bi == tt) {
+                    if (bj < tt) {
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) { pa[i] = pn[i]; tb[i] = tn[i]; }
-                }
-            } else if (bi == t) {
-                if (bj < t) {
+                        for (int i = 0; i < 6; ++i)
 #pragma unroll
-                    for (int i = 0; i < 6; ++i)
+                            for (int j = 0; j < 6; ++j) acc[i][j] = buf[(size_t)(20 + i) * ldp + 7 * bj + j];
+                    } else {
+                        const double* wp = Wp + (size_t)tt * 169;
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) acc[i][j] = buf[(size_t)(26 + i) * ldp + 7 * bj + j];
-                } else {
-                    const double* wp = Wp + (size_t)t * 169;
+                        for (int i = 0; i < 6; ++i)
 #pragma unroll
-                    for (int i = 0; i < 6; ++i)
+                            for (int j = 0; j < 6; ++j) {
+                                double v = wp[(7 + i) * 13 + 7 + j];
+                                if (i == j) v += 2.0 * cfg.R[i];
+                                acc[i][j] = v;
+                            }
+                        if (sigma > 0.0) {
+                            for (int r = 0; r < FTMPC_NH; ++r) {
+                                if (lam_prev[tt * FTMPC_NH + r] > 0.0) {
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) {
-                            double v = wp[(7 + i) * 13 + 7 + j];
-                            if (i == j) v += 2.0 * cfg.R[i];
-                            acc[i][j] = v;
-                        }
-                    if (sigma > 0.0) {
-                        for (int r = 0; r < FTMPC_NH; ++r) {
-                            if (lam_prev[t * FTMPC_NH + r] > 0.0) {
+                                    for (int i = 0; i < 6; ++i)
 #pragma unroll
-                                for (int i = 0; i < 6; ++i)
-#pragma unroll
-                                    for (int j = 0; j < 6; ++j) acc[i][j] += sigma * Ah[r * FTMPC_NU + i] * Ah[r * FTMPC_NU + j];
+                                        for (int j = 0; j < 6; ++j) acc[i][j] += sigma * Ah[r * FTMPC_NU + i] * Ah[r * FTMPC_NU + j];
+                                }
                             }
                         }
                     }
                 }
-            }
-        } else if (bi >= N && t == N) {
-            // extension block rows: X = G_N[0:9, :] (rows 6..8 of the second one are padding)
-            if (bj < N) {
+            } else if (tt == N && bj < N) {
+                // extension block rows: X = G_N[0:9, :] (rows 6..8 of the second one are padding)
 #pragma unroll
                 for (int i = 0; i < 6; ++i) {
                     const int row = 6 * (bi - N) + i;
@@ -567,17 +543,16 @@ __device__ __forceinline__ int chol_k_blocks(CudaBlock& blk, int N, const Qp2Scr
     blk.mark(PH_CHOL);
     // K blocks: (H^-1)_ij for i < N; X H^-1 = S for the extension rows; X H^-1 X' = -(trailing corner)
     if (bi >= 0) {
-        double* o = s.K + q2_blk(bi, bj);
         const double sg = (bi >= N && bj >= N) ? -1.0 : 1.0;
+        const int nk = 6 * N + FTMPC_NE;
 #pragma unroll
-        for (int i = 0; i < 6; ++i)
+        for (int i = 0; i < 6; ++i) {
+            const int r = 6 * bi + i;
+            if (r < nk) {                                     // (the last three rows of the second extension block are padding)
+                double* o = s.K + ((r * (r + 1)) >> 1) + 6 * bj;
 #pragma unroll
-            for (int j = 0; j < 6; ++j) o[i * 6 + j] = sg * acc[i][j];
-        if (bi == bj) {                                       // diagonal blocks are kept full: mirror the lower triangle
-#pragma unroll
-            for (int i = 0; i < 6; ++i)
-#pragma unroll
-                for (int j = 0; j < 6; ++j) if (j > i) o[i * 6 + j] = sg * acc[j][i];
+                for (int j = 0; j < 6; ++j) if (bi > bj || j <= i) o[j] = sg * acc[i][j];
+            }
         }
     }
     (void)NB;
@@ -587,313 +562,256 @@ __device__ __forceinline__ int chol_k_blocks(CudaBlock& blk, int N, const Qp2Scr
 }
 
 // =====================================================================================================================
-// range-space dual active-set iteration on the block-packed K (CUDA specialisation of ftmpc_gis.cuh::gis_solve for the
-// MPC constraint structure).  Vectors (xe, ye, ze, c) use the extended layout of MpcCons: [d (n) ; delta ; X d (9)].
+// range-space dual active-set iteration on the packed K (CUDA specialisation of ftmpc_gis.cuh::gis_solve for the MPC
+// constraint structure).  K is row-packed (lower triangle, K(i,j) at i (i + 1) / 2 + j) over the K coordinates
+// [d (n) ; X d (9)]; the vectors (xe, ye, ze) use the same coordinates with the elastic variable LAST (index n + 9) -- it
+// is decoupled in the Hessian, K_delta = 1 / rho_slack.  Per added constraint, seven barrier intervals:
+//   A  ye = K n_p                                  B  w_k = n_k . ye (cached normals of the working set)
+//   C  v = R^-T w      D  r = R^-1 v               E  ze = ye - sum_k r_k (K n_k)      (lane pair per row, k split by parity)
+//   F  e_k = n_k . ze (refinement test), dual step length              G  primal/dual step, slacks, next candidate, update
+// Every helper has ONE call site (the refinement re-enters C-E through a loop): with two CTAs per SM the instruction
+// cache is shared, and the first version of this routine (15 k instructions, two instantiations) stalled on fetches.
 // =====================================================================================================================
-struct Q2Row {           // constraint normal in K coordinates
-    int kind;            // 0 hull row, 1 terminal row, 2 delta >= 0, 3 delta <= 1
-    int base;            // first K coordinate of the (up to 6) consecutive entries of a hull row
-    double val[6];       // hull: -A_h[i][0..5];  terminal: val[0], val[1] at ext coordinates e0, e1
-    int e0, e1;
-    double el;           // coefficient on the elastic variable
-};
-__device__ __forceinline__ void q2_row(const MpcCons& cons, int p, Q2Row& r) {
+__device__ __forceinline__ int q2_tri(int i) { return (i * (i + 1)) >> 1; }
+__device__ __forceinline__ double q2_Kel(const double* K, int i, int c) {
+    const int hi = i > c ? i : c, lo = i > c ? c : i;
+    return K[q2_tri(hi) + lo];
+}
+// n_p . v for an arbitrary constraint row (v in K coordinates, elastic variable at index sl)
+__device__ __forceinline__ double q2_rowdot(const MpcCons& cons, int p, const double* v, int sl) {
     const int N = cons.N;
     if (p < FTMPC_NH * N) {
         const int t = p / FTMPC_NH, i = p - t * FTMPC_NH;
-        r.kind = 0; r.base = t * FTMPC_NU;
-#pragma unroll
-        for (int j = 0; j < 6; ++j) r.val[j] = -cons.Ah[i * FTMPC_NU + j];
-        const double c = cons.cv[p];
-        r.el = (c > 0.0) ? c : 0.0;
-        r.e0 = r.e1 = 0;
-    } else if (p < cons.mc) {
-        const int i = p - FTMPC_NH * N;
-        r.kind = 1; r.base = 0;
-        r.e0 = cons.tf_idx[2 * i]; r.e1 = cons.tf_idx[2 * i + 1];
-        r.val[0] = -cons.tf_val[2 * i]; r.val[1] = -cons.tf_val[2 * i + 1];
-#pragma unroll
-        for (int j = 2; j < 6; ++j) r.val[j] = 0.0;
-        const double c = cons.cv[p];
-        r.el = (c > 0.0) ? c : 0.0;
-    } else {
-        r.kind = (p == cons.mc) ? 2 : 3; r.base = 0; r.e0 = r.e1 = 0;
-#pragma unroll
-        for (int j = 0; j < 6; ++j) r.val[j] = 0.0;
-        r.el = (p == cons.mc) ? 1.0 : -1.0;
-    }
-}
-// n_p . v for a vector in the extended layout
-__device__ __forceinline__ double q2_dot(const Q2Row& r, const double* v, int n, int nv) {
-    double a = r.el * v[n];
-    if (r.kind == 0) {
-#pragma unroll
-        for (int j = 0; j < 6; ++j) a += r.val[j] * v[r.base + j];
-    } else if (r.kind == 1) {
-        a += r.val[0] * v[nv + r.e0] + r.val[1] * v[nv + r.e1];
-    }
-    return a;
-}
-
-// out[row] (+)= sign * sum_b K(row, block b) c_b  over the blocks in `bl`; rows in K coordinates, vectors in the extended
-// layout.  Lane pairs: rows 0 .. 6N-1 on threads 0 .. 12N-1 (even / odd entries of the block list), the first 8
-// extension rows on the next 16 threads, the last extension row on warp 0 afterwards.
-template <bool SUB>
-__device__ __forceinline__ void q2_matvec(const double* K, const double* c, const double* base_vec, double* out, const int* bl,
-                                          int nbl, int N, int tid, int nt) {
-    const int n = 6 * N, nv = n + 1, nrows = n + FTMPC_NE;
-    const int pair = tid >> 1, part = tid & 1;
-    {
-        const bool on = pair < nrows - 1 || (pair == nrows - 1 && 2 * nrows <= nt);
-        const int row = on ? pair : 0, br = row / 6, a = row - 6 * br;
-        double s0 = 0.0, s1 = 0.0;
-        for (int ii = part; on && ii < nbl; ii += 2) {
-            const int b = bl[ii];
-            const double* cb = c + ((b < N) ? 6 * b : 6 * b + 1);          // extension coordinates sit behind the elastic variable
-            const int len = (b <= N) ? 6 : FTMPC_NE - 6;                    // the last block holds 3 extension rows
-            if (b <= br) {
-                const double* kb = K + q2_blk(br, b) + a * 6;
-                s0 += kb[0] * cb[0] + kb[2] * cb[2];
-                s1 += kb[1] * cb[1];
-                if (len == 6) { s1 += kb[3] * cb[3] + kb[5] * cb[5]; s0 += kb[4] * cb[4]; }
-            } else {
-                const double* kb = K + q2_blk(b, br) + a;
-                s0 += kb[0] * cb[0] + kb[12] * cb[2];
-                s1 += kb[6] * cb[1];
-                if (len == 6) { s1 += kb[18] * cb[3] + kb[30] * cb[5]; s0 += kb[24] * cb[4]; }
-            }
-        }
-        double sv = s0 + s1;
-        sv += __shfl_xor_sync(0xffffffffu, sv, 1);
-        if (on && part == 0) {
-            const int o = (row < n) ? row : row + 1;
-            out[o] = SUB ? base_vec[o] - sv : -sv;
-        }
-    }
-    if (2 * nrows > nt && tid < 32) {              // last extension row: warp 0, lanes over (block, entry)
-        const int row = nrows - 1, br = row / 6, a = row - 6 * br;
+        const double* a = cons.Ah + i * FTMPC_NU;
+        const double* x = v + t * FTMPC_NU;
         double sv = 0.0;
-        for (int e = tid; e < 6 * nbl; e += 32) {
-            const int ii = e / 6, j = e - 6 * ii, b = bl[ii];
-            const int len = (b <= N) ? 6 : FTMPC_NE - 6;
-            if (j < len) {
-                const double cj = c[((b < N) ? 6 * b : 6 * b + 1) + j];
-                sv += ((b <= br) ? K[q2_blk(br, b) + a * 6 + j] : K[q2_blk(b, br) + j * 6 + a]) * cj;
-            }
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
-        if (tid == 0) out[row + 1] = SUB ? base_vec[row + 1] - sv : -sv;
+        for (int j = 0; j < FTMPC_NU; ++j) sv -= a[j] * x[j];
+        const double c = cons.cv[p];
+        if (c > 0.0) sv += c * v[sl];
+        return sv;
     }
-    (void)nv;
+    if (p < cons.mc) {
+        const int i = p - FTMPC_NH * N;
+        double sv = -cons.tf_val[2 * i] * v[cons.n + cons.tf_idx[2 * i]] - cons.tf_val[2 * i + 1] * v[cons.n + cons.tf_idx[2 * i + 1]];
+        const double c = cons.cv[p];
+        if (c > 0.0) sv += c * v[sl];
+        return sv;
+    }
+    return (p == cons.mc) ? v[sl] : -v[sl];
 }
 
-// Ui access: shared memory (UIG = false) or the CTA's global slot (UIG = true, capacity nv)
-template <bool UIG>
-__device__ __forceinline__ int gis2_solve(CudaBlock& blk, const MpcCons& cons, const Qp2Scratch& s, const Qp2Scratch::QVecs& qv,
-                                          double kslack, double* lam, int maxit, double tol, int* iters_out, int* nact_out) {
-    double* const Ui = qv.Ui;
-    const int qcap = qv.qcap;
-    const int tid = blk.tid(), nt = blk.nthreads(), lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-    const int N = cons.N, n = cons.n, nv = cons.nv, ne = nv + FTMPC_NE, m = cons.mc + 2, NB = N + 2;
+// returns GI_OK / GI_MAXIT / GI_INFEASIBLE, or 5 when the working set outgrew qcap (the caller hands the instance to the
+// null-space kernel).  On entry s.ze holds the unconstrained minimiser (K coordinates), on exit s.xe the solution.
+__device__ __forceinline__ int gis2_solve(CudaBlock& blk, const MpcCons& cons, const Qp2Scratch& s, double kslack, double* lam,
+                                          int maxit, double tol, int* iters_out, int* nact_out) {
+    const int tid = blk.tid(), nt = blk.nthreads(), lane = tid & 31, warp = tid >> 5;
+    const int N = cons.N, n = cons.n, NK = n + FTMPC_NE, SL = NK, m = cons.mc + 2, qcap = s.qv.qcap;
     const double dep_tol = 1e-14, refine_tol = 1e-13;
+    const Qp2Scratch::QVecs& qv = s.qv;
+    double* const Ui = qv.Ui;
     double* gsc = blk.scratch + 128;
     int q = 0, iters = 0, status = GI_OK;
+    // ---- primal step + slack update + most violated row not in the working set (two call sites: start-up, step G)
+    double nb;
+    int nbi;
+    auto apply_step = [&](double t, int skip) {
+        for (int i = tid; i <= NK; i += nt) s.xe[i] += t * s.ze[i];
+        nb = 0.0;
+        nbi = 0x7fffffff;
+        for (int i = tid; i < m; i += nt) {
+            const double v = s.s[i] + t * q2_rowdot(cons, i, s.ze, SL);
+            s.s[i] = v;
+            if (i != skip && s.pos[i] < 0 && (v < nb || (v == nb && i < nbi))) { nb = v; nbi = i; }
+        }
+    };
+    // start: x = 0, slacks -beta, then the step x += 1 * x_unc
     for (int i = tid; i < m; i += nt) {
-        s.s[i] = cons.slack(i, s.xe, 1.0);
+        s.s[i] = (i < cons.mc) ? -cons.cv[i] : ((i == cons.mc) ? 0.0 : 1.0);
         s.pos[i] = (short)-1;
     }
-    for (int i = tid; i < N + 4; i += nt) s.smask[i] = 0u;
-    if (tid == 0) s.blist[NB + 1] = 0;
+    for (int i = tid; i <= NK; i += nt) s.xe[i] = 0.0;
     blk.sync();
-    bool have_next = false;
-    double next_best = 0.0;
-    int next_bi = 0x7fffffff;
-    // c = N_W r in the extended layout, gathered per coordinate from the per-stage masks of the working set
-    auto gather_c = [&]() {
-        for (int i = tid; i < ne; i += nt) {
-            double a = 0.0;
-            if (i < n) {
-                const int t = i / FTMPC_NU, j = i - t * FTMPC_NU;
-                unsigned mk = s.smask[t];
-                while (mk) {
-                    const int row = __ffs(mk) - 1;
-                    mk &= mk - 1;
-                    a -= qv.r[s.pos[t * FTMPC_NH + row]] * cons.Ah[row * FTMPC_NU + j];
-                }
-            } else if (i > n) {
-                const int e = i - nv;
-                for (int wd = 0; wd < 3; ++wd) {
-                    unsigned mk = s.smask[N + wd];
-                    while (mk) {
-                        const int row = 32 * wd + __ffs(mk) - 1;
-                        mk &= mk - 1;
-                        const double av = (s.tf_idx[2 * row] == e) ? s.tf_val[2 * row] : ((s.tf_idx[2 * row + 1] == e) ? s.tf_val[2 * row + 1] : 0.0);
-                        a -= qv.r[s.pos[FTMPC_NH * N + row]] * av;
-                    }
-                }
-            }
-            if (i != n) s.c[i] = a;
-        }
-        if (warp == nw - 1) {                      // elastic coordinate: every member of the working set may touch it
-            double a = 0.0;
-            for (int k = lane; k < q; k += 32) {
-                const int p = qv.act[k];
-                const double cv = (p < cons.mc) ? cons.cv[p] : 0.0;
-                const double el = (p < cons.mc) ? ((cv > 0.0) ? cv : 0.0) : ((p == cons.mc) ? 1.0 : -1.0);
-                a += qv.r[k] * el;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (lane == 0) s.c[n] = a;
-        }
-    };
-    // list of K blocks with a non-zero c (thread 0; called when the working set changed)
-    auto rebuild_blist = [&]() {
-        if (tid == 0) {
-            int c = 0;
-            for (int t = 0; t < N; ++t) if (s.smask[t]) s.blist[c++] = t;
-            if (s.smask[N] | s.smask[N + 1] | s.smask[N + 2]) { s.blist[c++] = N; s.blist[c++] = N + 1; }
-            s.blist[NB + 1] = c;
-        }
-    };
-    // r = R^-1 R^-T w  (w in s.w): four lanes per entry
-    auto schur_solve = [&]() {
-        const int part = tid & 3, per = nt >> 2;
-        for (int k0 = 0; k0 < q; k0 += per) {         // (uniform trip count: the shuffles run in every lane)
-            const int k = k0 + (tid >> 2);
-            double a = 0.0;
-            if (k < q) {
-                const double* col = Ui + gi_tri(k);
-                for (int j = part; j <= k; j += 4) a += col[j] * qv.w[j];
-            }
-            a += __shfl_xor_sync(0xffffffffu, a, 1);
-            a += __shfl_xor_sync(0xffffffffu, a, 2);
-            if (k < q && part == 0) qv.v[k] = a;
-        }
-        blk.sync();
-        for (int k0 = 0; k0 < q; k0 += per) {
-            const int k = k0 + (tid >> 2);
-            double a = 0.0;
-            if (k < q)
-                for (int kk = k + part; kk < q; kk += 4) a += Ui[gi_tri(kk) + k] * qv.v[kk];
-            a += __shfl_xor_sync(0xffffffffu, a, 1);
-            a += __shfl_xor_sync(0xffffffffu, a, 2);
-            if (k < q && part == 0) qv.r[k] = a;
-        }
-        blk.sync();
-    };
+    apply_step(1.0, -1);
+    blk.argmin(nb, nbi);
     for (;;) {
-        // ---- most violated row
-        double best = next_best;
-        int bi = next_bi;
-        if (!have_next) {
-            best = 0.0;
-            bi = 0x7fffffff;
-            for (int i = tid; i < m; i += nt) {
-                if (s.pos[i] < 0) {
-                    const double v = s.s[i];
-                    if (v < best || (v == best && i < bi)) { best = v; bi = i; }
-                }
-            }
-            blk.argmin(best, bi);
-        }
-        if (bi == 0x7fffffff || best >= -tol) break;
-        have_next = false;
+        if (nbi == 0x7fffffff || nb >= -tol) break;      // primal feasible -> optimal
         blk.mark(PH_GI_SELECT);
-        const int p = bi;
-        double sp = best;
-        Q2Row np;
-        q2_row(cons, p, np);
-        if (tid == 0) qv.u[q] = 0.0;
-        // ye = K n_p (extended layout); the elastic variable is decoupled: K_delta = 1 / rho_slack
-        for (int i = tid; i < ne; i += nt) {
-            double a = 0.0;
-            if (i == n) a = np.el * kslack;
-            else {
-                const int r = (i < n) ? i : i - 1;
-                if (np.kind == 0) {
+        const int p = nbi;
+        double sp = nb;
+        // the normal of p as (index, value) pairs in K coordinates + the coefficient on the elastic variable
+        int pidx[6];
+        double pval[6], pel;
+        {
+            if (p < FTMPC_NH * N) {
+                const int t = p / FTMPC_NH, i = p - t * FTMPC_NH;
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) a += np.val[j] * q2_K(s.K, r, np.base + j);
-                } else if (np.kind == 1) {
-                    a = np.val[0] * q2_K(s.K, r, n + np.e0) + np.val[1] * q2_K(s.K, r, n + np.e1);
-                }
+                for (int j = 0; j < 6; ++j) { pidx[j] = t * FTMPC_NU + j; pval[j] = -cons.Ah[i * FTMPC_NU + j]; }
+                const double c = cons.cv[p];
+                pel = (c > 0.0) ? c : 0.0;
+            } else if (p < cons.mc) {
+                const int i = p - FTMPC_NH * N;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) { pidx[j] = n; pval[j] = 0.0; }
+                pidx[0] = n + cons.tf_idx[2 * i]; pval[0] = -cons.tf_val[2 * i];
+                pidx[1] = n + cons.tf_idx[2 * i + 1]; pval[1] = -cons.tf_val[2 * i + 1];
+                const double c = cons.cv[p];
+                pel = (c > 0.0) ? c : 0.0;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) { pidx[j] = 0; pval[j] = 0.0; }
+                pel = (p == cons.mc) ? 1.0 : -1.0;
+            }
+        }
+        if (tid == 0) qv.u[q] = 0.0;
+        // ---- A: ye = K n_p
+        for (int i = tid; i <= NK; i += nt) {
+            double a = pel * kslack;
+            if (i < NK) {
+                a = 0.0;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) a += pval[j] * q2_Kel(s.K, i, pidx[j]);
             }
             s.ye[i] = a;
         }
         blk.sync();
-        const double dn = q2_dot(np, s.ye, n, nv);
+        double dn = pel * s.ye[SL];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) dn += pval[j] * s.ye[pidx[j]];
         blk.mark(PH_GI_D);
         bool added = false;
         while (!added) {
             ++iters;
             if (iters > maxit) { status = GI_MAXIT; break; }
-            double d2n, t1 = INFINITY;
+            double d2n = dn, t1 = INFINITY;
             int l = 0x7fffffff;
-            if (q > 0) {
-                for (int k = tid; k < q; k += nt) qv.w[k] = cons.slack(qv.act[k], s.ye, 0.0);
+            if (q == 0) {
+                for (int i = tid; i <= NK; i += nt) s.ze[i] = s.ye[i];
                 blk.sync();
-                schur_solve();
-                gather_c();
-                blk.sync();
-                q2_matvec<true>(s.K, s.c, s.ye, s.ze, s.blist, s.blist[NB + 1], N, tid, nt);
-                if (tid == nt - 1) s.ze[n] = s.ye[n] - kslack * s.c[n];
-                blk.sync();
-                // refinement on the semi-normal equations: e = N_W' ze vanishes in exact arithmetic
-                double emax = 0.0;
+            } else {
+                // ---- B: w = N_W' ye
                 for (int k = tid; k < q; k += nt) {
-                    const double e = cons.slack(qv.act[k], s.ze, 0.0);
-                    qv.w[k] = e;
-                    qv.tmp[k] = qv.r[k];
-                    emax = fmax(emax, fabs(e));
+                    const double* av = qv.aval + 8 * k;
+                    const unsigned char* ai = reinterpret_cast<const unsigned char*>(av + 7);
+                    double a = av[6] * s.ye[SL];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) a += av[j] * s.ye[ai[j]];
+                    qv.w[k] = a;
                 }
-                emax = blk.max(emax);
-                if (emax > refine_tol * fabs(dn)) {
-                    schur_solve();                 // delta r
-                    gather_c();
+                blk.sync();
+                for (int pass = 0; pass < 2; ++pass) {
+                    // ---- C: v = R^-T w,  D: r = R^-1 v   (four lanes per entry)
+                    {
+                        const int part = tid & 3, per = nt >> 2;
+                        for (int k0 = 0; k0 < q; k0 += per) {
+                            const int k = k0 + (tid >> 2);
+                            double a = 0.0;
+                            if (k < q) {
+                                const double* col = Ui + gi_tri(k);
+                                for (int j = part; j <= k; j += 4) a += col[j] * qv.w[j];
+                            }
+                            a += __shfl_xor_sync(0xffffffffu, a, 1);
+                            a += __shfl_xor_sync(0xffffffffu, a, 2);
+                            if (k < q && part == 0) qv.v[k] = a;
+                        }
+                        blk.sync();
+                        for (int k0 = 0; k0 < q; k0 += per) {
+                            const int k = k0 + (tid >> 2);
+                            double a = 0.0;
+                            if (k < q)
+                                for (int kk = k + part; kk < q; kk += 4) a += Ui[gi_tri(kk) + k] * qv.v[kk];
+                            a += __shfl_xor_sync(0xffffffffu, a, 1);
+                            a += __shfl_xor_sync(0xffffffffu, a, 2);
+                            if (k < q && part == 0) qv.tmp[k] = a;         // r of this pass (delta r in the refinement pass)
+                        }
+                        blk.sync();
+                    }
+                    // ---- E: ze = (ye | ze) - sum_k r_k (K n_k): lane pair per row (k split by parity), last row on warp 0
+                    {
+                        const double* src = pass ? s.ze : s.ye;
+                        const int pair = tid >> 1, part = tid & 1;
+                        const bool on = pair < NK && (pair < NK - 1 || 2 * NK <= nt);
+                        const int row = on ? pair : 0;
+                        double sv = 0.0;
+                        for (int k = part; on && k < q; k += 2) {
+                            const double* av = qv.aval + 8 * k;
+                            const unsigned char* ai = reinterpret_cast<const unsigned char*>(av + 7);
+                            double a = 0.0;
+#pragma unroll
+                            for (int j = 0; j < 6; ++j) a += av[j] * q2_Kel(s.K, row, ai[j]);
+                            sv += qv.tmp[k] * a;
+                        }
+                        sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+                        if (on && part == 0) s.ze[row] = src[row] - sv;
+                        if (2 * NK > nt && warp == 0) {
+                            double tv = 0.0;
+                            for (int k = lane; k < q; k += 32) {
+                                const double* av = qv.aval + 8 * k;
+                                const unsigned char* ai = reinterpret_cast<const unsigned char*>(av + 7);
+                                double a = 0.0;
+#pragma unroll
+                                for (int j = 0; j < 6; ++j) a += av[j] * q2_Kel(s.K, NK - 1, ai[j]);
+                                tv += qv.tmp[k] * a;
+                            }
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) tv += __shfl_xor_sync(0xffffffffu, tv, o);
+                            if (lane == 0) s.ze[NK - 1] = src[NK - 1] - tv;
+                        }
+                        if (warp == (nt >> 5) - 1) {               // elastic coordinate
+                            double tv = 0.0;
+                            for (int k = lane; k < q; k += 32) tv += qv.tmp[k] * qv.aval[8 * k + 6];
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) tv += __shfl_xor_sync(0xffffffffu, tv, o);
+                            if (lane == 0) s.ze[SL] = src[SL] - kslack * tv;
+                        }
+                    }
+                    if (pass == 0) { for (int k = tid; k < q; k += nt) qv.r[k] = qv.tmp[k]; }
+                    else { for (int k = tid; k < q; k += nt) qv.r[k] += qv.tmp[k]; }
                     blk.sync();
-                    q2_matvec<true>(s.K, s.c, s.ze, s.ze, s.blist, s.blist[NB + 1], N, tid, nt);
-                    if (tid == nt - 1) s.ze[n] -= kslack * s.c[n];
-                    for (int k = tid; k < q; k += nt) qv.r[k] += qv.tmp[k];
-                    blk.sync();
+                    // ---- F: e = N_W' ze (vanishes in exact arithmetic), dual step length
+                    double emax = 0.0;
+                    t1 = INFINITY;
+                    l = 0x7fffffff;
+                    for (int k = tid; k < q; k += nt) {
+                        const double* av = qv.aval + 8 * k;
+                        const unsigned char* ai = reinterpret_cast<const unsigned char*>(av + 7);
+                        double e = av[6] * s.ze[SL];
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) e += av[j] * s.ze[ai[j]];
+                        qv.w[k] = e;
+                        emax = fmax(emax, fabs(e));
+                        const double rk = qv.r[k];
+                        if (rk > 1e-13) {
+                            const double tk = qv.u[k] / rk;
+                            if (tk < t1 || (tk == t1 && k < l)) { t1 = tk; l = k; }
+                        }
+                    }
+                    // one barrier for both reductions: the refinement flag rides on the arg-min exchange
+                    for (int o = 16; o > 0; o >>= 1) emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+                    if (lane == 0) gsc[32 + 8 * pass + warp] = emax;
+                    blk.argmin(t1, l);
+                    emax = 0.0;
+                    for (int i = 0; i < (nt >> 5); ++i) emax = fmax(emax, gsc[32 + 8 * pass + i]);
+                    if (pass == 1 || !(emax > refine_tol * fabs(dn))) break;
                     blk.count(CT_GI_REFINE);
                 }
-                d2n = q2_dot(np, s.ze, n, nv);
-                for (int j = tid; j < q; j += nt) {
-                    const double rj = qv.r[j];
-                    if (rj > 1e-13) {
-                        const double tj = qv.u[j] / rj;
-                        if (tj < t1 || (tj == t1 && j < l)) { t1 = tj; l = j; }
-                    }
-                }
-                blk.argmin(t1, l);
-            } else {
-                for (int i = tid; i < ne; i += nt) s.ze[i] = s.ye[i];
-                blk.sync();
-                d2n = dn;
+                d2n = pel * s.ze[SL];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) d2n += pval[j] * s.ze[pidx[j]];
             }
             blk.mark(PH_GI_Z);
             const bool dep = (q >= qcap) || !(d2n > dep_tol * fmax(1.0, dn)) || (d2n <= 1e-28);
             const double t2 = dep ? INFINITY : (-sp / d2n);
             const double t = fmin(t1, t2);
             if (t == INFINITY) { status = (q >= qcap) ? 5 : GI_INFEASIBLE; break; }
-            if (t2 == INFINITY) {
-                for (int j = tid; j <= q; j += nt) qv.u[j] += t * ((j < q) ? -qv.r[j] : 1.0);
-                blk.sync();
-            } else {
-                const bool full = (t == t2);
-                for (int i = tid; i < ne; i += nt) s.xe[i] += t * s.ze[i];
-                for (int j = tid; j <= q; j += nt) qv.u[j] += t * ((j < q) ? -qv.r[j] : 1.0);
-                double nb = 0.0;
-                int nbi = 0x7fffffff;
-                for (int i = tid; i < m; i += nt) {
-                    const double v = s.s[i] + t * cons.slack(i, s.ze, 0.0);
-                    s.s[i] = v;
-                    if (i != p && s.pos[i] < 0 && (v < nb || (v == nb && i < nbi))) { nb = v; nbi = i; }
-                }
+            // ---- G: step
+            for (int j = tid; j <= q; j += nt) qv.u[j] += t * ((j < q) ? -qv.r[j] : 1.0);
+            if (t2 != INFINITY) {
+                apply_step(t, p);
                 sp += t * d2n;
                 blk.mark(PH_GI_STEP);
-                if (full) {
+                if (t == t2) {
+                    // full step: p joins the working set
                     const double rho = sqrt(d2n);
                     double* col = Ui + gi_tri(q);
                     for (int j = tid; j < q; j += nt) col[j] = -qv.r[j] / rho;
@@ -901,23 +819,20 @@ __device__ __forceinline__ int gis2_solve(CudaBlock& blk, const MpcCons& cons, c
                         col[q] = 1.0 / rho;
                         qv.act[q] = p;
                         s.pos[p] = (short)q;
-                        if (p < FTMPC_NH * N) s.smask[p / FTMPC_NH] |= 1u << (p % FTMPC_NH);
-                        else if (p < cons.mc) s.smask[N + (p - FTMPC_NH * N) / 32] |= 1u << ((p - FTMPC_NH * N) % 32);
+                        double* av = qv.aval + 8 * q;
+                        unsigned char* ai = reinterpret_cast<unsigned char*>(av + 7);
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) { av[j] = pval[j]; ai[j] = (unsigned char)pidx[j]; }
+                        av[6] = pel;
                     }
                     blk.argmin(nb, nbi);           // barrier of the update + next selection in one
-                    next_best = nb;
-                    next_bi = nbi;
-                    have_next = true;
                     q += 1;
                     added = true;
-                    rebuild_blist();
-                    if (tid == 0) s.s[p] = 0.0;    // on the constraint by construction
-                    blk.sync();
                     blk.mark(PH_GI_UPD);
                     continue;
                 }
-                blk.sync();
             }
+            blk.sync();
             // ---- drop the l-th member of the working set (partial step or dual step): Givens on R^-1 only
             {
                 for (int k = l + tid; k <= q - 2; k += nt) {
@@ -953,13 +868,16 @@ __device__ __forceinline__ int gis2_solve(CudaBlock& blk, const MpcCons& cons, c
                         }
                     }
                 }
-                for (int i = l + tid; i < q; i += nt) { qv.tmp[i] = qv.u[i + 1]; qv.itmp[i] = (i + 1 < q) ? qv.act[i + 1] : -1; }
-                if (tid == 0) {
-                    const int pd = qv.act[l];
-                    s.pos[pd] = (short)-1;
-                    if (pd < FTMPC_NH * N) s.smask[pd / FTMPC_NH] &= ~(1u << (pd % FTMPC_NH));
-                    else if (pd < cons.mc) s.smask[N + (pd - FTMPC_NH * N) / 32] &= ~(1u << ((pd - FTMPC_NH * N) % 32));
+                // shifted copies of the per-member data (multiplier, id, cached normal)
+                for (int i = l + tid; i < q - 1; i += nt) {
+                    qv.tmp[i] = qv.u[i + 1];
+                    qv.itmp[i] = qv.act[i + 1];
                 }
+                if (tid == nt - 1) { qv.tmp[q - 1] = qv.u[q]; s.pos[qv.act[l]] = (short)-1; }
+                const int nsh = (q - 1 - l) * 8;                       // cached normals of the members behind l move up by one
+                double keep0 = 0.0, keep1 = 0.0;
+                if (tid < nsh) keep0 = qv.aval[8 * (l + 1) + tid];
+                if (tid + nt < nsh) keep1 = qv.aval[8 * (l + 1) + tid + nt];
                 blk.sync();
                 for (int k = l + tid; k <= q - 2; k += nt) {
                     double* col = Ui + gi_tri(k);
@@ -970,7 +888,8 @@ __device__ __forceinline__ int gis2_solve(CudaBlock& blk, const MpcCons& cons, c
                     qv.u[i] = qv.tmp[i];
                     if (i < q - 1) { qv.act[i] = qv.itmp[i]; s.pos[qv.itmp[i]] = (short)i; }
                 }
-                rebuild_blist();
+                if (tid < nsh) qv.aval[8 * l + tid] = keep0;
+                if (tid + nt < nsh) qv.aval[8 * l + tid + nt] = keep1;
                 blk.sync();
                 q -= 1;
                 blk.mark(PH_GI_DROP);
@@ -994,11 +913,11 @@ __device__ __forceinline__ int gis2_solve(CudaBlock& blk, const MpcCons& cons, c
 // `staged`: the linearisation left Jz / Wz in this phase's scratch (s.Jz, s.Wz).
 // =====================================================================================================================
 __device__ __forceinline__ void phase_qp2(CudaBlock& blk, const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst,
-                                          int slot, double* scratch, bool staged, double* ui_global) {
+                                          int slot, double* scratch, bool staged) {
     double* w = ws_slot(io, L, slot);
     double* sc = w + L.oSc;
     if (sc[SC_STATUS] != FTMPC_ST_RUNNING) return;
-    const int N = L.N, n = L.n, nv = L.nv, ne = nv + FTMPC_NE, tid = blk.tid(), nt = blk.nthreads(), NB = N + 2;
+    const int N = L.N, n = L.n, nv = L.nv, tid = blk.tid(), nt = blk.nthreads(), NB = N + 2;
     const Qp2Scratch s = qp2_carve(scratch, N, io);
     const double* xref = io.xref + (size_t)inst * io.xref_stride;
     const double* hull_g = io.hull_table + (size_t)io.hull_idx[inst] * FTMPC_HULL_STRIDE;
@@ -1017,7 +936,7 @@ __device__ __forceinline__ void phase_qp2(CudaBlock& blk, const ftmpc_config& cf
     if (skip_exact) theta = 0.0;
     bool aug_allowed = can_aug;
     int fails = 0, qit = 0, nact = 0, st = GI_OK, aug_retry = 0;
-    bool have_j = staged, have_w = staged;
+    bool have_w = staged;
     // block role of this thread
     int bi = -1, bj = 0;
     if (tid < NB * (NB + 1) / 2) q2_block_of(tid, bi, bj);
@@ -1025,15 +944,14 @@ __device__ __forceinline__ void phase_qp2(CudaBlock& blk, const ftmpc_config& cf
     for (;;) {        // QP attempts (re-solved without augmentation if a predicted-active row came out inactive)
         double sig0 = 0.0;
         for (;;) {
-            // the linearisation leaves Jz / Wz in place; Wz is scaled in place by the condensing, so a second attempt
-            // re-reads it (and, once the active-set solver has reused the region, Jz too) from the global backing copy
-            if (!have_j) for (int i = tid; i < N * 169; i += nt) s.Jz[i] = w[L.oJz + i];
+            // the linearisation leaves Wz in place (shared memory); the condensing scales it in place, so a second attempt
+            // re-reads it from the global backing copy.  The stage Jacobians are read from the CTA's global slot.
             if (!have_w) for (int i = tid; i < N * 169; i += nt) s.Wz[i] = w[L.oWz + i];
             if (sigma > 0.0) for (int i = tid; i < L.mc; i += nt) s.lam_prev[i] = lam_prev[i];
             for (int i = tid; i < 90; i += nt) s.hv[i] = (i < 81) ? w[L.oHV + i] : w[L.oGV + i - 81];
             blk.sync();
             double acc[6][6];
-            condense2(blk, cfg, L, s, w + L.oX, w + L.oU, xref, theta, sigma, Cq, acc, bi, bj);
+            condense2(blk, cfg, L, s, w + L.oJz, w + L.oX, w + L.oU, xref, theta, sigma, Cq, acc, bi, bj);
             blk.mark(PH_COND);
             blk.count(CT_CONDENSE);
             double dmaxl = 0.0;
@@ -1043,8 +961,7 @@ __device__ __forceinline__ void phase_qp2(CudaBlock& blk, const ftmpc_config& cf
             }
             const double dscale = blk.max(dmaxl);
             const int bad = chol_k_blocks(blk, N, s, acc, bi, bj, 1e-10 * fmax(1.0, dscale));
-            have_j = false;                 // the shared block column / row of the sweep may lie over the staged Jacobians
-            have_w = false;                 // (short horizons), and the condensing scaled Wz in place: reload both on a retry
+            have_w = false;                 // the condensing scaled Wz in place: reload on a retry
             if (!bad) break;
             blk.count(CT_CHOL_FAIL);
             ++fails;
@@ -1059,38 +976,28 @@ __device__ __forceinline__ void phase_qp2(CudaBlock& blk, const ftmpc_config& cf
             }
             else { theta = (theta > cfg.theta_first) ? 0.5 * theta : 0.0; }
         }
-        have_j = false;                     // K has overwritten the staged Jacobians
-        // unconstrained minimiser  x = -H^-1 ga  in the extended layout (the elastic variable has no gradient)
-        if (tid == 0) {
-            for (int b = 0; b < N; ++b) s.blist[b] = b;
-            s.blist[NB + 1] = N;
+        // unconstrained minimiser  x = -K [ga ; 0]  (K coordinates; the elastic variable has no gradient) -> s.ze
+        {
+            const int NK = n + FTMPC_NE, pair = tid >> 1, part = tid & 1;
+            for (int r0 = 0; r0 < NK; r0 += nt >> 1) {
+                const int row = r0 + pair;
+                double sv = 0.0;
+                if (row < NK) {
+                    const int tr = (row * (row + 1)) >> 1;
+                    for (int j = part; j < n; j += 2) sv += ((j <= row) ? s.K[tr + j] : s.K[((j * (j + 1)) >> 1) + row]) * s.ga[j];
+                }
+                sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+                if (row < NK && part == 0) s.ze[row] = -sv;
+            }
+            if (tid == nt - 1) s.ze[NK] = 0.0;
         }
-        for (int i = tid; i < ne + 1; i += nt) s.c[i] = (i < n) ? s.ga[i] : 0.0;
-        blk.sync();
-        q2_matvec<false>(s.K, s.c, s.c, s.xe, s.blist, N, N, tid, nt);
-        if (tid == nt - 1) s.xe[n] = 0.0;
         blk.sync();
         MpcCons cons{N, n, nv, L.mc, s.hull, io.cfg_g->Af, s.cv, io.tf_val, io.tf_idx};
         blk.mark(PH_QPSETUP);
         blk.count(CT_QP);
         int qit1 = 0;
         const double kslack = 1.0 / cfg.rho_slack;
-        st = gis2_solve<false>(blk, cons, s, s.qv, kslack, w + L.oLam + L.m, cfg.max_qp_iter, cfg.qp_tol, &qit1, &nact);
-        if (st == 5) {
-            // the working set outgrew the shared-memory R^-1: same QP again with R^-1 in the CTA's global slot
-            qit += qit1;
-            for (int i = tid; i < ne + 1; i += nt) s.c[i] = (i < n) ? s.ga[i] : 0.0;
-            if (tid == 0) {
-                for (int b = 0; b < N; ++b) s.blist[b] = b;
-                s.blist[NB + 1] = N;
-            }
-            blk.sync();
-            q2_matvec<false>(s.K, s.c, s.c, s.xe, s.blist, N, N, tid, nt);
-            if (tid == nt - 1) s.xe[n] = 0.0;
-            blk.sync();
-            st = gis2_solve<true>(blk, cons, s, qp2_overflow_carve(ui_global, N), kslack, w + L.oLam + L.m, cfg.max_qp_iter, cfg.qp_tol, &qit1, &nact);
-            if (st == 5) st = GI_MAXIT;
-        }
+        st = gis2_solve(blk, cons, s, kslack, w + L.oLam + L.m, cfg.max_qp_iter, cfg.qp_tol, &qit1, &nact);
         blk.mark(PH_GI);
         qit += qit1;
         if (sigma > 0.0 && st == GI_OK) {       // every predicted-active row must be active in the QP solution
@@ -1127,9 +1034,10 @@ __device__ __forceinline__ void phase_qp2(CudaBlock& blk, const ftmpc_config& cf
     dmx = blk.max(dmx);
     lmx = blk.max(lmx);
     if (tid == 0) {
-        w[L.oD + n] = s.xe[n];
+        const double delta = s.xe[n + FTMPC_NE];
+        w[L.oD + n] = delta;
         sc[SC_DPREV] = dprev_keep;
-        sc[SC_GD] = gd; sc[SC_DMAX] = dmx; sc[SC_LAMMAX] = lmx; sc[SC_DELTA] = s.xe[n];
+        sc[SC_GD] = gd; sc[SC_DMAX] = dmx; sc[SC_LAMMAX] = lmx; sc[SC_DELTA] = delta;
         sc[SC_HFAIL] = (skip_exact || (fails > 0 && theta == 0.0)) ? 1.0 : 0.0;
         sc[SC_THETA] = theta; sc[SC_SIGMA] = sigma; sc[SC_QPIT] += qit; sc[SC_NACT] = nact; sc[SC_CHOLFAIL] += fails;
         sc[SC_QPST] = (st == GI_OK && dmx == dmx) ? 0.0 : (double)(st ? st : 4);

@@ -40,6 +40,7 @@ namespace ftmpc {
 // and the exact remainder  -2 sum_i r_i d2 rho_i / d q2  goes into the (q,q) block of W_t next to the dynamics' second-
 // order terms (blended by theta like them).  u = u~ - rho is restored when results are written (phase_out_write).
 #define FTMPC_CQ 56
+#define FTMPC_ST_REDO 6          /* internal: k_solve2 hands the instance to the null-space kernel (never returned to the caller) */
 struct WsLayout {
     int N, n, nv, mc, m;
     size_t oU, oD, oX, oC, oLam, oMu, oJz, oWz, oGV, oHV, oSc, oCq, stride;
@@ -91,6 +92,10 @@ struct StepIO {
     const ftmpc_config* cfg_g;  // copy of the configuration in global memory (tables indexed per thread); the kernels
                                 // also receive it by value as a __grid_constant__ parameter for uniform accesses
     double* ws;                 // workspace: one slot of L.stride doubles per instance (CPU port) or per CTA (k_solve)
+    int* redo;                  // k_solve2 only: redo[0] = number of instances handed over to the null-space kernel (their working set
+                                // outgrew the shared-memory capacity of the range-space QP), redo[1..] = their ids; else nullptr
+    const int* inst_list;       // second pass: instance ids to solve (batch_dev[0] of them) instead of 0 .. batch-1; else nullptr
+    const int* batch_dev;
     size_t xref_stride;         // doubles between the reference windows of consecutive instances: (N+1)*9, or 0 when every
     size_t uref_stride;         // instance tracks the same window (closed-loop driver: one table shared by the batch)
 };
@@ -541,7 +546,7 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
         blk.sync();                                   // everybody has read the scalars
         if (status != FTMPC_ST_RUNNING) return;
         if (qpst != 0.0) {
-            if (tid == 0) sc[SC_STATUS] = FTMPC_ST_QPFAIL;
+            if (tid == 0) sc[SC_STATUS] = (qpst == 5.0) ? FTMPC_ST_REDO : FTMPC_ST_QPFAIL;
             blk.sync();
             return;
         }

@@ -37,7 +37,7 @@ int ftmpc_cpu_step(const ftmpc_config* cfg, const double* hull_table, int batch,
     std::vector<double> own;
     if (!ws) { own.resize(L.stride * (size_t)batch); ws = own.data(); }
     StepIO io{batch, state, xref, uref, fault_mask, fault_force, hull_idx, hull_table, warm, z_warm, thrust, u0,
-              active_set, status, iters, cost, nullptr, nullptr, cfg, ws, 0, 0};
+              active_set, status, iters, cost, nullptr, nullptr, cfg, ws, nullptr, nullptr, nullptr, 0, 0};
     stepio_default_strides(io, cfg->horizon);
     const size_t sdoubles = qp_scratch_doubles(cfg->horizon);
     const bool trace = std::getenv("FTMPC_TRACE") != nullptr;
