@@ -48,14 +48,74 @@ enum { PH_LS = 0, PH_LIN, PH_COND, PH_CHOL, PH_INV, PH_QPSETUP, PH_GI, PH_POST, 
        PH_COUNT };
 
 #if defined(__CUDACC__)
+// ---- TMA bulk staging (cp.async.bulk + mbarrier): per-instance problem data (input-bound hull, reference windows,
+// constraint values) travel from HBM / L2 to shared memory as bulk copies issued by ONE thread; the other threads
+// only wait on the mbarrier.  Addresses must be 16-byte aligned and sizes multiples of 16 bytes: a row of doubles
+// that starts or ends on an odd double gets that element moved by a plain load (tma_stage_row).
+struct TmaBar {
+    unsigned addr;       // shared-memory address of the mbarrier
+    unsigned parity;     // phase parity the next wait expects (per thread, all threads in step)
+};
+__device__ __forceinline__ void tma_bar_init(unsigned long long* bar_smem, TmaBar& b) {
+    b.addr = (unsigned)__cvta_generic_to_shared(bar_smem);
+    b.parity = 0u;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b.addr));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+}
+// one thread: announce `bytes` of bulk traffic on the barrier (also its single arrival)
+__device__ __forceinline__ void tma_expect(const TmaBar& b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b.addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(const TmaBar& b, void* dst_smem, const void* src_gmem, unsigned bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src_gmem),
+                 "r"(bytes), "r"(b.addr)
+                 : "memory");
+}
+// all threads: wait for the current phase of the barrier, then flip the expected parity
+__device__ __forceinline__ void tma_wait(TmaBar& b) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(b.addr), "r"(b.parity)
+                     : "memory");
+    }
+    b.parity ^= 1u;
+}
+// Where a row of n doubles starting at `src` lands in a 16-byte aligned staging buffer `raw` (n + 2 doubles): the data
+// pointer is raw + (src on an odd double ? 1 : 0), so that the 16-byte aligned body of the row is 16-byte aligned there too.
+__device__ __forceinline__ double* tma_row_ptr(double* raw, const double* src) {
+    return raw + ((reinterpret_cast<unsigned long long>(src) >> 3) & 1ull);
+}
+// one thread: odd head / tail element by plain loads, the aligned body as one bulk copy; returns the bytes announced
+__device__ __forceinline__ unsigned tma_stage_row(const TmaBar& b, double* raw, const double* src, int n) {
+    const int mis = (int)((reinterpret_cast<unsigned long long>(src) >> 3) & 1ull);
+    double* dst = raw + mis;
+    if (mis) dst[0] = src[0];
+    const int body = (n - mis) & ~1;
+    if ((n - mis) & 1) dst[n - 1] = src[n - 1];
+    if (body > 0) tma_bulk_g2s(b, dst + mis, src + mis, (unsigned)body * 8u);
+    return (unsigned)body * 8u;
+}
+__device__ __forceinline__ unsigned tma_row_bytes(const double* src, int n) {
+    const int mis = (int)((reinterpret_cast<unsigned long long>(src) >> 3) & 1ull);
+    return (unsigned)((n - mis) & ~1) * 8u;
+}
+
 // scratch: >= 2 * 32 * 2 doubles of shared memory (double-buffered so one barrier per reduction suffices)
 struct CudaBlock {
     double* scratch;
     int phase;
     long long* prof;         // optional per-phase cycle accumulators (global memory), thread 0 only
     long long t_last;
+    TmaBar tma;              // bulk-copy barrier of this CTA (addr = 0: the kernel stages with plain loads)
     __device__ __forceinline__ explicit CudaBlock(double* s, long long* p = nullptr) : scratch(s), phase(0), prof(p), t_last(0) {
         if (prof) t_last = clock64();
+        tma.addr = 0u;
+        tma.parity = 0u;
     }
     // attribute the cycles since the previous mark to phase `id` (call right after a block-wide barrier)
     __device__ __forceinline__ void mark(int id) {

@@ -58,10 +58,12 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(16) double red[192];
     __shared__ int s_inst;
+    __shared__ __align__(8) unsigned long long s_mbar;
     double* scratch = GS ? gscratch + (size_t)blockIdx.x * sdoubles : smem;
     __shared__ double s_tfv[2 * FTMPC_NF];
     __shared__ int s_tfi[2 * FTMPC_NF];
     CudaBlock blk(red, prof);
+    if (!GS) tma_bar_init(&s_mbar, blk.tma);      // per-instance data is staged by TMA bulk copies when the scratch is shared memory
     const int slot = blockIdx.x;
     const double* sc = ws_slot(io, L, slot) + L.oSc;
     // compact rows of the terminal set (A_f has at most two non-zeros per row; checked by ftmpc_create)
@@ -113,8 +115,10 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 2)
     __shared__ int s_inst;
     __shared__ double s_tfv[2 * FTMPC_NF];
     __shared__ int s_tfi[2 * FTMPC_NF];
+    __shared__ __align__(8) unsigned long long s_mbar;
     double* scratch = smem;
     CudaBlock blk(red, prof);
+    tma_bar_init(&s_mbar, blk.tma);
     const int slot = blockIdx.x;
     const double* sc = ws_slot(io, L, slot) + L.oSc;
     for (int i = threadIdx.x; i < FTMPC_NF; i += blockDim.x) {

@@ -346,7 +346,7 @@ struct LsScratch {
 };
 __host__ __device__ inline size_t ls_scratch_doubles(int N) {
     return (size_t)FTMPC_LS_CHUNK * ((N + 1) * FTMPC_NX + 1 + N * FTMPC_NU + 1) + 96 + FTMPC_HULL_STRIDE +
-           2 * (size_t)(FTMPC_NU * N + 1) + (size_t)(N + 1) * (FTMPC_NE + FTMPC_NU) +
+           2 * (size_t)(FTMPC_NU * N + 1) + (size_t)(N + 1) * (FTMPC_NE + FTMPC_NU) + 8 +
            (size_t)(FTMPC_MAX_POLY + FTMPC_MAX_ROOT) * FTMPC_TERM_REC + FTMPC_TERM_REC + 8;
 }
 __device__ __forceinline__ LsScratch ls_carve(double* buf, int N) {
@@ -359,11 +359,12 @@ __device__ __forceinline__ LsScratch ls_carve(double* buf, int N) {
     s.fa = p; p += 32;
     s.csa = p; p += 32;
     s.cma = p; p += 32;
+    p += ((size_t)(p - buf)) & 1;                  // 16-byte aligned staging buffers (bulk copies)
     s.hull = p; p += FTMPC_HULL_STRIDE;
+    s.xref = p; p += (((size_t)(N + 1) * FTMPC_NE + 2) + 1) & ~(size_t)1;       // + 2: a row may start / end on an odd double
+    s.uref = p; p += (((size_t)(N + 1) * FTMPC_NU + 2) + 1) & ~(size_t)1;
     s.U = p; p += FTMPC_NU * N + 1;
     s.D = p; p += FTMPC_NU * N + 1;
-    s.xref = p; p += (size_t)(N + 1) * FTMPC_NE;
-    s.uref = p; p += (size_t)(N + 1) * FTMPC_NU;
     s.rec = p; p += (size_t)(FTMPC_MAX_POLY + FTMPC_MAX_ROOT) * FTMPC_TERM_REC;
     s.out = p; p += FTMPC_TERM_REC;
     return s;
@@ -519,7 +520,7 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
     double* D = w + L.oD;
     double* X = w + L.oX;
     double* C = w + L.oC;
-    const LsScratch s = ls_carve(scratch, N);
+    LsScratch s = ls_carve(scratch, N);
     const int nterm = cfg.n_poly + cfg.n_root;
     double nu = 1.0, phi0 = 0.0, dphi = 0.0, dmax = 0.0, iter = 0.0, gd_prev = 0.0, f_prev = 0.0, dprev = 0.0, theta_qp = 0.0;
     if (first) {
@@ -552,9 +553,28 @@ __device__ __forceinline__ void phase_ls_block(CudaBlock& blk, const ftmpc_confi
         }
         for (int i = tid; i < L.n; i += nt) { s.U[i] = U[i]; s.D[i] = D[i]; }
     }
-    for (int i = tid; i < FTMPC_HULL_STRIDE; i += nt) s.hull[i] = hull_g[i];
-    for (int i = tid; i < (N + 1) * FTMPC_NE; i += nt) s.xref[i] = xref_g[i];
-    if (uref_g) for (int i = tid; i < (N + 1) * FTMPC_NU; i += nt) s.uref[i] = uref_g[i];
+    // per-instance data -> shared memory: input-bound hull (A_h, b_h), reference window, nominal wrench
+    if (blk.tma.addr) {
+        // TMA: thread 0 issues three bulk copies against the CTA's mbarrier, everybody waits on it
+        double* xr_raw = s.xref;
+        double* ur_raw = s.uref;
+        s.xref = tma_row_ptr(xr_raw, xref_g);
+        if (uref_g) s.uref = tma_row_ptr(ur_raw, uref_g);
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic-proxy accesses of these buffers are done (barrier above)
+            unsigned bytes = FTMPC_HULL_STRIDE * 8u + tma_row_bytes(xref_g, (N + 1) * FTMPC_NE);
+            if (uref_g) bytes += tma_row_bytes(uref_g, (N + 1) * FTMPC_NU);
+            tma_expect(blk.tma, bytes);
+            tma_bulk_g2s(blk.tma, s.hull, hull_g, FTMPC_HULL_STRIDE * 8u);
+            tma_stage_row(blk.tma, xr_raw, xref_g, (N + 1) * FTMPC_NE);
+            if (uref_g) tma_stage_row(blk.tma, ur_raw, uref_g, (N + 1) * FTMPC_NU);
+        }
+        tma_wait(blk.tma);
+    } else {
+        for (int i = tid; i < FTMPC_HULL_STRIDE; i += nt) s.hull[i] = hull_g[i];
+        for (int i = tid; i < (N + 1) * FTMPC_NE; i += nt) s.xref[i] = xref_g[i];
+        if (uref_g) for (int i = tid; i < (N + 1) * FTMPC_NU; i += nt) s.uref[i] = uref_g[i];
+    }
     blk.sync();
     const double* xrefN = s.xref + N * FTMPC_NE;
     // A. rollouts, one step length per lane
