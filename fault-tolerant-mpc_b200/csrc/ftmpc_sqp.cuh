@@ -902,7 +902,10 @@ struct MpcCons {
 };
 
 // per-CTA scratch carved out of one buffer of doubles (shared memory on the device)
+// horizons above this use the O(N^2) condensing (condense_long) in the generic path
+#define FTMPC_LONG_N 20
 struct QpScratch {
+    double* GL;                  // condense_long: sensitivity columns G_t[:, a], t = j+1 .. N, per column a = 6 j + ja
     const ftmpc_config* cg;      // configuration copy addressable per thread (global memory on the device)
     const double* tf_val;        // compact terminal-set rows (see StepIO), nullptr -> dense rows of cg->Af
     const int* tf_idx;
@@ -920,7 +923,8 @@ FT_HD size_t qp_scratch_doubles(int N) {
     size_t tt = (size_t)FTMPC_NE * n;
     if (tt > gi_vec) gi_vec = tt;
     size_t ints = ((nv + 1) + L.m + (nv + 1) + 1) / 2 + 1;
-    return ne * nv + rs + (size_t)FTMPC_NX * nv + gi_vec + 2 * nv /*g, ga*/ + 90 /*taug*/ + L.mc /*cv*/ + FTMPC_HULL_STRIDE + ints + 8;
+    const size_t gl = (N > FTMPC_LONG_N) ? (size_t)FTMPC_NX * FTMPC_NU * N * (N + 1) / 2 : 0;     // condense_long: G_t columns
+    return ne * nv + rs + (size_t)FTMPC_NX * nv + gi_vec + 2 * nv /*g, ga*/ + 90 /*taug*/ + L.mc /*cv*/ + FTMPC_HULL_STRIDE + ints + 8 + gl;
 }
 FT_HD QpScratch qp_carve(double* buf, int N, const ftmpc_config* cg = nullptr) {
     const WsLayout L = ws_layout(N);
@@ -961,7 +965,164 @@ FT_HD QpScratch qp_carve(double* buf, int N, const ftmpc_config* cg = nullptr) {
     s.gi.pos = ip; ip += L.m;
     s.gi.itmp = ip; ip += nv + 1;
     s.total = qp_scratch_doubles(N);
+    s.GL = (N > FTMPC_LONG_N) ? buf + s.total - (size_t)FTMPC_NX * FTMPC_NU * N * (N + 1) / 2 : nullptr;
     return s;
+}
+
+// ---- O(N^2) condensing for long horizons -------------------------------------------------------------------------
+// Same H, g, ga, G_N as `condense` below, which accumulates the rank-13 stage updates G_t' M_t G_t over the whole live
+// block of H at every stage: O(N^3) operations and read-modify-write traffic on H (96 M multiply-adds at N = 100, half the
+// time of a long-horizon solve).  Here every COLUMN a = 6 j + ja of the sensitivities is independent:
+//   forward   G_{j+1}[:, a] = B_j e_ja,   G_{t+1}[:, a] = A_t G_t[:, a]                      (stored, t = j+1 .. N)
+//   backward  P_N = Ht G_N[:, a];   for t = N-1 .. j+1:   H[6t.., a] = B_t' P_{t+1} + W_ux,t G_t[:, a],
+//                                                          P_t = M_t G_t[:, a] + A_t' P_{t+1};
+//             H[6j.., a] = B_j' P_{j+1} + W_uu,j[:, ja]
+// so each entry of H is written once, 17 M multiply-adds at N = 100, one thread per column, no barrier inside.  The
+// gradient (and its augmented-Lagrangian twin) are two more costate recursions.
+// M_t = diag(2Q, 0) + [theta sym(W_t) + Cq_t^GN on (omega, q)],  W_ux / W_uu = the input rows of the same stage matrix.
+template <class Blk>
+FT_HD void condense_long(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const QpScratch& s, const double* Jz,
+                         const double* Wz, const double* X, const double* U, const double* xref, const double* gradV,
+                         const double* hessV, double theta, double sigma, const double* lam_prev, const double* Cq) {
+    const int N = L.N, n = L.n, ld = L.nv, tid = blk.tid(), nt = blk.nthreads();
+    double* H = s.E;
+    double* GL = s.GL;
+    const double* Ah = s.hull;
+    // terminal rows of the augmentation: 9x9 matrix + 9-vector (as in `condense`)
+    for (int idx = tid; idx < 90; idx += nt) {
+        double v = 0.0;
+        if (sigma > 0.0) {
+            const int kk = idx / 9, l = idx % 9;
+            for (int i = 0; i < FTMPC_NF; ++i) {
+                if (lam_prev[FTMPC_NH * N + i] > 0.0) {
+                    const double a = cfg.Af[i * FTMPC_NE + l];
+                    v += (idx < 81) ? cfg.Af[i * FTMPC_NE + kk] * a : s.cv[FTMPC_NH * N + i] * a;
+                }
+            }
+        }
+        s.taug[idx] = sigma * v;
+    }
+    if (tid == 0) { s.g[n] = 0.0; s.ga[n] = 0.0; }
+    for (int r = tid; r < FTMPC_NX; r += nt) s.G[r * ld + n] = 0.0;
+    blk.sync();
+    auto gl_base = [&](int j, int ja) { return GL + (size_t)FTMPC_NX * ((size_t)FTMPC_NU * ((size_t)j * N - (size_t)j * (j - 1) / 2) + (size_t)ja * (N - j)); };
+    auto symw = [&](const double* wz, int r, int c) { return 0.5 * (wz[r * 13 + c] + wz[c * 13 + r]); };
+    // A_t' p  (A_t = [[I, dt I, *], [0, I, *], [0, 0, *]] with the (omega, q) columns in jz[l*13 + r], l < 7)
+    auto at_times = [&](const double* jz, const double* p, double* out) {
+        for (int c = 0; c < 3; ++c) out[c] = p[c];
+        for (int c = 3; c < 6; ++c) out[c] = p[c] + cfg.dt * p[c - 3];
+        for (int l = 0; l < 7; ++l) {
+            double v = 0.0;
+            for (int r = 0; r < FTMPC_NX; ++r) v += jz[l * 13 + r] * p[r];
+            out[6 + l] = v;
+        }
+    };
+    for (int a = tid; a < n + 2; a += nt) {
+        if (a >= n) {
+            // ---- costates of the gradient (a == n) and of the terminal augmentation (a == n + 1)
+            const bool aug = (a == n + 1);
+            double p[FTMPC_NX], q[FTMPC_NX];
+            for (int r = 0; r < FTMPC_NX; ++r) p[r] = 0.0;
+            for (int kk = 0; kk < FTMPC_NE; ++kk) p[kk] = aug ? s.taug[81 + kk] : gradV[kk];
+            for (int t = N - 1; t >= 0; --t) {
+                const double* jz = Jz + (size_t)t * 169;
+                for (int i = 0; i < FTMPC_NU; ++i) {
+                    double v = 0.0;
+                    for (int r = 0; r < FTMPC_NX; ++r) v += jz[(7 + i) * 13 + r] * p[r];
+                    if (aug) {
+                        double av = 0.0;
+                        if (sigma > 0.0)
+                            for (int k = 0; k < FTMPC_NH; ++k)
+                                if (lam_prev[t * FTMPC_NH + k] > 0.0) av += s.cv[t * FTMPC_NH + k] * Ah[k * FTMPC_NU + i];
+                        s.T[t * FTMPC_NU + i] = v + sigma * av;              // ga - g, combined below
+                    } else {
+                        s.g[t * FTMPC_NU + i] = v + 2.0 * cfg.R[i] * (U[t * FTMPC_NU + i] - (Cq ? Cq[(size_t)t * FTMPC_CQ + 32 + i] : 0.0));
+                    }
+                }
+                at_times(jz, p, q);
+                for (int r = 0; r < FTMPC_NX; ++r) p[r] = q[r];
+                if (!aug && t > 0) {
+                    for (int kk = 0; kk < FTMPC_NE; ++kk) p[kk] += 2.0 * cfg.Q[kk] * (X[t * FTMPC_NX + kk] - xref[t * FTMPC_NE + kk]);
+                    if (Cq) for (int l = 0; l < 4; ++l) p[9 + l] += Cq[(size_t)t * FTMPC_CQ + l];
+                }
+            }
+            continue;
+        }
+        const int j = a / FTMPC_NU, ja = a - j * FTMPC_NU;
+        double* gcol = gl_base(j, ja);                      // G_t[:, a] at gcol + 13 (t - j - 1)
+        // ---- forward
+        double g[FTMPC_NX], gn[FTMPC_NX];
+        {
+            const double* jz = Jz + (size_t)j * 169;
+            for (int r = 0; r < FTMPC_NX; ++r) { g[r] = jz[(7 + ja) * 13 + r]; gcol[r] = g[r]; }
+        }
+        for (int t = j + 1; t < N; ++t) {                   // G_{t+1} = A_t G_t
+            const double* jz = Jz + (size_t)t * 169;
+            for (int r = 0; r < FTMPC_NX; ++r) {
+                double v = (r < 3) ? g[r] + cfg.dt * g[r + 3] : ((r < 6) ? g[r] : 0.0);
+                for (int l = 0; l < 7; ++l) v += jz[l * 13 + r] * g[6 + l];
+                gn[r] = v;
+            }
+            double* o = gcol + (size_t)FTMPC_NX * (t - j);
+            for (int r = 0; r < FTMPC_NX; ++r) { g[r] = gn[r]; o[r] = gn[r]; }
+        }
+        for (int r = 0; r < FTMPC_NX; ++r) s.G[r * ld + a] = g[r];     // G_N[:, a]
+        // ---- backward
+        double p[FTMPC_NX], q[FTMPC_NX];
+        for (int kk = 0; kk < FTMPC_NE; ++kk) {
+            double v = 0.0;
+            for (int l = 0; l < FTMPC_NE; ++l) {
+                const double q0 = cfg.term_quad[kk * FTMPC_NE + l];
+                v += (q0 + theta * (hessV[kk * FTMPC_NE + l] - q0) + s.taug[kk * FTMPC_NE + l]) * g[l];
+            }
+            p[kk] = v;
+        }
+        for (int r = FTMPC_NE; r < FTMPC_NX; ++r) p[r] = 0.0;
+        for (int t = N - 1; t > j; --t) {
+            const double* jz = Jz + (size_t)t * 169;
+            const double* wz = Wz + (size_t)t * 169;
+            const double* gt = gcol + (size_t)FTMPC_NX * (t - j - 1);
+            const double* cq = Cq ? Cq + (size_t)t * FTMPC_CQ : nullptr;
+            for (int i = 0; i < FTMPC_NU; ++i) {            // H[6t + i][a] = B_t' P_{t+1} + W_ux,t G_t[:, a]
+                double v = 0.0, wv = 0.0;
+                for (int r = 0; r < FTMPC_NX; ++r) v += jz[(7 + i) * 13 + r] * p[r];
+                for (int l = 0; l < 7; ++l) wv += symw(wz, 7 + i, l) * gt[6 + l];
+                wv *= theta;
+                if (cq && i < 3) for (int l = 0; l < 4; ++l) wv += cq[4 + i * 4 + l] * gt[9 + l];
+                H[(size_t)(FTMPC_NU * t + i) * ld + a] = v + wv;
+            }
+            at_times(jz, p, q);                              // P_t = M_t G_t + A_t' P_{t+1}
+            for (int kk = 0; kk < FTMPC_NE; ++kk) q[kk] += 2.0 * cfg.Q[kk] * gt[kk];
+            for (int kk = 0; kk < 7; ++kk) {
+                double v = 0.0;
+                for (int l = 0; l < 7; ++l) v += symw(wz, kk, l) * gt[6 + l];
+                v *= theta;
+                if (cq && kk >= 3) for (int l = 0; l < 4; ++l) v += cq[16 + (kk - 3) * 4 + l] * gt[9 + l];
+                q[6 + kk] += v;
+            }
+            for (int r = 0; r < FTMPC_NX; ++r) p[r] = q[r];
+        }
+        {
+            const double* jz = Jz + (size_t)j * 169;
+            const double* wz = Wz + (size_t)j * 169;
+            for (int i = ja; i < FTMPC_NU; ++i) {           // diagonal block, lower triangle: rows i >= ja
+                double v = 0.0;
+                for (int r = 0; r < FTMPC_NX; ++r) v += jz[(7 + i) * 13 + r] * p[r];
+                v += theta * symw(wz, 7 + i, 7 + ja);
+                if (i == ja) v += 2.0 * cfg.R[i];
+                if (sigma > 0.0) {
+                    double av = 0.0;
+                    for (int k = 0; k < FTMPC_NH; ++k)
+                        if (lam_prev[j * FTMPC_NH + k] > 0.0) av += Ah[k * FTMPC_NU + i] * Ah[k * FTMPC_NU + ja];
+                    v += sigma * av;
+                }
+                H[(size_t)(FTMPC_NU * j + i) * ld + a] = v;
+            }
+        }
+    }
+    blk.sync();
+    for (int a = tid; a < n; a += nt) s.ga[a] = s.g[a] + s.T[a];
+    blk.sync();
 }
 
 // condensed Hessian (lower triangle of the n x n block of E, ld = nv) and gradient at blend theta
@@ -971,6 +1132,10 @@ FT_HD void condense(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
                     const double* hessV, double theta, double sigma, const double* lam_prev, const double* Cq = nullptr) {
     // Cq: input-cost coupling records of an accelerating reference (FTMPC_CQ) or nullptr
     const int N = L.N, n = L.n, ld = L.nv, tid = blk.tid(), nt = blk.nthreads();
+    if (s.GL && (cfg.qp_method & 8) == 0) {            // long horizons: O(N^2) column-wise condensing (bit 3 keeps the O(N^3) form)
+        condense_long(blk, cfg, L, s, Jz, Wz, X, U, xref, gradV, hessV, theta, sigma, lam_prev, Cq);
+        return;
+    }
     double* H = s.E;
     double* G = s.G;          // 13 x ld, current d x_t / d U
     double* T = s.T;
@@ -1535,6 +1700,23 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
                 double pa[6], tb[6], pn[6], tn[6];
 #pragma unroll
                 for (int i = 0; i < 6; ++i) { pa[i] = Pa[i]; tb[i] = Tb[i]; }
+#if !defined(FTMPC_UNROLL_COND)
+                // the row loop is ROLLED (800 B instead of 10 KB of straight-line code per stage): +4.7 % solves/s on the B200 --
+                // the unrolled form stalled on instruction fetch (profiles/README.md, r02k)
+                const int nr = (t < N) ? FTMPC_NX : FTMPC_NE;
+#pragma unroll 1
+                for (int r = 0; r < nr; ++r) {
+                    const int rn = (r + 1 < nr) ? r + 1 : r;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) { pn[i] = Pa[(size_t)rn * ldp + i]; tn[i] = Tb[(size_t)rn * ldp + i]; }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i)
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) acc[i][j] += pa[i] * tb[j];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) { pa[i] = pn[i]; tb[i] = tn[i]; }
+                }
+#else
 #pragma unroll
                 for (int r = 0; r < FTMPC_NX; ++r) {
                     if (r < FTMPC_NE || t < N) {               // the terminal stage has 9 rows (uniform branch)
@@ -1550,6 +1732,7 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
                         for (int i = 0; i < 6; ++i) { pa[i] = pn[i]; tb[i] = tn[i]; }
                     }
                 }
+#endif
             } else if (bi == t) {
                 if (bj < t) {
                     // new block row: theta W_ux G_t   (row i of the block <- input i, column j <- column 6 bj + j)
@@ -1748,6 +1931,23 @@ __device__ __forceinline__ int chol_inv_blocks(CudaBlock& blk, int Nb, int ld, d
             } else {
                 // second operand: rows 6 bj .. of E at columns 6k..: L_jk (j > k, lower triangle) or X_kj^T (j < k, upper
                 // triangle) -- the same addressing, only the sign of the product differs
+                const double sgn = (bj > k) ? -1.0 : 1.0;
+#if defined(FTMPC_ROLL_CHOL)
+                // rank-1 form with the inner-dimension loop ROLLED (12 operand loads + 36 FMAs per trip instead of 216 FMAs of
+                // straight-line code): the instruction footprint of the sweep, not its arithmetic, was what stalled it
+                const double* ea = E + (size_t)(6 * bi) * ld + 6 * k;
+                const double* eb = E + (size_t)(6 * bj) * ld + 6 * k;
+#pragma unroll 1
+                for (int m = 0; m < 6; ++m) {
+                    double a6[6], b6[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) { a6[i] = sgn * ea[(size_t)i * ld + m]; b6[i] = eb[(size_t)i * ld + m]; }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i)
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) acc[i][j] += a6[i] * b6[j];
+                }
+#else
                 double Ob[6][6];
 #pragma unroll
                 for (int j = 0; j < 6; ++j) {
@@ -1755,7 +1955,6 @@ __device__ __forceinline__ int chol_inv_blocks(CudaBlock& blk, int Nb, int ld, d
 #pragma unroll
                     for (int m = 0; m < 6; ++m) Ob[j][m] = er[m];
                 }
-                const double sgn = (bj > k) ? -1.0 : 1.0;
 #pragma unroll
                 for (int i = 0; i < 6; ++i) {
                     const double* er = E + (size_t)(6 * bi + i) * ld + 6 * k;
@@ -1770,6 +1969,7 @@ __device__ __forceinline__ int chol_inv_blocks(CudaBlock& blk, int Nb, int ld, d
                         acc[i][j] = v;
                     }
                 }
+#endif
                 if (bi == k + 1 && bj == k + 1) chol_diag_block(acc, k + 1, ld, E, linv, flag, piv_tol);
             }
         }
