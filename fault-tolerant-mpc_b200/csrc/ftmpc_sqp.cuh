@@ -904,6 +904,7 @@ struct MpcCons {
 // per-CTA scratch carved out of one buffer of doubles (shared memory on the device)
 // horizons above this use the O(N^2) condensing (condense_long) in the generic path
 #define FTMPC_LONG_N 20
+#define FTMPC_RIC_WORK 1100      /* doubles of scratch riccati_factor needs (ftmpc_riccati.cuh) */
 struct QpScratch {
     double* GL;                  // condense_long: sensitivity columns G_t[:, a], t = j+1 .. N, per column a = 6 j + ja
     const ftmpc_config* cg;      // configuration copy addressable per thread (global memory on the device)
@@ -924,7 +925,9 @@ FT_HD size_t qp_scratch_doubles(int N) {
     if (tt > gi_vec) gi_vec = tt;
     size_t ints = ((nv + 1) + L.m + (nv + 1) + 1) / 2 + 1;
     const size_t gl = (N > FTMPC_LONG_N) ? (size_t)FTMPC_NX * FTMPC_NU * N * (N + 1) / 2 : 0;     // condense_long: G_t columns
-    return ne * nv + rs + (size_t)FTMPC_NX * nv + gi_vec + 2 * nv /*g, ga*/ + 90 /*taug*/ + L.mc /*cv*/ + FTMPC_HULL_STRIDE + ints + 8 + gl;
+    size_t gw = (size_t)FTMPC_NX * nv;                 // G = d x_N / d U of the dense path; workspace of riccati_factor
+    if (gw < FTMPC_RIC_WORK) gw = FTMPC_RIC_WORK;
+    return ne * nv + rs + gw + gi_vec + 2 * nv /*g, ga*/ + 90 /*taug*/ + L.mc /*cv*/ + FTMPC_HULL_STRIDE + ints + 8 + gl;
 }
 FT_HD QpScratch qp_carve(double* buf, int N, const ftmpc_config* cg = nullptr) {
     const WsLayout L = ws_layout(N);
@@ -938,7 +941,7 @@ FT_HD QpScratch qp_carve(double* buf, int N, const ftmpc_config* cg = nullptr) {
     size_t rs = nv * (nv + 1) / 2;
     if ((size_t)N * 338 > rs) rs = (size_t)N * 338;
     s.RS = p; p += rs;
-    s.G = p; p += (size_t)FTMPC_NX * nv;
+    s.G = p; p += ((size_t)FTMPC_NX * nv < FTMPC_RIC_WORK) ? (size_t)FTMPC_RIC_WORK : (size_t)FTMPC_NX * nv;
     s.g = p; p += nv;
     s.ga = p; p += nv;
     s.taug = p; p += 90;
@@ -2057,6 +2060,36 @@ extern thread_local int g_ftmpc_warm_hit;
 #define FT_DBG_COUNT(k) ((void)0)
 #endif
 
+}  // namespace ftmpc
+#include "ftmpc_riccati.cuh"      // needs FTMPC_CQ and the scratch structs above
+namespace ftmpc {
+
+// the dense path (condense + Cholesky + L^-T) stays selectable on the host (qp_method bit 4) and in CUDA builds made
+// with -DFTMPC_DENSE_FACTOR (A/B measurements); the product kernel carries only the Riccati factorisation
+#if !defined(__CUDACC__) || defined(FTMPC_DENSE_FACTOR)
+#define FTMPC_HAVE_DENSE_FACTOR 1
+#else
+#define FTMPC_HAVE_DENSE_FACTOR 0
+#endif
+
+// ---- J, X J, g, ga, J' ga by the Riccati factorisation (ftmpc_riccati.cuh); same contract as factor_hessian ---------
+template <class Blk>
+FT_HD int factor_riccati(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const QpScratch& s, double* Jz, double* Wz,
+                         const double* Jz_src, const double* Wz_src, const double* X, const double* U, const double* xref,
+                         const double* gradV, const double* hessV, double theta, double sigma, const double* lam_prev,
+                         double* dscale_out, bool copy_j, bool copy_w, const double* Cq) {
+    const int N = L.N, tid = blk.tid(), nt = blk.nthreads();
+    // the linearisation may have left Jz / Wz in place; the stage records overwrite Wz, so another attempt re-reads it
+    if (copy_j) for (int i = tid; i < N * 169; i += nt) Jz[i] = Jz_src[i];
+    if (copy_w) for (int i = tid; i < N * 169; i += nt) Wz[i] = Wz_src[i];
+    blk.sync();
+    const int bad = riccati_factor(blk, cfg, L, s, Jz, Wz, X, U, xref, gradV, hessV, theta, sigma, lam_prev, Cq, s.G, s.E,
+                                   dscale_out);
+    blk.mark(PH_CHOL);
+    blk.count(CT_CONDENSE);
+    return bad;
+}
+
 // ---- phase_qp ------------------------------------------------------------------------------------------
 template <class Blk>
 FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst, int slot, double* scratch,
@@ -2100,12 +2133,22 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     bool aug_allowed = can_aug;
     int fails = 0, qit = 0, nact = 0, st = GI_OK, aug_retry = 0;
     bool have_j = staged, have_w = staged;
+#if FTMPC_HAVE_DENSE_FACTOR
+    const bool dense_factor = (cfg.qp_method & 16) != 0;      // bit 4: condensed Hessian + Cholesky + triangular inverse (the round-1 path)
+#endif
     for (;;) {        // QP attempts (re-solved without augmentation if a predicted-active row came out inactive)
     double sig0 = 0.0;
     for (;;) {
         double dscale = 0.0;
-        const int bad = factor_hessian(blk, cfg, L, s, Jz, Wz, w + L.oJz, w + L.oWz, w + L.oX, w + L.oU, xref, w + L.oGV,
-                                       w + L.oHV, theta, sigma, lam_prev, &dscale, !have_j, !have_w, io.uref ? w + L.oCq : nullptr);
+        int bad;
+#if FTMPC_HAVE_DENSE_FACTOR
+        if (dense_factor)
+            bad = factor_hessian(blk, cfg, L, s, Jz, Wz, w + L.oJz, w + L.oWz, w + L.oX, w + L.oU, xref, w + L.oGV,
+                                 w + L.oHV, theta, sigma, lam_prev, &dscale, !have_j, !have_w, io.uref ? w + L.oCq : nullptr);
+        else
+#endif
+            bad = factor_riccati(blk, cfg, L, s, Jz, Wz, w + L.oJz, w + L.oWz, w + L.oX, w + L.oU, xref, w + L.oGV,
+                                 w + L.oHV, theta, sigma, lam_prev, &dscale, !have_j, !have_w, io.uref ? w + L.oCq : nullptr);
         have_j = true;                  // Jz survives a failed factorisation, the scaled Wz does not
         have_w = false;
         if (!bad) break;
@@ -2130,6 +2173,8 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         s.E[(size_t)n * ld + i] = (i == n) ? 1.0 / sqrt(cfg.rho_slack) : 0.0;
     }
     blk.sync();
+#if FTMPC_HAVE_DENSE_FACTOR
+    if (dense_factor) {
     // column i of [X J ; ga' J]: ten accumulators share one sweep down column i of J (J is upper triangular)
     for (int i = tid; i < nv; i += nt) {
         double acc[FTMPC_NE + 1];
@@ -2143,6 +2188,14 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         }
         for (int kk = 0; kk < FTMPC_NE; ++kk) s.E[(size_t)(nv + kk) * ld + i] = acc[kk];
         s.gi.d[i] = acc[FTMPC_NE];
+    }
+    } else
+#endif
+    {   // riccati_factor has written X J and J' ga; only the slack column is left
+        for (int kk = tid; kk <= FTMPC_NE; kk += nt) {
+            if (kk < FTMPC_NE) s.E[(size_t)(nv + kk) * ld + n] = 0.0;
+            else s.gi.d[n] = 0.0;
+        }
     }
     blk.sync();
     // unconstrained minimiser  x = -J J' ga  (extended coordinates)

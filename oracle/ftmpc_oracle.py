@@ -4,19 +4,27 @@ Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl
 import this module.  The product package (`fault-tolerant-mpc_b200/`, imported as `ft_mpc_b200`)
 never does; it fails loudly when its CUDA library is missing.
 
-PARITY: pinned for the problem definition, UNPINNED for the NLP solve.
-  * Pinned against the reference's own code: tools/gen_ref_fixtures.py executes ft_mpc.util.utils,
-    ft_mpc.models.sys_model / spiral_model, SpiralParameters, InputBounds and get_trajectory in the build
-    container (numeric stand-in for the few CasADi calls they make) and tests/test_reference_fixtures.py
-    checks every model function below against those outputs (tests/golden/ref_fixtures.npz) -- including the
-    ROW ORDER of the input-bound hull, i.e. the numbering of the constraints -- and, likewise executed from the
-    reference, SpiralingController.assign_trajectory / get_next_trajectory_part (reference window + nominal wrench)
-    and the CSV written by ControllerDebug.export.  The stored terminal
-    ingredients (config/terminal.yaml) are pinned through sympy evaluation (tools/gen_terminal_data.py).
-  * Unpinned: the reference ships no tests or golden vectors for solve_mpc, and casadi 3.6.7 / IPOPT and
-    cvxpy 1.6.4 / OSQP are not installable here, so the optimiser outputs (KKT point, active set, thrust)
-    come from an independent solver on the restated NLP (scipy SLSQP + Newton polish to tight KKT
-    tolerance); every function cites the reference file:line it follows (paths relative to /root/reference).
+PARITY: the problem definition, the NLP (f, g, lbg, ubg, row order), the allocation QP and the get_control
+post-processing are PINNED against the reference's own code; which local solution IPOPT (tol 1e-3) would return is not.
+  * tools/gen_ref_fixtures.py executes ft_mpc.util.utils, ft_mpc.models.sys_model / spiral_model, SpiralParameters,
+    InputBounds and get_trajectory in the build container (numeric stand-in for the few CasADi calls they make) and
+    tests/test_reference_fixtures.py checks every model function below against those outputs
+    (tests/golden/ref_fixtures.npz) -- including the ROW ORDER of the input-bound hull, i.e. the numbering of the
+    constraints -- and, likewise executed from the reference, SpiralingController.assign_trajectory /
+    get_next_trajectory_part (reference window + nominal wrench) and the CSV written by ControllerDebug.export.
+    The stored terminal ingredients (config/terminal.yaml) are pinned through sympy evaluation
+    (tools/gen_terminal_data.py).
+  * tools/gen_ref_nlp_fixtures.py executes the reference's SpiralingController.__init__ -> set_model /
+    set_cost_functions / build_solver (spiraling_mpc.py:27-238), ControlAllocator.__init__ / get_physical_input
+    (control_allocator.py:12-95) and get_control (:288-317) on numeric casadi / cvxpy stand-ins and records f(z,p),
+    g(z,p), lbg, ubg of the reference's `nlp` dict at seeded decision vectors (non-zero u_ref included), the
+    allocation QP's data and the thrust the reference's own post-processing returns for a prescribed NLP solution;
+    tests/test_reference_nlp.py holds Problem.nlp_eval, allocate and get_control below to them (1e-12).
+  * Not pinnable here: the reference ships no tests or golden vectors for solve_mpc, and casadi 3.6.7 / IPOPT and
+    cvxpy 1.6.4 / OSQP are not installable offline, so the optimiser OUTPUT (KKT point, active set) comes from an
+    independent solver on the (pinned) NLP: scipy SLSQP + Newton polish to tight KKT tolerance.  The NLP is
+    non-convex; "same local minimum as IPOPT" rests on the survey's probe and stays a stated assumption.
+Every function cites the reference file:line it follows (paths relative to /root/reference).
 
 Derivatives in this file are obtained by complex-step differentiation (the prediction model is a
 polynomial map, so complex-step is exact to rounding) -- deliberately independent of the
