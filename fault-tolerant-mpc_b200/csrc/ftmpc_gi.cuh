@@ -711,6 +711,8 @@ __device__ __forceinline__ int gi_solve(CudaBlock& blk, const Cons& cons, const 
     // row sweeps over E: a lane pair per row (gi_pair_row), rpp = nt / 2 rows per pass; ne_main rows are covered by full
     // passes, up to 2 nw rows left over after the last full pass are swept one per warp instead of paying a whole pass
     const int rpp = nt >> 1, prow = gi_pair_row(tid), part = tid & 1;
+    // (with E in global memory -- long horizons -- a whole warp per row, lanes along the row, was measured 2x slower than
+    //  this lane-pair mapping: 16 rows in flight per warp hide the latency, and the pair shares every 32-byte sector)
     const int ne_main = ((nt & 31) != 0) ? 0 : ((ne % rpp <= 2 * nw) ? ne - ne % rpp : ne);
     int q = 0, iters = 0, status = GI_OK;
     for (int i = tid; i < m; i += nt) {

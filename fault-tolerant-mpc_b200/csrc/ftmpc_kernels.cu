@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
             // with the shared-memory scratch the linearisation leaves Jz / Wz where condensing reads them
             const bool staged = !GS && lin_scratch_doubles(L.N) <= (size_t)(L.nv + FTMPC_NE) * L.nv && condense_fast_path(L, blockDim.x);
             phase_lin(blk, cfg, L, io, inst, slot, lin_place_v1(scratch, L.N, staged));
-            phase_qp(blk, cfg, L, io, inst, slot, scratch, staged);
+            phase_qp(blk, cfg, L, io, inst, slot, scratch, staged, GS ? smem : nullptr);
             phase_ls_block(blk, cfg, L, io, inst, slot, 0, scratch);
         }
         phase_out_write(blk, cfg, L, io, inst, slot);
@@ -617,7 +617,7 @@ static int launch_step(ftmpc_ctx* h, const StepIO& io, void* workspace, size_t n
         CU(cudaEventRecord(h->ev[0], stream));
     }
     if (use_global)
-        k_solve<true><<<grid, FTMPC_QP_THREADS, 0, stream>>>(h->cfg, L, io, queue, gscratch, sdoubles,
+        k_solve<true><<<grid, FTMPC_QP_THREADS, FTMPC_RIC_WORK * sizeof(double), stream>>>(h->cfg, L, io, queue, gscratch, sdoubles,
                                                              h->profile ? h->d_prof : nullptr);
     else
         k_solve<false><<<grid, FTMPC_QP_THREADS, smem, stream>>>(h->cfg, L, io, queue, nullptr, 0,

@@ -44,7 +44,11 @@ FT_HD int ric_chol6(double (&A)[6][6], double (&Ci)[6][6], double piv_tol) {
 #pragma unroll
         for (int m = 0; m < 6; ++m) if (m < j) d -= A[j][m] * A[j][m];
         if (!(d > piv_tol) && !bad) bad = j + 1;
+#if defined(__CUDA_ARCH__)
+        const double rs = rsqrt(d);
+#else
         const double rs = 1.0 / sqrt(d);
+#endif
         inv[j] = rs;
         A[j][j] = d * rs;
 #pragma unroll
@@ -74,6 +78,243 @@ FT_HD int ric_chol6(double (&A)[6][6], double (&Ci)[6][6], double piv_tol) {
     return bad;
 }
 
+// (row, col) of the idx-th entry of a lower triangle stored by rows: idx = row (row + 1) / 2 + col
+FT_HD void ric_tri(int idx, int& row, int& col) {
+    int r = (int)((sqrtf(8.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
+    while ((r + 1) * (r + 2) / 2 <= idx) ++r;
+    while (r * (r + 1) / 2 > idx) --r;
+    row = r;
+    col = idx - r * (r + 1) / 2;
+}
+
+#if defined(__CUDACC__)
+// ---- backward sweep, CUDA block of 256 threads -------------------------------------------------------------------
+// The generic sweep below pays four block barriers per stage, each with a fixed cost (hand-over through shared memory,
+// task decode, the slowest warp) that is several times the 13-long multiply-add chains it separates, and during the 6x6
+// Cholesky seven of the eight warps wait.  Here a stage is TWO barrier intervals:
+//   AB  one group of 10 lanes per column c2 of [A B] (3 groups per warp, warps 0-6): the group forms P [A B][:, c2]
+//       (13 entries over 10 lanes), __syncwarp, then its ten entries F[(c2 + j) mod 19][c2], j = 0..9, of the symmetric
+//       19 x 19 matrix (the circulant assignment gives every column the same load and covers each pair once).  Warp 7
+//       advances the costates / gradients.
+//   CD  thread (r, c), c <= r, of the 91 entries of P_t factors Lam = F_uu ITSELF (the 6x6 Cholesky is a serial chain
+//       either way; 91 redundant copies cost nothing but otherwise idle issue slots), forward-substitutes the two
+//       columns r and c of F_ux alongside, and writes P_t[r][c] = F[r][c] - kh_r . kh_c.  Threads (r, 0) leave Kh[:, r] in
+//       the stage record, thread (0, 0) the factor C.
+// K_t = C^-T Kh_t and the columns of C_t^-T (what the forward rollouts read) are not on the critical path: one parallel
+// pass over all stages after the sweep turns (C, Kh) into them by back substitution.
+__device__ __forceinline__ int ric_backward_cuda(CudaBlock& blk, const ftmpc_config& cfg, int N, const double* Jz, double* Wz,
+                                                 double theta, bool aug, const double* Cq, double* P, double* PABs, double* F,
+                                                 double* cst, double* flg, const double* pre, const double* hau, double* g_out,
+                                                 double* ga_out, double* dscale_out) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // ---- AB roles
+    const int grp = 3 * warp + lane / 10, j10 = lane % 10;
+    const bool ab_on = warp < 7 && lane < 30 && grp < 19;
+    const int c2 = ab_on ? grp : 0;
+    const int c1 = (c2 + j10) % 19;
+    const int hi = c1 > c2 ? c1 : c2, lo = c1 > c2 ? c2 : c1;
+    // stage-Hessian entry (hi, lo): constant diagonal, offsets of the two W entries, optional Cq / hull-augmentation slots
+    double h_diag = 0.0;
+    int h_o1 = -1, h_o2 = -1, h_cq = -1, h_au = -1;
+    if (ab_on) {
+        if (hi == lo) h_diag = (hi < FTMPC_NE) ? 2.0 * cfg.Q[hi < FTMPC_NE ? hi : 0] : ((hi >= 13) ? 2.0 * cfg.R[hi - 13] : 0.0);
+        if (lo >= 6) {
+            const int k1 = hi - 6, k2 = lo - 6;
+            h_o1 = k1 * 13 + k2; h_o2 = k2 * 13 + k1;
+            if (k1 >= 3 && k1 < 7 && k2 >= 3) h_cq = 16 + (k1 - 3) * 4 + (k2 - 3);
+            else if (k1 >= 7 && k1 < 10 && k2 >= 3 && k2 < 7) h_cq = 4 + (k1 - 7) * 4 + (k2 - 3);
+            if (k2 >= 7) h_au = (k1 - 7) * (k1 - 6) / 2 + k2 - 7;
+        }
+    }
+    // ---- CD roles
+    int d_r = 0, d_c = 0;
+    ric_tri(tid < 91 ? tid : 0, d_r, d_c);
+    const bool cd_on = tid < 91;
+    for (int t = N - 1; t >= 0; --t) {
+        const double* jz = Jz + (size_t)t * 169;
+        double* wz = Wz + (size_t)t * 169;
+        // ================= AB
+        if (ab_on) {
+            const int ra = j10, rb = 10 + j10;                      // rows of P [A B][:, c2]: lanes 0-2 of the group take two
+            double va, vb = 0.0;
+            if (c2 < 6) {
+                const int cc = (c2 < 3) ? c2 : c2 - 3;
+                va = (c2 < 3) ? P[ra * 13 + c2] : cfg.dt * P[ra * 13 + cc] + P[ra * 13 + c2];
+                if (j10 < 3) vb = (c2 < 3) ? P[rb * 13 + c2] : cfg.dt * P[rb * 13 + cc] + P[rb * 13 + c2];
+            } else {
+                const double* col = jz + (c2 - 6) * 13;
+                const double* pa = P + ra * 13;
+                const double* pb = P + ((j10 < 3) ? rb : ra) * 13;
+                double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 12; k += 2) {
+                    const double x0 = col[k], x1 = col[k + 1];
+                    a0 += pa[k] * x0; a1 += pa[k + 1] * x1;
+                    b0 += pb[k] * x0; b1 += pb[k + 1] * x1;
+                }
+                va = a0 + a1 + pa[12] * col[12];
+                vb = b0 + b1 + pb[12] * col[12];
+            }
+            PABs[c2 * 13 + ra] = va;
+            if (j10 < 3) PABs[c2 * 13 + rb] = vb;
+        } else if (warp == 7 && lane < 19) {
+            // costates of stage t and the gradient entries of stage t (kind 0: cost, kind 1: augmentation, only when sigma > 0)
+            const double* pr = pre + (size_t)t * 25;
+            const int c = lane;
+            for (int kd = 0; kd < (aug ? 2 : 1); ++kd) {
+                const double* p = cst + ((N - 1 - t) & 1) * 26 + kd * 13;
+                double v;
+                if (c < 3) v = p[c];
+                else if (c < 6) v = p[c] + cfg.dt * p[c - 3];
+                else {
+                    const double* col = jz + (c - 6) * 13;
+                    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 12; k += 2) { a0 += col[k] * p[k]; a1 += col[k + 1] * p[k + 1]; }
+                    v = a0 + a1 + col[12] * p[12];
+                }
+                double* cn = cst + ((N - t) & 1) * 26 + kd * 13;
+                if (c < 13) cn[c] = (kd == 0) ? v + pr[c] : v;
+                else if (kd == 0) g_out[t * FTMPC_NU + c - 13] = v + pr[c];
+                else ga_out[t * FTMPC_NU + c - 13] = v + pr[c + 6];
+            }
+            if (!aug && c >= 13) ga_out[t * FTMPC_NU + c - 13] = 0.0;
+        }
+        __syncwarp();
+        blk.mark(PH_WS_QR);
+        if (ab_on) {
+            const double* pc = PABs + c2 * 13;
+            double v;
+            if (c1 < 3) v = pc[c1];
+            else if (c1 < 6) v = cfg.dt * pc[c1 - 3] + pc[c1];
+            else {
+                const double* col = jz + (c1 - 6) * 13;
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 12; k += 2) { a0 += col[k] * pc[k]; a1 += col[k + 1] * pc[k + 1]; }
+                v = a0 + a1 + col[12] * pc[12];
+            }
+            v += h_diag;
+            if (h_o1 >= 0) {
+                double hsv = theta * 0.5 * (wz[h_o1] + wz[h_o2]);
+                if (Cq && h_cq >= 0) hsv += Cq[(size_t)t * FTMPC_CQ + h_cq];
+                if (aug && h_au >= 0) hsv += hau[t * 21 + h_au];
+                v += hsv;
+            }
+            F[hi * 19 + lo] = v;
+            F[lo * 19 + hi] = v;
+        }
+        blk.mark(PH_CHOL_PANEL);
+        blk.sync();
+        blk.mark(PH_WS_D0);
+        // ================= CD
+        const int par = t & 1;
+        if (cd_on) {
+            double Lm[6][6], fr[6], fc[6], yr[6], yc[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) Lm[i][j] = (j <= i) ? F[(13 + i) * 19 + 13 + j] : 0.0;
+                fr[i] = F[(13 + i) * 19 + d_r];
+                fc[i] = F[(13 + i) * 19 + d_c];
+            }
+            double pv = F[d_r * 19 + d_c];
+            double dmx = 0.0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) dmx = fmax(dmx, fabs(Lm[i][i]));
+            const double run = fmax(flg[1 + par], dmx);
+            const double piv_tol = 1e-10 * fmax(1.0, run);
+            int bad = 0;
+            double rsv[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                double d = Lm[j][j];
+#pragma unroll
+                for (int m = 0; m < 6; ++m) if (m < j) d -= Lm[j][m] * Lm[j][m];
+                if (!(d > piv_tol) && !bad) bad = j + 1;
+                const double rs = rsqrt(d);
+                rsv[j] = rs;
+                Lm[j][j] = d * rs;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    if (i > j) {
+                        double v = Lm[i][j];
+#pragma unroll
+                        for (int m = 0; m < 6; ++m) if (m < j) v -= Lm[i][m] * Lm[j][m];
+                        Lm[i][j] = v * rs;
+                    }
+                }
+                double vr = fr[j], vc = fc[j];
+#pragma unroll
+                for (int m = 0; m < 6; ++m) if (m < j) { vr -= Lm[j][m] * yr[m]; vc -= Lm[j][m] * yc[m]; }
+                yr[j] = vr * rs;
+                yc[j] = vc * rs;
+                pv -= yr[j] * yc[j];
+            }
+            P[d_r * 13 + d_c] = pv;
+            P[d_c * 13 + d_r] = pv;
+            if (d_c == 0) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) wz[i * 13 + d_r] = yr[i];
+                if (d_r == 0) {
+                    int o = 120;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i)
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) if (j <= i) wz[o++] = Lm[i][j];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) wz[141 + i] = rsv[i];
+                    if (bad) flg[0] = (double)(FTMPC_NU * t + bad);
+                    flg[1 + (par ^ 1)] = run;
+                }
+            }
+        }
+        blk.mark(PH_CHOL_SYRK);
+        blk.sync();
+        blk.mark(PH_WS_SOLVE);
+        if (flg[0] != 0.0) { *dscale_out = flg[1 + (par ^ 1)]; return (int)flg[0]; }
+    }
+    *dscale_out = flg[2];                                           // written at t = 0
+    // ---- (C, Kh) -> (C^-T columns, K = C^-T Kh): back substitution, one task per (stage, column)
+    for (int idx = tid; idx < N * 19; idx += blockDim.x) {
+        const int t = idx / 19, e = idx - t * 19;
+        double* wz = Wz + (size_t)t * 169;
+        double Lm[6][6], rs[6], x[6];
+        {
+            int o = 120;
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int j = 0; j < 6; ++j) Lm[i][j] = (j <= i) ? wz[o++] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            rs[i] = wz[141 + i];
+            x[i] = (e < 13) ? wz[i * 13 + e] : ((e - 13 == i) ? 1.0 : 0.0);
+        }
+#pragma unroll
+        for (int i = 5; i >= 0; --i) {
+            double v = x[i];
+#pragma unroll
+            for (int m = 0; m < 6; ++m) if (m > i) v -= Lm[m][i] * x[m];
+            x[i] = v * rs[i];
+        }
+        if (e < 13) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) wz[i * 13 + e] = x[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) wz[78 + (e - 13) * 6 + i] = x[i];        // row j of C^-1 = column j of C^-T
+        }
+    }
+    blk.sync();
+    blk.mark(PH_WS_E);
+    return 0;
+}
+template <class Blk> struct RicCuda { static constexpr bool value = false; };
+template <> struct RicCuda<CudaBlock> { static constexpr bool value = true; };
+#endif
+
 // Inputs: Jz [N][13][13] ([col][row]: columns 0-6 = d x+ / d (omega, q), 7-12 = d x+ / d u; the (p, v) columns of A_t are
 // [[I, dt I], [0, I], 0]), Wz [N][13][13] stage Hessians of the Lagrangian over (omega, q, u) -- OVERWRITTEN by the stage
 // records (K_t, C_t^-1) --, X, U, xref, gradV / hessV of the terminal cost, blend theta, augmentation sigma on the rows
@@ -96,49 +337,131 @@ FT_HD int riccati_factor(Blk& blk, const ftmpc_config& cfg, const Lay& L, const 
     double* cst = Cs + 36;            // costates: [2 buffers][2 kinds (g, aug)][13]
     double* Ht = cst + 52;            // [9][9] terminal Hessian model (+ augmentation), [9] augmentation of the terminal gradient
     double* tgv = Ht + 81;
-    double* flg = tgv + 9;            // [0] failing pivot + 1, [1] running max of diag(Lam)
+    double* flg = tgv + 9;            // [0] failing pivot + 1, [1] running max of diag(Lam), [2] its candidate of the current stage
+    // scratch of the set-up in the (still free) E region, behind the staged multipliers:
+    //   pre [N][25]  per-stage vectors of the costate / gradient recursion (see below)
+    //   hau [N][21]  lower triangle of sigma sum_A a_i a_i' (hull rows of stage t), only when sigma > 0
+    //   lists        active rows (lam_prev > 0) of every stage [N][27] and of the terminal set [73] (count first), ints
+    // (a horizon of 1 has no room there: it uses the tail of `work`)
+    const size_t es_need = (size_t)L.mc + (size_t)60 * N + 40;
+    double* es = (es_need <= (size_t)(nv + FTMPC_NE) * nv) ? lam_stage + L.mc : work + 1040;
+    double* pre = es;
+    double* hau = pre + (size_t)25 * N;
+    int* hlist = reinterpret_cast<int*>(hau + (size_t)21 * N);
+    int* tlist = hlist + (size_t)27 * N + (N & 1);
     const double* Ah = s.hull;
     const double* lam_prev = lam_prev_g;
-    if (sigma > 0.0) {
+    const bool aug = sigma > 0.0;
+    // ---- set-up, first interval: everything that comes from global memory is requested at once -- the multipliers (when the
+    //      augmentation is on), the per-stage vectors of the costate / gradient recursion
+    //        pre[t][0:13]  running-cost gradient joining the costate of stage t (t >= 1)
+    //        pre[t][13:19] 2 R (u~_t - rho_t)        pre[t][19:25] sigma sum_A c_i a_i  (hull rows of stage t; below)
+    //      (two tasks per thread and trip, loads first: one memory round trip instead of one per pass), and the
+    //      un-augmented terminal model  Ht = term_quad + theta (hessV - term_quad)
+    if (aug) {
         for (int i = tid; i < L.mc; i += nt) lam_stage[i] = lam_prev_g[i];
         lam_prev = lam_stage;
     }
-    if (tid == 0) { flg[0] = 0.0; flg[1] = 0.0; s.g[n] = 0.0; s.ga[n] = 0.0; }
+    if (tid == 0) { flg[0] = 0.0; flg[1] = 0.0; flg[2] = 0.0; s.g[n] = 0.0; s.ga[n] = 0.0; }
+    {
+        const int ntask = N * 19;
+        for (int i0 = tid; i0 < ntask; i0 += 2 * nt) {
+            double a[2], b[2], w[2];
+            int tt[2], cc[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int idx = i0 + h * nt;
+                const bool on = idx < ntask;
+                const int t = on ? idx / 19 : 0, c = on ? idx - t * 19 : 0;
+                tt[h] = on ? t : -1; cc[h] = c;
+                a[h] = 0.0; b[h] = 0.0; w[h] = 0.0;
+                if (!on) continue;
+                if (c < FTMPC_NE) {
+                    if (t > 0) { a[h] = X[t * FTMPC_NX + c]; b[h] = xref[t * FTMPC_NE + c]; w[h] = 2.0 * cfg.Q[c]; }
+                } else if (c < 13) {
+                    if (t > 0 && Cq) { a[h] = Cq[(size_t)t * FTMPC_CQ + c - FTMPC_NE]; w[h] = 1.0; }
+                } else {
+                    a[h] = U[t * FTMPC_NU + c - 13];
+                    if (Cq) b[h] = Cq[(size_t)t * FTMPC_CQ + 32 + c - 13];
+                    w[h] = 2.0 * cfg.R[c - 13];
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (tt[h] >= 0) pre[tt[h] * 25 + cc[h]] = w[h] * (a[h] - b[h]);
+        }
+        for (int idx = tid; idx < 81; idx += nt) {
+            const double q0 = cfg.term_quad[idx];
+            Ht[idx] = q0 + theta * (hessV[idx] - q0);
+        }
+        for (int idx = tid; idx < 9; idx += nt) tgv[idx] = 0.0;
+        if (!aug) for (int idx = tid; idx < N * FTMPC_NU; idx += nt) pre[(idx / FTMPC_NU) * 25 + 19 + idx % FTMPC_NU] = 0.0;
+    }
     blk.sync();
-    // ---- terminal model: Ht = term_quad + theta (hessV - term_quad) + sigma sum_A a a',  tgv = sigma sum_A c a
-    for (int idx = tid; idx < 90; idx += nt) {
-        double v = 0.0;
-        const int kk = idx / 9, l = idx - kk * 9;
-        if (sigma > 0.0) {
-            if (s.tf_val) {                        // <= 2 non-zeros per row of A_f
-                for (int i = 0; i < FTMPC_NF; ++i) {
-                    if (lam_prev[FTMPC_NH * N + i] > 0.0) {
+    if (aug) {
+        // active-row lists (one thread per stage, the last thread takes the terminal set)
+        for (int t = tid; t <= N; t += nt) {
+            if (t < N) {
+                int c = 0;
+                for (int k = 0; k < FTMPC_NH; ++k)
+                    if (lam_prev[t * FTMPC_NH + k] > 0.0) hlist[t * 27 + 1 + c++] = k;
+                hlist[t * 27] = c;
+            } else {
+                int c = 0;
+                for (int i = 0; i < FTMPC_NF; ++i)
+                    if (lam_prev[FTMPC_NH * N + i] > 0.0) tlist[1 + c++] = i;
+                tlist[0] = c;
+            }
+        }
+        blk.sync();
+        // augmentation: Ht += sigma sum_A a a',  tgv = sigma sum_A c a  (terminal rows);  per stage sigma sum_A c a and the
+        // lower triangle of sigma sum_A a a' (hull rows)
+        for (int idx = tid; idx < 90 + N * 27; idx += nt) {
+            double v = 0.0;
+            if (idx < 90) {
+                const int kk = idx / 9, l = idx - kk * 9;
+                const int na = tlist[0];
+                if (s.tf_val) {                        // <= 2 non-zeros per row of A_f
+                    for (int e = 0; e < na; ++e) {
+                        const int i = tlist[1 + e];
                         const int k0 = s.tf_idx[2 * i], k1 = s.tf_idx[2 * i + 1];
                         const double v0 = s.tf_val[2 * i], v1 = s.tf_val[2 * i + 1];
                         const double al = (l == k0) ? v0 : ((l == k1) ? v1 : 0.0);
                         const double ak = (kk == k0) ? v0 : ((kk == k1) ? v1 : 0.0);
                         v += (idx < 81) ? ak * al : s.cv[FTMPC_NH * N + i] * al;
                     }
-                }
-            } else {
-                const double* Af = s.cg ? s.cg->Af : cfg.Af;
-                for (int i = 0; i < FTMPC_NF; ++i) {
-                    if (lam_prev[FTMPC_NH * N + i] > 0.0) {
+                } else {
+                    const double* Af = s.cg ? s.cg->Af : cfg.Af;
+                    for (int e = 0; e < na; ++e) {
+                        const int i = tlist[1 + e];
                         const double al = Af[i * FTMPC_NE + l];
                         v += (idx < 81) ? Af[i * FTMPC_NE + kk] * al : s.cv[FTMPC_NH * N + i] * al;
                     }
                 }
+                if (idx < 81) Ht[idx] += sigma * v;
+                else tgv[l] = sigma * v;
+            } else {
+                const int e0 = idx - 90, t = e0 / 27, c = e0 - t * 27;
+                const int na = hlist[t * 27];
+                if (c < 6) {
+                    for (int e = 0; e < na; ++e) {
+                        const int k = hlist[t * 27 + 1 + e];
+                        v += s.cv[t * FTMPC_NH + k] * Ah[k * FTMPC_NU + c];
+                    }
+                    pre[t * 25 + 19 + c] = sigma * v;
+                } else {
+                    int i, j;
+                    ric_tri(c - 6, i, j);
+                    for (int e = 0; e < na; ++e) {
+                        const int k = hlist[t * 27 + 1 + e];
+                        v += Ah[k * FTMPC_NU + i] * Ah[k * FTMPC_NU + j];
+                    }
+                    hau[t * 21 + c - 6] = sigma * v;
+                }
             }
-            v *= sigma;
         }
-        if (idx < 81) {
-            const double q0 = cfg.term_quad[idx];
-            Ht[idx] = q0 + theta * (hessV[idx] - q0) + v;
-        } else {
-            tgv[l] = v;
-        }
+        blk.sync();
     }
-    blk.sync();
     for (int idx = tid; idx < 169 + 26; idx += nt) {
         if (idx < 169) {
             const int r = idx / 13, c = idx - r * 13;
@@ -148,30 +471,47 @@ FT_HD int riccati_factor(Blk& blk, const ftmpc_config& cfg, const Lay& L, const 
             cst[kd * 13 + r] = (r < FTMPC_NE) ? (kd == 0 ? gradV[r] : tgv[r]) : 0.0;
         }
     }
+    // task decode of this thread's first pass (the triangular index needs a square root: once, not per stage)
+    int b_c1, b_c2, d_r, d_c;
+    ric_tri(tid, b_c1, b_c2);
+    d_r = b_c1; d_c = b_c2;
+    double b_diag = 0.0;                   // constant diagonal of the stage Hessian: 2Q on (p, v, omega), 2R on u
+    if (tid < 190 && b_c1 == b_c2) b_diag = (b_c1 < FTMPC_NE) ? 2.0 * cfg.Q[b_c1 < FTMPC_NE ? b_c1 : 0] : ((b_c1 >= 13) ? 2.0 * cfg.R[b_c1 - 13] : 0.0);
     blk.sync();
+    blk.mark(PH_COND_PRE);
+    bool swept = false;
+#if defined(__CUDA_ARCH__)
+    if (RicCuda<Blk>::value && nt == 256) {
+        // PAB is kept by columns ([19][13]) and F full symmetric in this path; same buffers
+        const int bad = ric_backward_cuda(reinterpret_cast<CudaBlock&>(blk), cfg, N, Jz, Wz, theta, aug, Cq, P, PAB, F, cst, flg, pre, hau,
+                                          s.g, s.ga, dscale_out);
+        if (bad) return bad;
+        swept = true;
+    }
+#endif
     // ---- backward sweep
-    for (int t = N - 1; t >= 0; --t) {
+    for (int t = swept ? -1 : N - 1; t >= 0; --t) {
         const double* jz = Jz + (size_t)t * 169;
         double* wz = Wz + (size_t)t * 169;
         const double* co = cst + ((N - 1 - t) & 1) * 26;            // costates of stage t + 1
         double* cn = cst + ((N - t) & 1) * 26;                      // costates of stage t
-        // (A) PAB = P [A B]  (13 x 19; the (p, v) columns of A are trivial), and the two costate / gradient products
-        for (int idx = tid; idx < 247 + 38; idx += nt) {
-            if (idx < 247) {
-                const int c = idx / 13, r = idx - c * 13;          // consecutive threads: consecutive rows of one column
-                double v;
-                if (c < 3) v = P[r * 13 + c];
-                else if (c < 6) v = cfg.dt * P[r * 13 + c - 3] + P[r * 13 + c];
-                else {
-                    const double* col = jz + (c - 6) * 13;
-                    double a0 = 0.0, a1 = 0.0;
+        const double* pr = pre + (size_t)t * 25;
+        // (A) PAB = P [A B]  (13 x 19; the (p, v) columns of A are trivial: they ride with the first 78 tasks), and the two
+        //     costate / gradient products [A B]' lambda
+        //     (task ids 169..191 are left empty so that no warp runs both kinds of task one after the other)
+        for (int idx = tid; idx < 192 + 38; idx += nt) {
+            if (idx >= 169 && idx < 192) continue;
+            if (idx < 169) {
+                const int cm = idx / 13, r = idx - cm * 13;        // consecutive threads: consecutive rows of one column
+                const double* col = jz + cm * 13;
+                const double* pr_ = P + r * 13;
+                double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 12; k += 2) { a0 += P[r * 13 + k] * col[k]; a1 += P[r * 13 + k + 1] * col[k + 1]; }
-                    v = a0 + a1 + P[r * 13 + 12] * col[12];
-                }
-                PAB[r * 19 + c] = v;
+                for (int k = 0; k < 12; k += 2) { a0 += pr_[k] * col[k]; a1 += pr_[k + 1] * col[k + 1]; }
+                PAB[r * 19 + 6 + cm] = a0 + a1 + pr_[12] * col[12];
+                if (cm < 6) PAB[r * 19 + cm] = (cm < 3) ? pr_[cm] : cfg.dt * pr_[cm - 3] + pr_[cm];
             } else {
-                const int kd = (idx - 247) / 19, c = (idx - 247) - kd * 19;
+                const int kd = (idx - 192) / 19, c = (idx - 192) - kd * 19;
                 const double* p = co + kd * 13;
                 double v;
                 if (c < 3) v = p[c];
@@ -184,68 +524,52 @@ FT_HD int riccati_factor(Blk& blk, const ftmpc_config& cfg, const Lay& L, const 
                     v = a0 + a1 + col[12] * p[12];
                 }
                 if (c < 13) {                                      // costate of stage t (the running-cost gradient joins for t > 0)
-                    if (kd == 0 && t > 0) {
-                        if (c < FTMPC_NE) v += 2.0 * cfg.Q[c] * (X[t * FTMPC_NX + c] - xref[t * FTMPC_NE + c]);
-                        else if (Cq) v += Cq[(size_t)t * FTMPC_CQ + c - FTMPC_NE];
-                    }
-                    cn[kd * 13 + c] = v;
+                    cn[kd * 13 + c] = (kd == 0) ? v + pr[c] : v;
                 } else {
-                    const int i = c - 13, a = t * FTMPC_NU + i;
-                    if (kd == 0) {
-                        s.g[a] = v + 2.0 * cfg.R[i] * (U[a] - (Cq ? Cq[(size_t)t * FTMPC_CQ + 32 + i] : 0.0));
-                    } else {
-                        double av = 0.0;
-                        if (sigma > 0.0)
-                            for (int k = 0; k < FTMPC_NH; ++k)
-                                if (lam_prev[t * FTMPC_NH + k] > 0.0) av += s.cv[t * FTMPC_NH + k] * Ah[k * FTMPC_NU + i];
-                        s.ga[a] = v + sigma * av;                  // ga - g; combined below
-                    }
+                    const int a = t * FTMPC_NU + c - 13;
+                    if (kd == 0) s.g[a] = v + pr[c];
+                    else s.ga[a] = v + pr[c + 6];                  // ga - g; combined below
                 }
             }
         }
         blk.sync();
+        blk.mark(PH_WS_D0);
         // (B) F = [A B]' PAB + stage Hessian, lower triangle (c1 >= c2)
         for (int idx = tid; idx < 190; idx += nt) {
-            int c1 = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
-            while ((c1 + 1) * (c1 + 2) / 2 <= idx) ++c1;
-            while (c1 * (c1 + 1) / 2 > idx) --c1;
-            const int c2 = idx - c1 * (c1 + 1) / 2;
+            int c1 = b_c1, c2 = b_c2;
+            double dg = b_diag;
+            if (idx != tid) {
+                ric_tri(idx, c1, c2);
+                dg = (c1 != c2) ? 0.0 : ((c1 < FTMPC_NE) ? 2.0 * cfg.Q[c1 < FTMPC_NE ? c1 : 0] : ((c1 >= 13) ? 2.0 * cfg.R[c1 - 13] : 0.0));
+            }
             double v;
             if (c1 < 3) v = PAB[c1 * 19 + c2];
             else if (c1 < 6) v = cfg.dt * PAB[(c1 - 3) * 19 + c2] + PAB[c1 * 19 + c2];
             else {
                 const double* col = jz + (c1 - 6) * 13;
+                const double* pc = PAB + c2;
                 double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-                for (int k = 0; k < 12; k += 2) { a0 += col[k] * PAB[k * 19 + c2]; a1 += col[k + 1] * PAB[(k + 1) * 19 + c2]; }
-                v = a0 + a1 + col[12] * PAB[12 * 19 + c2];
+                for (int k = 0; k < 12; k += 2) { a0 += col[k] * pc[k * 19]; a1 += col[k + 1] * pc[(k + 1) * 19]; }
+                v = a0 + a1 + col[12] * pc[12 * 19];
             }
             // stage Hessian: blkdiag(2 Q[0:6], theta sym(W) + 2Q on omega + 2R on u + Cq Gauss-Newton + sigma hull rows)
-            if (c1 < 6) {
-                if (c1 == c2) v += 2.0 * cfg.Q[c1];
-            } else if (c2 >= 6) {
+            v += dg;
+            if (c2 >= 6) {
                 const int k1 = c1 - 6, k2 = c2 - 6;
                 double hsv = theta * 0.5 * (wz[k1 * 13 + k2] + wz[k2 * 13 + k1]);
-                if (k1 == k2) {
-                    if (k1 < 3) hsv += 2.0 * cfg.Q[6 + k1];
-                    else if (k1 >= 7) hsv += 2.0 * cfg.R[k1 - 7];
-                }
                 if (Cq) {
                     const double* cq = Cq + (size_t)t * FTMPC_CQ;
                     if (k1 >= 3 && k1 < 7 && k2 >= 3) hsv += cq[16 + (k1 - 3) * 4 + (k2 - 3)];                 // (q, q)
                     else if (k1 >= 7 && k1 < 10 && k2 >= 3 && k2 < 7) hsv += cq[4 + (k1 - 7) * 4 + (k2 - 3)];  // (u~_F, q)
                 }
-                if (sigma > 0.0 && k2 >= 7) {
-                    double av = 0.0;
-                    for (int k = 0; k < FTMPC_NH; ++k)
-                        if (lam_prev[t * FTMPC_NH + k] > 0.0) av += Ah[k * FTMPC_NU + k1 - 7] * Ah[k * FTMPC_NU + k2 - 7];
-                    hsv += sigma * av;
-                }
+                if (aug && k2 >= 7) hsv += hau[t * 21 + (k1 - 7) * (k1 - 6) / 2 + k2 - 7];
                 v += hsv;
             }
             F[c1 * 19 + c2] = v;
         }
         blk.sync();
+        blk.mark(PH_WS_QR);
         // (C) Lam = F_uu = C C', C^-1; Kh = C^-1 F_ux: the 13 threads of the columns of F_ux factor Lam redundantly
         //     (a 6x6 Cholesky is a serial chain either way) and go on to their forward substitution without a barrier
         for (int c = tid; c < FTMPC_NX; c += nt) {
@@ -254,28 +578,20 @@ FT_HD int riccati_factor(Blk& blk, const ftmpc_config& cfg, const Lay& L, const 
             for (int i = 0; i < 6; ++i)
 #pragma unroll
                 for (int j = 0; j < 6; ++j) A6[i][j] = (j <= i) ? F[(13 + i) * 19 + 13 + j] : 0.0;
+            double fx[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) fx[i] = F[(13 + i) * 19 + c];
             double dmx = 0.0;
 #pragma unroll
             for (int i = 0; i < 6; ++i) dmx = fmax(dmx, fabs(A6[i][i]));
             const double run = fmax(flg[1], dmx);
             const int bad = ric_chol6(A6, Ci, 1e-10 * fmax(1.0, run));
-            double kh[6];
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
                 double v = 0.0;
 #pragma unroll
-                for (int m = 0; m < 6; ++m) if (m <= i) v += Ci[i][m] * F[(13 + m) * 19 + c];
-                kh[i] = v;
-            }
-#pragma unroll
-            for (int i = 0; i < 6; ++i) Kh[i * 13 + c] = kh[i];
-            // K[:, c] = C^-T kh  -> stage record (the Wz slot of this stage is dead: F has absorbed it)
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                double v = 0.0;
-#pragma unroll
-                for (int m = 0; m < 6; ++m) if (m >= i) v += Ci[m][i] * kh[m];
-                wz[i * 13 + c] = v;
+                for (int m = 0; m < 6; ++m) if (m <= i) v += Ci[i][m] * fx[m];
+                Kh[i * 13 + c] = v;
             }
             if (c == 0) {
 #pragma unroll
@@ -287,26 +603,40 @@ FT_HD int riccati_factor(Blk& blk, const ftmpc_config& cfg, const Lay& L, const 
             }
         }
         blk.sync();
+        blk.mark(PH_WS_SOLVE);
         if (flg[0] != 0.0) { *dscale_out = flg[2]; return (int)flg[0]; }
-        // (D) P_t = F_xx - Kh' Kh   (symmetric; both halves written)
-        for (int idx = tid; idx < 91 + 1; idx += nt) {
-            if (idx == 91) { flg[1] = flg[2]; continue; }
-            int r = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
-            while ((r + 1) * (r + 2) / 2 <= idx) ++r;
-            while (r * (r + 1) / 2 > idx) --r;
-            const int c = idx - r * (r + 1) / 2;
-            double v = F[r * 19 + c];
+        // (D) P_t = F_xx - Kh' Kh  (symmetric; both halves written);  K_t = C^-T Kh -> stage record (off the critical path)
+        for (int idx = tid; idx < 96 + 78 + 1; idx += nt) {
+            if (idx >= 91 && idx < 96) continue;                   // (warp-aligned task kinds, as in (A))
+            if (idx < 91) {
+                int r = d_r, c = d_c;
+                if (idx != tid) ric_tri(idx, r, c);
+                double v = F[r * 19 + c];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) v -= Kh[i * 13 + r] * Kh[i * 13 + c];
-            P[r * 13 + c] = v;
-            P[c * 13 + r] = v;
+                for (int i = 0; i < 6; ++i) v -= Kh[i * 13 + r] * Kh[i * 13 + c];
+                P[r * 13 + c] = v;
+                P[c * 13 + r] = v;
+            } else if (idx < 96 + 78) {
+                const int e = idx - 96, i = e / 13, c = e - i * 13;
+                const double* ci = wz + 78;
+                double v = 0.0;
+#pragma unroll
+                for (int m = 0; m < 6; ++m) if (m >= i) v += ci[m * 6 + i] * Kh[m * 13 + c];
+                wz[i * 13 + c] = v;
+            } else {
+                flg[1] = flg[2];
+            }
         }
         blk.sync();
+        blk.mark(PH_WS_E);
     }
-    *dscale_out = flg[1];
+    if (!swept) *dscale_out = flg[1];
     for (int a = tid; a < n; a += nt) s.ga[a] += s.g[a];
     blk.sync();
+    blk.mark(PH_COND_BLK);
     // ---- forward: one closed-loop rollout per column of J
+    // (a lane pair per column with shuffled halves was measured slower: the rollouts are bound by the shared-memory
+    //  instruction rate -- one broadcast load per multiply-add -- and the shuffles add to it; profiles/README.md r02u)
     for (int a = tid; a < n; a += nt) {
         const int st = a / FTMPC_NU, j = a - st * FTMPC_NU;
         double u[FTMPC_NU], dx[FTMPC_NX], dn[FTMPC_NX];
@@ -361,6 +691,7 @@ FT_HD int riccati_factor(Blk& blk, const ftmpc_config& cfg, const Lay& L, const 
         s.gi.d[a] = dacc;
     }
     blk.sync();
+    blk.mark(PH_COND_COL);
     return 0;
 }
 

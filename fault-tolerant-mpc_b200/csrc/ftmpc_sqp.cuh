@@ -904,7 +904,7 @@ struct MpcCons {
 // per-CTA scratch carved out of one buffer of doubles (shared memory on the device)
 // horizons above this use the O(N^2) condensing (condense_long) in the generic path
 #define FTMPC_LONG_N 20
-#define FTMPC_RIC_WORK 1100      /* doubles of scratch riccati_factor needs (ftmpc_riccati.cuh) */
+#define FTMPC_RIC_WORK 1160      /* doubles of scratch riccati_factor needs (ftmpc_riccati.cuh) */
 struct QpScratch {
     double* GL;                  // condense_long: sensitivity columns G_t[:, a], t = j+1 .. N, per column a = 6 j + ja
     const ftmpc_config* cg;      // configuration copy addressable per thread (global memory on the device)
@@ -2093,7 +2093,8 @@ FT_HD int factor_riccati(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, c
 // ---- phase_qp ------------------------------------------------------------------------------------------
 template <class Blk>
 FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst, int slot, double* scratch,
-                   bool staged = false /* Jz, Wz already sit in the scratch (CUDA linearisation) */) {
+                   bool staged = false /* Jz, Wz already sit in the scratch (CUDA linearisation) */,
+                   double* fast_work = nullptr /* FTMPC_RIC_WORK doubles of on-chip memory when the scratch itself is not */) {
     double* w = ws_slot(io, L, slot);
     double* sc = w + L.oSc;
     if (sc[SC_STATUS] != FTMPC_ST_RUNNING) return;
@@ -2101,6 +2102,7 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     QpScratch s = qp_carve(scratch, N, io.cfg_g);
     s.tf_val = io.tf_val;
     s.tf_idx = io.tf_idx;
+    if (fast_work) s.G = fast_work;              // workspace of riccati_factor (the G region is only read by the dense path)
     const double* xref = io.xref + (size_t)inst * io.xref_stride;
     const double* hull_g = io.hull_table + (size_t)io.hull_idx[inst] * FTMPC_HULL_STRIDE;
     // stage data -> scratch (the R^-1 region is free until the active-set solve starts)

@@ -4,7 +4,7 @@
 set -u
 TAG=${1:-dev}
 KEXPR=${2:-}
-shift 2 || true
+[ $# -ge 2 ] && shift 2 || shift $#
 OUT=gpurun_out
 mkdir -p $OUT
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -3 $OUT/smoke_$TAG.log
@@ -19,7 +19,7 @@ import json
 try:
     d=json.loads(open("$1").read().strip().splitlines()[-1])
     r=d["roofline"]
-    print("$1 value",round(d["value"]),"e2e",round(d["e2e"]["value"]),"conv",d["converged_frac"],"sqp",round(d["sqp_iters_mean"],2),"qp",round(d["qp_iters_mean"],1),"k_ms",r["kernel_ms"],"busy",r["sm_busy_frac"],"frac",round(r["frac"],4), "lat", d.get("latency",{}).get("p50_ms"))
+    print("$1 value",round(d["value"]),"e2e",round(d["e2e"]["value"]),"conv",d["converged_frac"],"sqp",round(d["sqp_iters_mean"],2),"qp",round(d["qp_iters_mean"],1),"k_ms",r["kernel_ms"],"busy",r["sm_busy_frac"],"frac",round(r["frac"],4), "lat", (d.get("latency") or {}).get("p50_ms"))
     print({k:v for k,v in r["phase_share"].items() if v>0.004})
     print(r["phase_counters"])
 except Exception as e:

@@ -116,13 +116,13 @@ def full(tag, instances):
         lines.append(f"  {100 * b / total:5.2f} %  after " + ", ".join(f"{f}:{n}" for f, n in ctx))
     lines.append(f"  total stall_barrier: {100 * sum(o[2] for o in offs) / total:.1f} %")
     lines += ["", "source lines by samples (innermost inlined frame), top stall reasons:"]
-    for k, s in per_line.most_common(30):
+    for k, s in per_line.most_common(70):
         top = ", ".join(f"{n.replace('stall_', '')} {100 * v / max(s, 1):.0f}%" for n, v in per_stall[k].most_common(4))
         lines.append(f"  {100 * s / total:5.2f} %  {k[0] if k else '?'}:{k[1] if k else 0}   [{top}]")
     (PROF / f"{tag}_k_solve_stalls_by_source.txt").write_text("\n".join(lines) + "\n")
 
 
-KNAME = "_Z8k_solve2"          # mangled prefix of the captured kernel (k_solve<false>: "_Z7k_solveILb0EE")
+KNAME = "_Z7k_solveILb0EE"    # mangled prefix of the captured kernel (k_solve2: "_Z8k_solve2")
 
 if __name__ == "__main__":
     tag = sys.argv[1]
