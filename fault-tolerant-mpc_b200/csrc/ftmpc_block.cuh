@@ -105,6 +105,13 @@ __device__ __forceinline__ unsigned tma_row_bytes(const double* src, int n) {
     return (unsigned)((n - mis) & ~1) * 8u;
 }
 
+// one warp as a block (serial sweeps that need nothing wider: ric_apply)
+struct WarpBlock {
+    __device__ __forceinline__ int tid() const { return threadIdx.x & 31; }
+    __device__ __forceinline__ int nthreads() const { return 32; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
+
 // scratch: >= 2 * 32 * 2 doubles of shared memory (double-buffered so one barrier per reduction suffices)
 struct CudaBlock {
     double* scratch;

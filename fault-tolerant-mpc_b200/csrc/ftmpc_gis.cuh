@@ -283,4 +283,170 @@ FT_HD int gis_solve(Blk& blk, const Cons& cons, const GisWork& w, int ne, int m,
     return status;
 }
 
+// ---- the same iteration with K as an OPERATOR (long horizons: ric_apply, ftmpc_riccati.cuh) ---------------------------------
+// KOp::apply(blk, v, out, t_top, has_e) computes out = K v for a dense v in extended coordinates (called by every thread of
+// the block; t_top = highest stage with a non-zero input entry, -1 for none; has_e = the terminal part of v is non-zero).
+// Work vectors: ye, ze, c as above plus vin (ne).  c = N_W r is GATHERED per coordinate (fixed summation order: results do
+// not depend on the thread count or on timing), which needs the structure of the MPC rows (MpcCons).
+template <class Blk, class Cons>
+FT_HD void gis_gather(Blk& blk, const Cons& cons, const GisWork& w, int ne, int q) {
+    const int tid = blk.tid(), nt = blk.nthreads();
+    const int n = cons.n, nv = cons.nv, nh = FTMPC_NH * cons.N;
+    for (int i = tid; i < ne; i += nt) {
+        double a = 0.0;
+        if (i < n) {
+            const int t = i / FTMPC_NU, j = i - t * FTMPC_NU;
+            for (int k = 0; k < q; ++k) {
+                const int p = w.act[k];
+                if (p < nh && p / FTMPC_NH == t) a -= w.r[k] * cons.Ah[(p - t * FTMPC_NH) * FTMPC_NU + j];
+            }
+        } else if (i == n) {
+            for (int k = 0; k < q; ++k) {
+                const int p = w.act[k];
+                if (p < cons.mc) { const double c = cons.cv[p]; if (c > 0.0) a += w.r[k] * c; }
+                else a += (p == cons.mc) ? w.r[k] : -w.r[k];
+            }
+        } else {
+            const int e = i - nv;
+            for (int k = 0; k < q; ++k) {
+                const int p = w.act[k];
+                if (p >= nh && p < cons.mc) a -= w.r[k] * cons.Af[(p - nh) * FTMPC_NE + e];
+            }
+        }
+        w.c[i] = a;
+    }
+    blk.sync();
+}
+
+template <class Blk, class Cons, class KOp>
+FT_HD int gis_solve_op(Blk& blk, const Cons& cons, const GisWork& w, KOp& kop, double* vin, int ne, int m, double* lam, int maxit,
+                       double tol, int* iters_out, int* nact_out) {
+    const int tid = blk.tid(), nt = blk.nthreads();
+    const double dep_tol = 1e-14, refine_tol = 1e-13;
+    const int nh = FTMPC_NH * cons.N;
+    int q = 0, iters = 0, status = GI_OK;
+    for (int i = tid; i < m; i += nt) {
+        w.s[i] = cons.slack(i, w.xe, 1.0);
+        w.pos[i] = -1;
+    }
+    blk.sync();
+    for (;;) {
+        double best = 0.0;
+        int bi = 0x7fffffff;
+        for (int i = tid; i < m; i += nt) {
+            if (w.pos[i] < 0) {
+                const double v = w.s[i];
+                if (v < best || (v == best && i < bi)) { best = v; bi = i; }
+            }
+        }
+        blk.argmin(best, bi);
+        blk.mark(PH_GI_SELECT);
+        if (bi == 0x7fffffff || best >= -tol) break;
+        const int p = bi;
+        double sp = best;
+        SparseRow np;
+        cons.row(p, np);
+        if (tid == 0) w.u[q] = 0.0;
+        // ye = K n_p
+        for (int i = tid; i < ne; i += nt) vin[i] = 0.0;
+        blk.sync();
+        if (tid == 0) for (int k = 0; k < np.nnz; ++k) vin[np.idx[k]] = np.val[k];
+        blk.sync();
+        kop.apply(blk, vin, w.ye, (p < nh) ? p / FTMPC_NH : ((p < cons.mc) ? cons.N - 1 : -1), p >= nh && p < cons.mc);
+        blk.mark(PH_GI_D);
+        double dn = 0.0;
+        for (int k = 0; k < np.nnz; ++k) dn += np.val[k] * w.ye[np.idx[k]];
+        bool added = false;
+        while (!added) {
+            ++iters;
+            if (iters > maxit) { status = GI_MAXIT; break; }
+            for (int k = tid; k < q; k += nt) w.w[k] = cons.slack(w.act[k], w.ye, 0.0);
+            blk.sync();
+            if (q > 0) {
+                gis_schur_solve(blk, w, q);
+                gis_gather(blk, cons, w, ne, q);
+                blk.mark(PH_GI_UPD);
+                kop.apply(blk, w.c, vin, cons.N - 1, true);
+                for (int i = tid; i < ne; i += nt) w.ze[i] = w.ye[i] - vin[i];
+                blk.sync();
+                blk.mark(PH_GI_Z);
+                double emax = 0.0;
+                for (int k = tid; k < q; k += nt) {
+                    const double e = cons.slack(w.act[k], w.ze, 0.0);
+                    w.w[k] = e;
+                    w.tmp[k] = w.r[k];
+                    emax = fmax(emax, fabs(e));
+                }
+                emax = blk.max(emax);
+                if (emax > refine_tol * fabs(dn)) {
+                    gis_schur_solve(blk, w, q);
+                    gis_gather(blk, cons, w, ne, q);
+                    kop.apply(blk, w.c, vin, cons.N - 1, true);
+                    for (int i = tid; i < ne; i += nt) w.ze[i] -= vin[i];
+                    for (int k = tid; k < q; k += nt) w.r[k] += w.tmp[k];
+                    blk.sync();
+                    blk.count(CT_GI_REFINE);
+                }
+            } else {
+                for (int i = tid; i < ne; i += nt) w.ze[i] = w.ye[i];
+                blk.sync();
+            }
+            double d2n = 0.0;
+            for (int k = 0; k < np.nnz; ++k) d2n += np.val[k] * w.ze[np.idx[k]];
+            double t1 = INFINITY;
+            int l = 0x7fffffff;
+            for (int j = tid; j < q; j += nt) {
+                if (w.r[j] > 1e-13) {
+                    const double tj = w.u[j] / w.r[j];
+                    if (tj < t1 || (tj == t1 && j < l)) { t1 = tj; l = j; }
+                }
+            }
+            blk.argmin(t1, l);
+            const bool dep = (q >= w.qcap) || !(d2n > dep_tol * fmax(1.0, dn)) || (d2n <= 1e-28);
+            const double t2 = dep ? INFINITY : (-sp / d2n);
+            const double t = fmin(t1, t2);
+            if (t == INFINITY) { status = (q >= w.qcap) ? GI_MAXIT : GI_INFEASIBLE; break; }
+            if (t2 == INFINITY) {
+                for (int j = tid; j <= q; j += nt) w.u[j] += t * ((j < q) ? -w.r[j] : 1.0);
+                blk.sync();
+                gis_drop(blk, w, q, l);
+                blk.count(CT_GI_DROP);
+                continue;
+            }
+            for (int i = tid; i < ne; i += nt) w.xe[i] += t * w.ze[i];
+            for (int j = tid; j <= q; j += nt) w.u[j] += t * ((j < q) ? -w.r[j] : 1.0);
+            for (int i = tid; i < m; i += nt) w.s[i] += t * cons.slack(i, w.ze, 0.0);
+            sp += t * d2n;
+            blk.sync();
+            blk.mark(PH_GI_STEP);
+            if (t == t2) {
+                const double rho = sqrt(d2n);
+                double* col = w.Ui + gi_tri(q);
+                for (int j = tid; j < q; j += nt) col[j] = -w.r[j] / rho;
+                if (tid == 0) {
+                    col[q] = 1.0 / rho;
+                    w.act[q] = p;
+                    w.pos[p] = q;
+                    w.s[p] = 0.0;
+                }
+                blk.sync();
+                q += 1;
+                added = true;
+            } else {
+                gis_drop(blk, w, q, l);
+                blk.count(CT_GI_DROP);
+            }
+        }
+        if (status != GI_OK) break;
+    }
+    for (int i = tid; i < m; i += nt) lam[i] = 0.0;
+    blk.sync();
+    for (int j = tid; j < q; j += nt) lam[w.act[j]] = w.u[j];
+    blk.sync();
+    blk.count(CT_GI_ITER, iters);
+    *iters_out = iters;
+    *nact_out = q;
+    return status;
+}
+
 }  // namespace ftmpc

@@ -24,11 +24,6 @@
 
 using namespace ftmpc;
 
-struct WarpBlock {
-    __device__ __forceinline__ int tid() const { return threadIdx.x & 31; }
-    __device__ __forceinline__ int nthreads() const { return 32; }
-    __device__ __forceinline__ void sync() const { __syncwarp(); }
-};
 
 struct ftmpc_ctx {
     ftmpc_config cfg;          // host copy
@@ -416,7 +411,7 @@ static size_t solve2_smem_bytes(int N) {
 }
 static bool use_solve2(const ftmpc_ctx* h) {
     const int N = h->cfg.horizon;
-    return h->cfg.qp_method != 0 && (N + 2) * (N + 3) / 2 <= FTMPC_QP_THREADS && 6 * N <= FTMPC_QP_THREADS &&
+    return (h->cfg.qp_method & 3) != 0 && (N + 2) * (N + 3) / 2 <= FTMPC_QP_THREADS && 6 * N <= FTMPC_QP_THREADS &&
            solve2_smem_bytes(N) <= h->smem_dyn2_max;
 }
 
@@ -478,8 +473,8 @@ int ftmpc_create(ftmpc_handle* out, const ftmpc_config* cfg, const double* hull_
     // dynamic shared memory opt-in, once per handle: the attribute is per function and per device, so it is raised to the
     // device maximum (every horizon whose scratch fits uses the same kernel instantiation)
     {
-        const void* fns[3] = {(const void*)k_solve<false>, (const void*)k_condense, (const void*)k_qp_generic};
-        for (int i = 0; i < 3; ++i) {               // the opt-in limit covers static + dynamic shared memory of a block
+        const void* fns[4] = {(const void*)k_solve<false>, (const void*)k_condense, (const void*)k_qp_generic, (const void*)k_solve<true>};
+        for (int i = 0; i < 4; ++i) {               // the opt-in limit covers static + dynamic shared memory of a block
             cudaFuncAttributes fa;
             CREATE_TRY(cudaFuncGetAttributes(&fa, fns[i]));
             const int dyn = (int)h->smem_optin - (int)fa.sharedSizeBytes;
@@ -617,7 +612,7 @@ static int launch_step(ftmpc_ctx* h, const StepIO& io, void* workspace, size_t n
         CU(cudaEventRecord(h->ev[0], stream));
     }
     if (use_global)
-        k_solve<true><<<grid, FTMPC_QP_THREADS, FTMPC_RIC_WORK * sizeof(double), stream>>>(h->cfg, L, io, queue, gscratch, sdoubles,
+        k_solve<true><<<grid, FTMPC_QP_THREADS, gs_fast_doubles(h->cfg.horizon) * sizeof(double), stream>>>(h->cfg, L, io, queue, gscratch, sdoubles,
                                                              h->profile ? h->d_prof : nullptr);
     else
         k_solve<false><<<grid, FTMPC_QP_THREADS, smem, stream>>>(h->cfg, L, io, queue, nullptr, 0,

@@ -327,7 +327,7 @@ template <class Blk, class QpS, class Lay>
 FT_HD int riccati_factor(Blk& blk, const ftmpc_config& cfg, const Lay& L, const QpS& s, const double* Jz, double* Wz,
                          const double* X, const double* U, const double* xref, const double* gradV, const double* hessV,
                          double theta, double sigma, const double* lam_prev_g, const double* Cq, double* work,
-                         double* lam_stage, double* dscale_out) {
+                         double* lam_stage, double* dscale_out, bool want_columns = true) {
     const int N = L.N, n = L.n, ld = L.nv, nv = L.nv, tid = blk.tid(), nt = blk.nthreads();
     double* P = work;                 // [13][13]  cost-to-go Hessian P_{t+1}
     double* PAB = P + 169;            // [13][19]  P_{t+1} [A_t B_t]
@@ -634,6 +634,7 @@ FT_HD int riccati_factor(Blk& blk, const ftmpc_config& cfg, const Lay& L, const 
     for (int a = tid; a < n; a += nt) s.ga[a] += s.g[a];
     blk.sync();
     blk.mark(PH_COND_BLK);
+    if (!want_columns) return 0;                   // operator form (ric_apply): the stage records are all the QP needs
     // ---- forward: one closed-loop rollout per column of J
     // (a lane pair per column with shuffled halves was measured slower: the rollouts are bound by the shared-memory
     //  instruction rate -- one broadcast load per multiply-add -- and the shuffles add to it; profiles/README.md r02u)
@@ -694,5 +695,286 @@ FT_HD int riccati_factor(Blk& blk, const ftmpc_config& cfg, const Lay& L, const 
     blk.mark(PH_COND_COL);
     return 0;
 }
+
+
+// ---- K = E E' as an OPERATOR (long horizons) -------------------------------------------------------------------------
+// E = [J ; X J] never has to exist: with the stage records of riccati_factor (K_t, C_t^-1) and the stage Jacobians,
+//   out = K v,   v = [v_x (n) ; v_delta ; v_e (9)]   in the extended coordinates of the active-set solver,
+// is one adjoint sweep and one closed-loop rollout:
+//   backward  mu_N = [v_e ; 0];   y_t = v_x,t + B_t' mu_{t+1},   z_t = C_t^-1 y_t,   mu_t = A_t' mu_{t+1} - K_t' y_t
+//   forward   dx_0 = 0;   u_t = C_t^-T z_t - K_t dx_t,   dx_{t+1} = A_t dx_t + B_t u_t;   out_x,t = u_t,  out_e = dx_N[0:9]
+// (E' v = blkdiag(C_t^-1) Phi^-T [v_x + X' v_e], E w = Phi^-1 blkdiag(C_t^-T) w), 540 multiply-adds per stage instead of
+// the 2 (6N + 10)(6N + 1) of the dense products -- and nothing of size N^2 in memory.  The elastic variable is decoupled:
+// out_delta = v_delta / rho_slack.  Written against a block of ANY width (one warp on the device: the sweeps are serial
+// over the stages and a warp barrier is all a stage needs).
+struct RicOp {
+    int N, n, nv;
+    const double* Jz;      // [N][169]
+    const double* Rec;     // [N][169]  K_t [6][13] at 0, C_t^-1 [6][6] (lower) at 78
+    double dt, inv_rho;
+    double* scr;           // 64 doubles of (fast) scratch
+};
+// one stage of the adjoint sweep: y = vx + B' mu, z = C^-1 y -> zout, mu_t = A' mu - K' y -> mn   (two barrier intervals)
+template <class WB>
+FT_HD void ric_back_step(WB& wb, const double* jz, const double* rec, double dt, const double* vx, const double* mu, double* mn,
+                         double* y, double* zout) {
+    const int tid = wb.tid(), nt = wb.nthreads();
+    for (int i = tid; i < FTMPC_NU; i += nt) {
+        const double* col = jz + (7 + i) * 13;
+        double a0 = 0.0, a1 = 0.0;
+        for (int r = 0; r < 12; r += 2) { a0 += col[r] * mu[r]; a1 += col[r + 1] * mu[r + 1]; }
+        y[i] = vx[i] + (a0 + a1 + col[12] * mu[12]);
+    }
+    wb.sync();
+    for (int idx = tid; idx < FTMPC_NU + FTMPC_NX; idx += nt) {
+        if (idx < FTMPC_NU) {
+            const double* ci = rec + 78 + idx * 6;
+            double a = 0.0;
+            for (int m = 0; m <= idx; ++m) a += ci[m] * y[m];
+            zout[idx] = a;
+        } else {
+            const int c = idx - FTMPC_NU;
+            double a;
+            if (c < 3) a = mu[c];
+            else if (c < 6) a = mu[c] + dt * mu[c - 3];
+            else {
+                const double* col = jz + (c - 6) * 13;
+                double a0 = 0.0, a1 = 0.0;
+                for (int r = 0; r < 12; r += 2) { a0 += col[r] * mu[r]; a1 += col[r + 1] * mu[r + 1]; }
+                a = a0 + a1 + col[12] * mu[12];
+            }
+            for (int i = 0; i < FTMPC_NU; ++i) a -= rec[i * 13 + c] * y[i];
+            mn[c] = a;
+        }
+    }
+    wb.sync();
+}
+// one stage of the closed-loop rollout: u = C^-T z - K dx -> zu (in place of z), dx+ = A dx + B u -> dn
+template <class WB>
+FT_HD void ric_fwd_step(WB& wb, const double* jz, const double* rec, double dt, double* zu, const double* dx, double* dn, double* ub) {
+    const int tid = wb.tid(), nt = wb.nthreads();
+    for (int i = tid; i < FTMPC_NU; i += nt) {
+        double a = 0.0;
+        for (int m = i; m < FTMPC_NU; ++m) a += rec[78 + m * 6 + i] * zu[m];
+        double a0 = 0.0, a1 = 0.0;
+        for (int k = 0; k < 12; k += 2) { a0 += rec[i * 13 + k] * dx[k]; a1 += rec[i * 13 + k + 1] * dx[k + 1]; }
+        ub[i] = a - (a0 + a1 + rec[i * 13 + 12] * dx[12]);
+    }
+    wb.sync();
+    for (int r = tid; r < FTMPC_NX; r += nt) {
+        double a = (r < 3) ? dx[r] + dt * dx[r + 3] : ((r < 6) ? dx[r] : 0.0);
+        for (int l = 0; l < 7; ++l) a += jz[l * 13 + r] * dx[6 + l];
+        for (int i = 0; i < FTMPC_NU; ++i) a += jz[(7 + i) * 13 + r] * ub[i];
+        dn[r] = a;
+        if (r < FTMPC_NU) zu[r] = ub[r];
+    }
+    wb.sync();
+}
+// t_top: highest stage with a non-zero v_x (N - 1 when v_e != 0 or unknown): the adjoint sweep starts there
+template <class WB>
+FT_HD void ric_apply(WB& wb, const RicOp& op, const double* v, double* out, int t_top, bool has_e) {
+    const int N = op.N, n = op.n, nv = op.nv, tid = wb.tid(), nt = wb.nthreads();
+    double* mu0 = op.scr;          // [2][13]
+    double* y = op.scr + 26;       // [6]
+    double* dxb = op.scr + 32;     // [2][13]
+    double* ub = op.scr + 58;      // [6]
+    if (has_e) t_top = N - 1;
+    for (int i = tid; i < 13; i += nt) mu0[((t_top + 1) & 1) * 13 + i] = (has_e && i < FTMPC_NE) ? v[nv + i] : 0.0;
+    for (int i = tid; i < n; i += nt) if (i >= FTMPC_NU * (t_top + 1)) out[i] = 0.0;       // z_t = 0 above the top stage
+    wb.sync();
+    for (int t = t_top; t >= 0; --t)
+        ric_back_step(wb, op.Jz + (size_t)t * 169, op.Rec + (size_t)t * 169, op.dt, v + FTMPC_NU * t, mu0 + ((t + 1) & 1) * 13,
+                      mu0 + (t & 1) * 13, y, out + FTMPC_NU * t);
+    for (int i = tid; i < 13; i += nt) dxb[i] = 0.0;
+    wb.sync();
+    for (int t = 0; t < N; ++t)
+        ric_fwd_step(wb, op.Jz + (size_t)t * 169, op.Rec + (size_t)t * 169, op.dt, out + FTMPC_NU * t, dxb + (t & 1) * 13,
+                     dxb + ((t + 1) & 1) * 13, ub);
+    const double* dx = dxb + (N & 1) * 13;
+    for (int i = tid; i <= FTMPC_NE; i += nt) {
+        if (i < FTMPC_NE) out[nv + i] = dx[i];
+        else out[n] = v[n] * op.inv_rho;
+    }
+    wb.sync();
+}
+
+// ---- the operator in G-form ----------------------------------------------------------------------------------------------
+// With the closed-loop matrix A~_t = A_t - B_t K_t both sweeps are products with ONE 19 x 19 matrix per stage,
+//   G_t = [[A~_t, B_t], [-K_t, I]]:    backward  [mu_t ; y_t]    = G_t' [mu_{t+1} ; v_x,t]
+//                                      forward   [dx_{t+1} ; u_t] = G_t  [dx_t ; w_t],   w_t = Lam_t^-1 y_t,
+// i.e. one barrier interval per stage and direction, 19 lanes running the same 19-long dot product (no divergent
+// branches; the two-interval form above serialises four of them per stage).  G_t and Lam_t^-1 are built once per
+// factorisation, all stages in parallel (ric_build_g), FTMPC_RIC_GSTG doubles per stage.
+#define FTMPC_RIC_GSTG 397          /* G [19][19] row-major, then Lam^-1 [6][6] */
+template <class Blk>
+FT_HD void ric_build_g(Blk& blk, int N, double dt, const double* Jz, const double* Rec, double* G) {
+    const int tid = blk.tid(), nt = blk.nthreads();
+    for (int idx = tid; idx < N * FTMPC_RIC_GSTG; idx += nt) {
+        const int t = idx / FTMPC_RIC_GSTG, e = idx - t * FTMPC_RIC_GSTG;
+        const double* jz = Jz + (size_t)t * 169;
+        const double* rec = Rec + (size_t)t * 169;
+        double v;
+        if (e < 361) {
+            const int r = e / 19, c = e - r * 19;
+            if (r < 13 && c < 13) {                         // A~ = A - B K
+                v = (c < 6) ? ((r == c) ? 1.0 : ((c >= 3 && r == c - 3) ? dt : 0.0)) : jz[(c - 6) * 13 + r];
+                for (int i = 0; i < FTMPC_NU; ++i) v -= jz[(7 + i) * 13 + r] * rec[i * 13 + c];
+            } else if (r < 13) v = jz[(7 + c - 13) * 13 + r];     // B
+            else if (c < 13) v = -rec[(r - 13) * 13 + c];         // -K
+            else v = (r == c) ? 1.0 : 0.0;
+        } else {
+            const int i = (e - 361) / 6, j = (e - 361) - i * 6;   // Lam^-1 = C^-T C^-1
+            v = 0.0;
+            for (int m = (i > j ? i : j); m < FTMPC_NU; ++m) v += rec[78 + m * 6 + i] * rec[78 + m * 6 + j];
+        }
+        G[idx] = v;
+    }
+    blk.sync();
+}
+// out[lane] = sum_k G(lane, k) in[k]  (forward, TR = false)  or  sum_k G(k, lane) in[k]  (backward, TR = true), 19 lanes
+template <bool TR, class WB>
+FT_HD void ric_g_step(WB& wb, const double* G, const double* in13, const double* in6, double* out13, double* out6) {
+    for (int l = wb.tid(); l < 19; l += wb.nthreads()) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 12; k += 3) {
+            a0 += (TR ? G[k * 19 + l] : G[l * 19 + k]) * in13[k];
+            a1 += (TR ? G[(k + 1) * 19 + l] : G[l * 19 + k + 1]) * in13[k + 1];
+            a2 += (TR ? G[(k + 2) * 19 + l] : G[l * 19 + k + 2]) * in13[k + 2];
+        }
+        a0 += (TR ? G[12 * 19 + l] : G[l * 19 + 12]) * in13[12];
+#pragma unroll
+        for (int k = 0; k < 6; k += 3) {
+            a0 += (TR ? G[(13 + k) * 19 + l] : G[l * 19 + 13 + k]) * in6[k];
+            a1 += (TR ? G[(14 + k) * 19 + l] : G[l * 19 + 14 + k]) * in6[k + 1];
+            a2 += (TR ? G[(15 + k) * 19 + l] : G[l * 19 + 15 + k]) * in6[k + 2];
+        }
+        const double v = (a0 + a1) + a2;
+        if (l < 13) out13[l] = v; else out6[l - 13] = v;
+    }
+    wb.sync();
+}
+// w = Lam^-1 y for the stages t0 .. t0 + cnt - 1 (in place in zu), Gs = the G records of those stages
+template <class WB>
+FT_HD void ric_g_scale(WB& wb, const double* Gs, double* zu, int cnt) {
+    for (int k = wb.tid(); k < cnt; k += wb.nthreads()) {          // a thread per stage: nothing shared inside
+        const double* li = Gs + (size_t)k * FTMPC_RIC_GSTG + 361;
+        double yk[FTMPC_NU], wk[FTMPC_NU];
+#pragma unroll
+        for (int m = 0; m < FTMPC_NU; ++m) yk[m] = zu[k * FTMPC_NU + m];
+#pragma unroll
+        for (int i = 0; i < FTMPC_NU; ++i) {
+            double a = 0.0;
+#pragma unroll
+            for (int m = 0; m < FTMPC_NU; ++m) a += li[i * 6 + m] * yk[m];
+            wk[i] = a;
+        }
+#pragma unroll
+        for (int i = 0; i < FTMPC_NU; ++i) zu[k * FTMPC_NU + i] = wk[i];
+    }
+    wb.sync();
+}
+template <class WB>
+FT_HD void ric_apply_g(WB& wb, const RicOp& op, const double* G, const double* v, double* out, int t_top, bool has_e) {
+    const int N = op.N, n = op.n, nv = op.nv, tid = wb.tid(), nt = wb.nthreads();
+    double* mu0 = op.scr;          // [2][13]
+    double* dxb = op.scr + 32;     // [2][13]
+    if (has_e) t_top = N - 1;
+    for (int i = tid; i < 13; i += nt) mu0[((t_top + 1) & 1) * 13 + i] = (has_e && i < FTMPC_NE) ? v[nv + i] : 0.0;
+    for (int i = tid; i < n; i += nt) if (i >= FTMPC_NU * (t_top + 1)) out[i] = 0.0;
+    wb.sync();
+    for (int t = t_top; t >= 0; --t)
+        ric_g_step<true>(wb, G + (size_t)t * FTMPC_RIC_GSTG, mu0 + ((t + 1) & 1) * 13, v + FTMPC_NU * t, mu0 + (t & 1) * 13,
+                         out + FTMPC_NU * t);
+    for (int t0 = 0; t0 <= t_top; t0 += 16)
+        ric_g_scale(wb, G + (size_t)t0 * FTMPC_RIC_GSTG, out + FTMPC_NU * t0, (t_top + 1 - t0 < 16) ? t_top + 1 - t0 : 16);
+    for (int i = tid; i < 13; i += nt) dxb[i] = 0.0;
+    wb.sync();
+    for (int t = 0; t < N; ++t)
+        ric_g_step<false>(wb, G + (size_t)t * FTMPC_RIC_GSTG, dxb + (t & 1) * 13, out + FTMPC_NU * t, dxb + ((t + 1) & 1) * 13,
+                          out + FTMPC_NU * t);
+    const double* dx = dxb + (N & 1) * 13;
+    for (int i = tid; i <= FTMPC_NE; i += nt) {
+        if (i < FTMPC_NE) out[nv + i] = dx[i];
+        else out[n] = v[n] * op.inv_rho;
+    }
+    wb.sync();
+}
+
+#if defined(__CUDACC__)
+// ---- G-form with the stage matrices STAGED through shared memory (scratch in global memory: long horizons) -----------------
+// Every interval of the sweeps would otherwise start with a round trip to L2 for the stage matrix (measured with the
+// two-interval form: 0.35 ms per active-set iteration at N = 100).  Warp 0 sweeps a chunk of RIC_CH stages out of one half
+// of a double buffer while the other seven warps fetch the next chunk into the other half; v and the result live in shared
+// memory for the duration of the product.  One block barrier per chunk.
+#define FTMPC_RIC_CH 16
+struct RicStage {
+    double* buf;       // [2][RIC_CH][RIC_GSTG]
+    double* sv;        // [nv + 9]
+    double* so;        // [nv + 9]
+};
+__device__ __forceinline__ void ric_stage_chunk(const double* G, double* dst, int t0, int cnt, int tid0, int nthr) {
+    const double* src = G + (size_t)t0 * FTMPC_RIC_GSTG;
+    for (int idx = tid0; idx < cnt * FTMPC_RIC_GSTG; idx += nthr) dst[idx] = src[idx];
+}
+__device__ __forceinline__ void ric_apply_staged(CudaBlock& blk, const RicOp& op, const double* G, const RicStage& sg, const double* v,
+                                                 double* out, int t_top, bool has_e) {
+    const int N = op.N, n = op.n, nv = op.nv, tid = threadIdx.x, nt = blockDim.x, ne = nv + FTMPC_NE;
+    double* mu0 = op.scr;
+    double* dxb = op.scr + 32;
+    WarpBlock wb;
+    if (has_e) t_top = N - 1;
+    for (int i = tid; i < ne; i += nt) { sg.sv[i] = v[i]; sg.so[i] = 0.0; }
+    if (tid < 13) mu0[((t_top + 1) & 1) * 13 + tid] = (has_e && tid < FTMPC_NE) ? v[nv + tid] : 0.0;
+    if (tid >= 32 && tid < 45) dxb[tid - 32] = 0.0;
+    const size_t half = (size_t)FTMPC_RIC_CH * FTMPC_RIC_GSTG;
+    // ---- backward, chunks from the top stage down (w = Lam^-1 y of a chunk right behind its sweep)
+    int hi = t_top, b = 0;
+    {
+        const int lo = (hi - FTMPC_RIC_CH + 1 > 0) ? hi - FTMPC_RIC_CH + 1 : 0;
+        ric_stage_chunk(G, sg.buf, lo, hi - lo + 1, tid, nt);
+    }
+    blk.sync();
+    while (hi >= 0) {
+        const int lo = (hi - FTMPC_RIC_CH + 1 > 0) ? hi - FTMPC_RIC_CH + 1 : 0;
+        const double* cur = sg.buf + (size_t)b * half;
+        if (tid < 32) {
+            for (int t = hi; t >= lo; --t)
+                ric_g_step<true>(wb, cur + (size_t)(t - lo) * FTMPC_RIC_GSTG, mu0 + ((t + 1) & 1) * 13, sg.sv + FTMPC_NU * t,
+                                 mu0 + (t & 1) * 13, sg.so + FTMPC_NU * t);
+            ric_g_scale(wb, cur, sg.so + FTMPC_NU * lo, hi - lo + 1);
+        } else if (lo > 0) {
+            const int nhi = lo - 1, nlo = (nhi - FTMPC_RIC_CH + 1 > 0) ? nhi - FTMPC_RIC_CH + 1 : 0;
+            ric_stage_chunk(G, sg.buf + (size_t)(b ^ 1) * half, nlo, nhi - nlo + 1, tid - 32, nt - 32);
+        }
+        blk.sync();
+        hi = lo - 1;
+        b ^= 1;
+    }
+    // ---- forward, chunks from stage 0 up
+    int lo = 0;
+    b = 0;
+    ric_stage_chunk(G, sg.buf, 0, (N < FTMPC_RIC_CH) ? N : FTMPC_RIC_CH, tid, nt);
+    blk.sync();
+    while (lo < N) {
+        const int cnt = (N - lo < FTMPC_RIC_CH) ? N - lo : FTMPC_RIC_CH;
+        const double* cur = sg.buf + (size_t)b * half;
+        if (tid < 32) {
+            for (int t = lo; t < lo + cnt; ++t)
+                ric_g_step<false>(wb, cur + (size_t)(t - lo) * FTMPC_RIC_GSTG, dxb + (t & 1) * 13, sg.so + FTMPC_NU * t,
+                                  dxb + ((t + 1) & 1) * 13, sg.so + FTMPC_NU * t);
+        } else if (lo + cnt < N) {
+            const int nlo = lo + cnt, ncnt = (N - nlo < FTMPC_RIC_CH) ? N - nlo : FTMPC_RIC_CH;
+            ric_stage_chunk(G, sg.buf + (size_t)(b ^ 1) * half, nlo, ncnt, tid - 32, nt - 32);
+        }
+        blk.sync();
+        lo += cnt;
+        b ^= 1;
+    }
+    const double* dx = dxb + (N & 1) * 13;
+    for (int i = tid; i < ne; i += nt) out[i] = (i < n) ? sg.so[i] : ((i == n) ? v[n] * op.inv_rho : dx[i - nv]);
+    blk.sync();
+}
+#endif
 
 }  // namespace ftmpc

@@ -2077,18 +2077,81 @@ template <class Blk>
 FT_HD int factor_riccati(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const QpScratch& s, double* Jz, double* Wz,
                          const double* Jz_src, const double* Wz_src, const double* X, const double* U, const double* xref,
                          const double* gradV, const double* hessV, double theta, double sigma, const double* lam_prev,
-                         double* dscale_out, bool copy_j, bool copy_w, const double* Cq) {
+                         double* dscale_out, bool copy_j, bool copy_w, const double* Cq, bool want_columns = true) {
     const int N = L.N, tid = blk.tid(), nt = blk.nthreads();
     // the linearisation may have left Jz / Wz in place; the stage records overwrite Wz, so another attempt re-reads it
     if (copy_j) for (int i = tid; i < N * 169; i += nt) Jz[i] = Jz_src[i];
     if (copy_w) for (int i = tid; i < N * 169; i += nt) Wz[i] = Wz_src[i];
     blk.sync();
     const int bad = riccati_factor(blk, cfg, L, s, Jz, Wz, X, U, xref, gradV, hessV, theta, sigma, lam_prev, Cq, s.G, s.E,
-                                   dscale_out);
+                                   dscale_out, want_columns);
     blk.mark(PH_CHOL);
     blk.count(CT_CONDENSE);
     return bad;
 }
+
+// ---- K as an operator for gis_solve_op: the whole block calls, one warp (device) or the caller (host) sweeps -------------
+template <class Blk>
+struct RicKOp {
+    RicOp op;
+    const double* G;        // stage matrices of the G-form (ric_build_g) or nullptr: two-interval form on (Jz, records)
+    FT_HD void apply(Blk& blk, const double* v, double* out, int t_top, bool has_e) {
+        if (t_top < 0 && !has_e) {                  // only the elastic variable: K is diagonal there
+            for (int i = blk.tid(); i < op.nv + FTMPC_NE; i += blk.nthreads()) out[i] = (i == op.n) ? v[op.n] * op.inv_rho : 0.0;
+            blk.sync();
+            return;
+        }
+        if (G) ric_apply_g(blk, op, G, v, out, t_top, has_e);
+        else ric_apply(blk, op, v, out, t_top, has_e);
+    }
+};
+#if defined(__CUDACC__)
+// on-chip memory the global-scratch kernel hands to phase_qp (fast_work): Riccati workspace / operator scratch, the double
+// buffer of staged stages, v and K v
+FT_HD size_t gs_fast_doubles(int N) {
+    return (size_t)FTMPC_RIC_WORK + 2 * (size_t)FTMPC_RIC_CH * FTMPC_RIC_GSTG + 2 * (size_t)(FTMPC_NU * N + 1 + FTMPC_NE);
+}
+template <>
+struct RicKOp<CudaBlock> {
+    RicOp op;
+    const double* G;
+    RicStage sg;
+    bool staged;
+    __device__ __forceinline__ void apply(CudaBlock& blk, const double* v, double* out, int t_top, bool has_e) {
+        if (t_top < 0 && !has_e) {
+            for (int i = blk.tid(); i < op.nv + FTMPC_NE; i += blk.nthreads()) out[i] = (i == op.n) ? v[op.n] * op.inv_rho : 0.0;
+            blk.sync();
+            return;
+        }
+        if (staged && G) {
+            ric_apply_staged(blk, op, G, sg, v, out, t_top, has_e);
+            return;
+        }
+        if (threadIdx.x < 32) {
+            WarpBlock wb;
+            if (G) ric_apply_g(wb, op, G, v, out, t_top, has_e);
+            else ric_apply(wb, op, v, out, t_top, has_e);
+        }
+        blk.sync();
+    }
+};
+#endif
+template <class Blk>
+FT_HD void qp_op_stage(RicKOp<Blk>&, double*, int) {}
+#if defined(__CUDACC__)
+__device__ __forceinline__ void qp_op_stage(RicKOp<CudaBlock>& kop, double* fast_work, int ne) {
+    kop.staged = fast_work != nullptr;
+    kop.sg.buf = fast_work ? fast_work + FTMPC_RIC_WORK : nullptr;
+    kop.sg.sv = fast_work ? kop.sg.buf + 2 * (size_t)FTMPC_RIC_CH * FTMPC_RIC_GSTG : nullptr;
+    kop.sg.so = fast_work ? kop.sg.sv + ne : nullptr;
+}
+#endif
+// horizons above FTMPC_LONG_N run the QP in operator form (qp_method bit 5 forces it at any horizon, bit 6 forbids it)
+FT_HD bool qp_operator_form(const ftmpc_config& cfg, int N) {
+    if (cfg.qp_method & 64) return false;
+    return N > FTMPC_LONG_N || (cfg.qp_method & 32) != 0;
+}
+#define FTMPC_OP_QCAP 320        /* capacity of the working set in operator form */
 
 // ---- phase_qp ------------------------------------------------------------------------------------------
 template <class Blk>
@@ -2135,6 +2198,7 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     bool aug_allowed = can_aug;
     int fails = 0, qit = 0, nact = 0, st = GI_OK, aug_retry = 0;
     bool have_j = staged, have_w = staged;
+    const bool use_op = qp_operator_form(cfg, N);
 #if FTMPC_HAVE_DENSE_FACTOR
     const bool dense_factor = (cfg.qp_method & 16) != 0;      // bit 4: condensed Hessian + Cholesky + triangular inverse (the round-1 path)
 #endif
@@ -2150,7 +2214,8 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         else
 #endif
             bad = factor_riccati(blk, cfg, L, s, Jz, Wz, w + L.oJz, w + L.oWz, w + L.oX, w + L.oU, xref, w + L.oGV,
-                                 w + L.oHV, theta, sigma, lam_prev, &dscale, !have_j, !have_w, io.uref ? w + L.oCq : nullptr);
+                                 w + L.oHV, theta, sigma, lam_prev, &dscale, !have_j, !have_w, io.uref ? w + L.oCq : nullptr,
+                                 !use_op);
         have_j = true;                  // Jz survives a failed factorisation, the scaled Wz does not
         have_w = false;
         if (!bad) break;
@@ -2169,6 +2234,43 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         }
         else { FT_DBG_COUNT(theta == 1.0 ? 3 : 4); theta = (theta > cfg.theta_first) ? 0.5 * theta : 0.0; }     // below the first blend level: Gauss-Newton
     }
+    MpcCons cons{N, n, nv, L.mc, s.hull, io.cfg_g->Af, s.cv, io.tf_val, io.tf_idx};
+    int qit1 = 0;
+    if (use_op) {
+        // ---- operator form: nothing of size n^2 exists; K = E E' is applied through the stage records (ric_apply)
+        RicKOp<Blk> kop;
+        kop.op.N = N; kop.op.n = n; kop.op.nv = nv; kop.op.Jz = Jz; kop.op.Rec = Wz; kop.op.dt = cfg.dt;
+        kop.op.inv_rho = 1.0 / cfg.rho_slack;
+        kop.op.scr = s.G;                           // on-chip when the caller provided fast_work
+        qp_op_stage(kop, fast_work, ne);
+        // G-form when the scratch has the room (the GL region of long horizons), else the two-interval form
+        kop.G = nullptr;
+        if (s.GL) {
+            ric_build_g(blk, N, cfg.dt, Jz, Wz, s.GL);
+            kop.G = s.GL;
+        }
+        // work vectors carved from the (unused) E region; R^-1 goes behind them: the RS region holds the stage records
+        double* p = s.E;
+        GisWork gw;
+        gw.qcap = (nv < FTMPC_OP_QCAP) ? nv : FTMPC_OP_QCAP;
+        gw.K = nullptr;
+        gw.xe = s.gi.xe; gw.s = s.gi.s; gw.pos = s.gi.pos;
+        gw.ye = p; p += ne; gw.ze = p; p += ne; gw.c = p; p += ne;
+        double* vin = p; p += ne;
+        gw.u = p; p += gw.qcap + 2; gw.w = p; p += gw.qcap + 2; gw.v = p; p += gw.qcap + 2; gw.r = p; p += gw.qcap + 2;
+        gw.cs = p; p += 2 * (gw.qcap + 2); gw.tmp = p; p += gw.qcap + 2; gw.sub = p; p += gw.qcap + 2;
+        gw.act = reinterpret_cast<int*>(p); p += (gw.qcap + 3) / 2 + 1;
+        gw.itmp = reinterpret_cast<int*>(p); p += (gw.qcap + 3) / 2 + 1;
+        gw.Ui = p;
+        // unconstrained minimiser  x = -K [ga ; 0 ; 0]
+        for (int i = tid; i < ne; i += nt) vin[i] = (i < n) ? -s.ga[i] : 0.0;
+        blk.sync();
+        kop.apply(blk, vin, s.gi.xe, N - 1, false);
+        blk.mark(PH_QPSETUP);
+        blk.count(CT_QP);
+        st = gis_solve_op(blk, cons, gw, kop, vin, ne, L.m, w + L.oLam + L.m, cfg.max_qp_iter, cfg.qp_tol, &qit1, &nact);
+        have_j = false; have_w = false;
+    } else {
     // slack variable column/row, extension rows  X J  (X = d x_N[0:9] / d U)
     for (int i = tid; i < nv; i += nt) {
         s.E[(size_t)i * ld + n] = 0.0;
@@ -2215,10 +2317,8 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         s.gi.xe[row] = -((a0 + a1) + (a2 + a3));
     }
     blk.sync();
-    MpcCons cons{N, n, nv, L.mc, s.hull, io.cfg_g->Af, s.cv, io.tf_val, io.tf_idx};
     blk.mark(PH_QPSETUP);
     blk.count(CT_QP);
-    int qit1 = 0;
     // the previous multipliers are still needed if this attempt is rejected: the QP writes to the spare copy
 #if !defined(__CUDACC__)
     if (cfg.qp_method == 2) {
@@ -2245,6 +2345,7 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     st = gi_solve(blk, cons, s.gi, nv, ne, ld, L.m, 0, w + L.oLam + L.m, cfg.max_qp_iter, cfg.qp_tol, &qit1, &nact,
                   (cfg.warm_qp != 0 && sc[SC_ITER] > 0.0 && sc[SC_DMAX] <= 1.0) ? lam_prev : nullptr, L.mc);    // hit rate 4 % above |d| = 1
     have_j = false;                     // R^-1 has overwritten the staged Jacobians
+    }
 #if defined(FTMPC_DEBUG_COUNTERS) && !defined(__CUDACC__)
     if (cfg.warm_qp != 0 && sc[SC_ITER] > 0.0) {       // warm-start outcome binned by the size of the previous step
         const double dm = sc[SC_DMAX];

@@ -67,10 +67,18 @@ typedef struct ftmpc_config {
     int32_t warm_qp;           /* 1 = start each QP from the previous QP's active set (gi_warm_start): -40 % active-set iterations, same
                                   results; default 0 -- on the B200 the bulk update currently costs what it saves (profiles/README.md) */
     int32_t n_poly, n_root, n_hull_sets;
-    int32_t qp_method;         /* 0 = null-space form of the dual active-set QP (J = L^-T Q rotated in shared memory, ftmpc_gi.cuh), one
-                                      CTA per SM (default);  1 = range-space form on the packed extended inverse K (ftmpc_qp2.cuh /
-                                      ftmpc_gis.cuh), two CTAs per SM, for horizons N <= 20 (longer ones fall back to 0);
-                                  2 = as 1, and the CPU checker (oracle/cpu_port) runs its range-space prototype too          */
+    int32_t qp_method;         /* bit field; 0 = default.  The QP of every SQP iteration is factorised stage by stage (Riccati
+                                  recursion, csrc/ftmpc_riccati.cuh) and solved by a dual active-set method in
+                                    - null-space form, J = Phi^-1 blkdiag(C_t^-T) rotated in shared memory (ftmpc_gi.cuh), one CTA per
+                                      SM, for horizons N <= 20;
+                                    - operator form for N > 20: range-space iteration, K = E E' applied through the stage records,
+                                      nothing of size N^2 in memory (ftmpc_gis.cuh: gis_solve_op, ric_apply_g).
+                                  bits 0-1: 1 = experimental k_solve2 (two CTAs per SM, range-space form on the packed dense K,
+                                            ftmpc_qp2.cuh; N <= 20), 2 = as 1 and the CPU checker runs its dense range-space prototype;
+                                  bit 3 (8):  long horizons condense with the O(N^3) form (only with bit 4);
+                                  bit 4 (16): round-1 factorisation (condensed Hessian + Cholesky + L^-T) -- host builds and CUDA
+                                              builds made with -DFTMPC_DENSE_FACTOR only (A/B measurements);
+                                  bit 5 (32): operator form at every horizon;   bit 6 (64): never the operator form.           */
     double dt, mass, inertia[3], r[3], f_virt[3], max_thrust;   /* sys_model.py:52-61, spiral_parameters.py:33-39 */
     double Q[FTMPC_NE], R[FTMPC_NU];                            /* reactive.yaml:32-33                      */
     double D[FTMPC_NU * FTMPC_NTHR];                            /* allocation matrix, sys_model.py:73-123   */
