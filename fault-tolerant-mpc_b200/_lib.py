@@ -21,9 +21,10 @@ MAX_POLY, MAX_ROOT = 32, 16
 PHASE_NAMES = ['ls', 'lin', 'condense', 'cholesky', 'inverse', 'qp_setup', 'qp_active_set', 'qp_post', 'out',
                'ls_rollout', 'ls_eval', 'ls_terminal', 'chol_panel', 'chol_syrk', 'gi_select', 'gi_d', 'gi_z', 'gi_step', 'gi_update',
                'gi_drop', 'lin_jac', 'lin_costate', 'cond_pre', 'cond_col', 'cond_blk', 'warm_d0', 'warm_qr', 'warm_solve', 'warm_E',
+               'ric_setup', 'ric_ab_step1', 'ric_ab_step2', 'ric_ab_wait', 'ric_cd', 'ric_cd_wait', 'ric_backsubst', 'ric_forward',
                'n_instances', 'n_sqp_iter', 'n_condense', 'n_chol_fail', 'n_qp', 'n_gi_iter', 'n_gi_drop', 'n_ls_backtrack', 'n_gi_warm_ok', 'n_gi_warm_miss', 'n_gi_refine']
 N_PHASES = len(PHASE_NAMES)
-N_CYCLE_PHASES = 29
+N_CYCLE_PHASES = 37
 ST_OK, ST_MAXITER, ST_QPFAIL, ST_INFEASIBLE, ST_ALLOC, ST_BADINPUT = 0, 1, 2, 3, 4, 5
 
 _PKG = Path(__file__).resolve().parent

@@ -43,6 +43,9 @@ enum { PH_LS = 0, PH_LIN, PH_COND, PH_CHOL, PH_INV, PH_QPSETUP, PH_GI, PH_POST, 
        // finer attribution inside the phases above (the coarse ids then only receive the remainder)
        PH_LS_ROLL, PH_LS_EVAL, PH_LS_TERM, PH_CHOL_PANEL, PH_CHOL_SYRK, PH_GI_SELECT, PH_GI_D, PH_GI_Z, PH_GI_STEP, PH_GI_UPD,
        PH_GI_DROP, PH_LIN_JAC, PH_LIN_MU, PH_COND_PRE, PH_COND_COL, PH_COND_BLK, PH_WS_D0, PH_WS_QR, PH_WS_SOLVE, PH_WS_E,
+       // Riccati factorisation (ftmpc_riccati.cuh): set-up, the two steps of the AB interval as warp 0 sees them + its wait at
+       // the barrier, the CD interval (thread 0's Cholesky chain) + wait, the back-substitution pass, the forward rollouts
+       PH_RIC_PRE, PH_RIC_AB1, PH_RIC_AB2, PH_RIC_ABW, PH_RIC_CD, PH_RIC_CDW, PH_RIC_POST, PH_RIC_FWD,
        // event counters (not cycles)
        CT_INST, CT_SQP, CT_CONDENSE, CT_CHOL_FAIL, CT_QP, CT_GI_ITER, CT_GI_DROP, CT_LS_BACKTRACK, CT_GI_WARM_OK, CT_GI_WARM_MISS, CT_GI_REFINE,
        PH_COUNT };

@@ -181,7 +181,7 @@ __device__ __forceinline__ int ric_backward_cuda(CudaBlock& blk, const ftmpc_con
             if (!aug && c >= 13) ga_out[t * FTMPC_NU + c - 13] = 0.0;
         }
         __syncwarp();
-        blk.mark(PH_WS_QR);
+        blk.mark(PH_RIC_AB1);
         if (ab_on) {
             const double* pc = PABs + c2 * 13;
             double v;
@@ -204,9 +204,9 @@ __device__ __forceinline__ int ric_backward_cuda(CudaBlock& blk, const ftmpc_con
             F[hi * 19 + lo] = v;
             F[lo * 19 + hi] = v;
         }
-        blk.mark(PH_CHOL_PANEL);
+        blk.mark(PH_RIC_AB2);
         blk.sync();
-        blk.mark(PH_WS_D0);
+        blk.mark(PH_RIC_ABW);
         // ================= CD
         const int par = t & 1;
         if (cd_on) {
@@ -269,9 +269,9 @@ __device__ __forceinline__ int ric_backward_cuda(CudaBlock& blk, const ftmpc_con
                 }
             }
         }
-        blk.mark(PH_CHOL_SYRK);
+        blk.mark(PH_RIC_CD);
         blk.sync();
-        blk.mark(PH_WS_SOLVE);
+        blk.mark(PH_RIC_CDW);
         if (flg[0] != 0.0) { *dscale_out = flg[1 + (par ^ 1)]; return (int)flg[0]; }
     }
     *dscale_out = flg[2];                                           // written at t = 0
@@ -308,7 +308,7 @@ __device__ __forceinline__ int ric_backward_cuda(CudaBlock& blk, const ftmpc_con
         }
     }
     blk.sync();
-    blk.mark(PH_WS_E);
+    blk.mark(PH_RIC_POST);
     return 0;
 }
 template <class Blk> struct RicCuda { static constexpr bool value = false; };
@@ -478,7 +478,7 @@ FT_HD int riccati_factor(Blk& blk, const ftmpc_config& cfg, const Lay& L, const 
     double b_diag = 0.0;                   // constant diagonal of the stage Hessian: 2Q on (p, v, omega), 2R on u
     if (tid < 190 && b_c1 == b_c2) b_diag = (b_c1 < FTMPC_NE) ? 2.0 * cfg.Q[b_c1 < FTMPC_NE ? b_c1 : 0] : ((b_c1 >= 13) ? 2.0 * cfg.R[b_c1 - 13] : 0.0);
     blk.sync();
-    blk.mark(PH_COND_PRE);
+    blk.mark(PH_RIC_PRE);
     bool swept = false;
 #if defined(__CUDA_ARCH__)
     if (RicCuda<Blk>::value && nt == 256) {
@@ -533,7 +533,7 @@ FT_HD int riccati_factor(Blk& blk, const ftmpc_config& cfg, const Lay& L, const 
             }
         }
         blk.sync();
-        blk.mark(PH_WS_D0);
+        blk.mark(PH_RIC_AB1);
         // (B) F = [A B]' PAB + stage Hessian, lower triangle (c1 >= c2)
         for (int idx = tid; idx < 190; idx += nt) {
             int c1 = b_c1, c2 = b_c2;
@@ -569,7 +569,7 @@ FT_HD int riccati_factor(Blk& blk, const ftmpc_config& cfg, const Lay& L, const 
             F[c1 * 19 + c2] = v;
         }
         blk.sync();
-        blk.mark(PH_WS_QR);
+        blk.mark(PH_RIC_AB2);
         // (C) Lam = F_uu = C C', C^-1; Kh = C^-1 F_ux: the 13 threads of the columns of F_ux factor Lam redundantly
         //     (a 6x6 Cholesky is a serial chain either way) and go on to their forward substitution without a barrier
         for (int c = tid; c < FTMPC_NX; c += nt) {
@@ -603,7 +603,7 @@ FT_HD int riccati_factor(Blk& blk, const ftmpc_config& cfg, const Lay& L, const 
             }
         }
         blk.sync();
-        blk.mark(PH_WS_SOLVE);
+        blk.mark(PH_RIC_CD);
         if (flg[0] != 0.0) { *dscale_out = flg[2]; return (int)flg[0]; }
         // (D) P_t = F_xx - Kh' Kh  (symmetric; both halves written);  K_t = C^-T Kh -> stage record (off the critical path)
         for (int idx = tid; idx < 96 + 78 + 1; idx += nt) {
@@ -628,12 +628,12 @@ FT_HD int riccati_factor(Blk& blk, const ftmpc_config& cfg, const Lay& L, const 
             }
         }
         blk.sync();
-        blk.mark(PH_WS_E);
+        blk.mark(PH_RIC_CDW);
     }
     if (!swept) *dscale_out = flg[1];
     for (int a = tid; a < n; a += nt) s.ga[a] += s.g[a];
     blk.sync();
-    blk.mark(PH_COND_BLK);
+    blk.mark(PH_RIC_POST);
     if (!want_columns) return 0;                   // operator form (ric_apply): the stage records are all the QP needs
     // ---- forward: one closed-loop rollout per column of J
     // (a lane pair per column with shuffled halves was measured slower: the rollouts are bound by the shared-memory
@@ -692,7 +692,7 @@ FT_HD int riccati_factor(Blk& blk, const ftmpc_config& cfg, const Lay& L, const 
         s.gi.d[a] = dacc;
     }
     blk.sync();
-    blk.mark(PH_COND_COL);
+    blk.mark(PH_RIC_FWD);
     return 0;
 }
 
