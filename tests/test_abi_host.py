@@ -241,3 +241,16 @@ def test_bench_reference_arm_prints_one_json_line(built):
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "solves/s" and d["value"] > 0 and d["dtype"] == "f64"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_state_bounds_are_refused_with_the_reference_lines():
+    """params['xub'] / params['xlb'] (spiraling_mpc.py:129-130, 180-185) are part of the reference constructor's contract and
+    are REFUSED here -- before any device work, so the refusal does not depend on a GPU"""
+    import ftmpc_import
+    ftmpc_import.load()
+    from ft_mpc_b200.controllers import SpiralingController
+    from ft_mpc_b200.models import SpiralModel, SystemModel
+    model = SpiralModel.from_system_model(SystemModel(0.1))
+    for key in ("xub", "xlb"):
+        with pytest.raises(NotImplementedError, match="spiraling_mpc.py:129-130"):
+            SpiralingController(model, {"horizon": 15, key: [1.0] * 13}, None)
