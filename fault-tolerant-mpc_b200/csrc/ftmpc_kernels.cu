@@ -58,6 +58,12 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
     __shared__ double s_tfv[2 * FTMPC_NF];
     __shared__ int s_tfi[2 * FTMPC_NF];
     CudaBlock blk(red, prof);
+    __shared__ unsigned s_op_par;
+    if (GS && threadIdx.x == 0) {                 // global-scratch kernel: the mbarrier belongs to the operator products (ric_apply_staged)
+        s_op_par = 0u;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&s_mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     if (!GS) tma_bar_init(&s_mbar, blk.tma);      // per-instance data is staged by TMA bulk copies when the scratch is shared memory
     const int slot = blockIdx.x;
     const double* sc = ws_slot(io, L, slot) + L.oSc;
@@ -94,7 +100,8 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
             // with the shared-memory scratch the linearisation leaves Jz / Wz where condensing reads them
             const bool staged = !GS && lin_scratch_doubles(L.N) <= (size_t)(L.nv + FTMPC_NE) * L.nv && condense_fast_path(L, blockDim.x);
             phase_lin(blk, cfg, L, io, inst, slot, lin_place_v1(scratch, L.N, staged));
-            phase_qp(blk, cfg, L, io, inst, slot, scratch, staged, GS ? smem : nullptr);
+            phase_qp(blk, cfg, L, io, inst, slot, scratch, staged, GS ? smem : nullptr,
+                     GS ? (unsigned)__cvta_generic_to_shared(&s_mbar) : 0u, GS ? &s_op_par : nullptr);
             phase_ls_block(blk, cfg, L, io, inst, slot, 0, scratch);
         }
         phase_out_write(blk, cfg, L, io, inst, slot);

@@ -712,7 +712,7 @@ struct RicOp {
     const double* Jz;      // [N][169]
     const double* Rec;     // [N][169]  K_t [6][13] at 0, C_t^-1 [6][6] (lower) at 78
     double dt, inv_rho;
-    double* scr;           // 64 doubles of (fast) scratch
+    double* scr;           // 72 doubles of (fast) scratch
 };
 // one stage of the adjoint sweep: y = vx + B' mu, z = C^-1 y -> zout, mu_t = A' mu - K' y -> mn   (two barrier intervals)
 template <class WB>
@@ -805,7 +805,7 @@ FT_HD void ric_apply(WB& wb, const RicOp& op, const double* v, double* out, int 
 // i.e. one barrier interval per stage and direction, 19 lanes running the same 19-long dot product (no divergent
 // branches; the two-interval form above serialises four of them per stage).  G_t and Lam_t^-1 are built once per
 // factorisation, all stages in parallel (ric_build_g), FTMPC_RIC_GSTG doubles per stage.
-#define FTMPC_RIC_GSTG 397          /* G [19][19] row-major, then Lam^-1 [6][6] */
+#define FTMPC_RIC_GSTG 398          /* G [19][19] row-major, then Lam^-1 [6][6], one pad: a multiple of 16 bytes (bulk copies) */
 template <class Blk>
 FT_HD void ric_build_g(Blk& blk, int N, double dt, const double* Jz, const double* Rec, double* G) {
     const int tid = blk.tid(), nt = blk.nthreads();
@@ -822,18 +822,22 @@ FT_HD void ric_build_g(Blk& blk, int N, double dt, const double* Jz, const doubl
             } else if (r < 13) v = jz[(7 + c - 13) * 13 + r];     // B
             else if (c < 13) v = -rec[(r - 13) * 13 + c];         // -K
             else v = (r == c) ? 1.0 : 0.0;
-        } else {
+        } else if (e < 397) {
             const int i = (e - 361) / 6, j = (e - 361) - i * 6;   // Lam^-1 = C^-T C^-1
             v = 0.0;
             for (int m = (i > j ? i : j); m < FTMPC_NU; ++m) v += rec[78 + m * 6 + i] * rec[78 + m * 6 + j];
-        }
+        } else v = 0.0;
         G[idx] = v;
     }
     blk.sync();
 }
 // out[lane] = sum_k G(lane, k) in[k]  (forward, TR = false)  or  sum_k G(k, lane) in[k]  (backward, TR = true), 19 lanes
+// (cp_dst / cp_src: six values copied by the first lanes on the way -- the forward sweep parks u_t in a two-slot buffer and
+//  moves it to the result one step later, so that no lane overwrites a w_t entry another lane is still reading)
 template <bool TR, class WB>
-FT_HD void ric_g_step(WB& wb, const double* G, const double* in13, const double* in6, double* out13, double* out6) {
+FT_HD void ric_g_step(WB& wb, const double* G, const double* in13, const double* in6, double* out13, double* out6,
+                      double* cp_dst = nullptr, const double* cp_src = nullptr) {
+    if (cp_dst) for (int l = wb.tid(); l < FTMPC_NU; l += wb.nthreads()) cp_dst[l] = cp_src[l];
     for (int l = wb.tid(); l < 19; l += wb.nthreads()) {
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;
 #pragma unroll
@@ -890,13 +894,15 @@ FT_HD void ric_apply_g(WB& wb, const RicOp& op, const double* G, const double* v
         ric_g_scale(wb, G + (size_t)t0 * FTMPC_RIC_GSTG, out + FTMPC_NU * t0, (t_top + 1 - t0 < 16) ? t_top + 1 - t0 : 16);
     for (int i = tid; i < 13; i += nt) dxb[i] = 0.0;
     wb.sync();
+    double* ub = op.scr + 58;      // [2][6]  u_t of the last two stages
     for (int t = 0; t < N; ++t)
         ric_g_step<false>(wb, G + (size_t)t * FTMPC_RIC_GSTG, dxb + (t & 1) * 13, out + FTMPC_NU * t, dxb + ((t + 1) & 1) * 13,
-                          out + FTMPC_NU * t);
+                          ub + (t & 1) * 6, t > 0 ? out + FTMPC_NU * (t - 1) : nullptr, ub + ((t - 1) & 1) * 6);
     const double* dx = dxb + (N & 1) * 13;
-    for (int i = tid; i <= FTMPC_NE; i += nt) {
+    for (int i = tid; i <= FTMPC_NE + FTMPC_NU; i += nt) {
         if (i < FTMPC_NE) out[nv + i] = dx[i];
-        else out[n] = v[n] * op.inv_rho;
+        else if (i == FTMPC_NE) out[n] = v[n] * op.inv_rho;
+        else out[FTMPC_NU * (N - 1) + i - FTMPC_NE - 1] = ub[((N - 1) & 1) * 6 + i - FTMPC_NE - 1];
     }
     wb.sync();
 }
@@ -904,75 +910,154 @@ FT_HD void ric_apply_g(WB& wb, const RicOp& op, const double* G, const double* v
 #if defined(__CUDACC__)
 // ---- G-form with the stage matrices STAGED through shared memory (scratch in global memory: long horizons) -----------------
 // Every interval of the sweeps would otherwise start with a round trip to L2 for the stage matrix (measured with the
-// two-interval form: 0.35 ms per active-set iteration at N = 100).  Warp 0 sweeps a chunk of RIC_CH stages out of one half
-// of a double buffer while the other seven warps fetch the next chunk into the other half; v and the result live in shared
-// memory for the duration of the product.  One block barrier per chunk.
+// two-interval form: 0.35 ms per active-set iteration at N = 100).  Warp 0 sweeps a chunk of RIC_CH stages out of one half of
+// a double buffer while the NEXT chunk arrives in the other half as ONE bulk copy (cp.async.bulk global -> shared, 50 KB,
+// issued by lane 0, completion on an mbarrier): no load / store instruction of any warp is spent on the staging, and the
+// other seven warps simply wait for the product at the block barrier behind it.  v and the result live in shared memory for
+// the duration of the product.
 #define FTMPC_RIC_CH 16
 struct RicStage {
-    double* buf;       // [2][RIC_CH][RIC_GSTG]
+    double* buf;       // [2][RIC_CH][RIC_GSTG], 16-byte aligned
     double* sv;        // [nv + 9]
     double* so;        // [nv + 9]
+    unsigned mbar;     // shared address of the mbarrier of the bulk copies (initialised once per kernel, count 1)
+    unsigned* par;     // its phase parity, carried from product to product (shared memory, written by lane 0 of warp 0)
 };
-__device__ __forceinline__ void ric_stage_chunk(const double* G, double* dst, int t0, int cnt, int tid0, int nthr) {
-    const double* src = G + (size_t)t0 * FTMPC_RIC_GSTG;
-    for (int idx = tid0; idx < cnt * FTMPC_RIC_GSTG; idx += nthr) dst[idx] = src[idx];
+// shared-memory accessors on 32-bit shared addresses: the staged sweeps run entirely out of shared memory, but their pointers
+// reach them through run-time selected fields, so the compiler would emit generic LD / ST (longer latency, long scoreboard)
+__device__ __forceinline__ double ric_lds(unsigned a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void ric_sts(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+template <bool TR>
+__device__ __forceinline__ void ric_g_step_sh(unsigned G, unsigned in13, unsigned in6, unsigned out13, unsigned out6, unsigned cp_dst,
+                                              unsigned cp_src, bool cp) {
+    const int l = threadIdx.x & 31;
+    if (cp && l < FTMPC_NU) ric_sts(cp_dst + 8u * l, ric_lds(cp_src + 8u * l));
+    if (l < 19) {
+        double g[19], x[19];
+#pragma unroll
+        for (int k = 0; k < 19; ++k) g[k] = ric_lds(G + 8u * (unsigned)(TR ? k * 19 + l : l * 19 + k));
+#pragma unroll
+        for (int k = 0; k < 13; ++k) x[k] = ric_lds(in13 + 8u * k);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) x[13 + k] = ric_lds(in6 + 8u * k);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 16; k += 4) { a0 += g[k] * x[k]; a1 += g[k + 1] * x[k + 1]; a2 += g[k + 2] * x[k + 2]; a3 += g[k + 3] * x[k + 3]; }
+        a0 += g[16] * x[16]; a1 += g[17] * x[17]; a2 += g[18] * x[18];
+        const double v = (a0 + a1) + (a2 + a3);
+        ric_sts((l < 13) ? out13 + 8u * l : out6 + 8u * (l - 13), v);
+    }
+    __syncwarp();
+}
+// w = Lam^-1 y for cnt <= 32 stages, a lane per stage (Gs, zu in shared memory)
+__device__ __forceinline__ void ric_g_scale_sh(unsigned Gs, unsigned zu, int cnt) {
+    const int k = threadIdx.x & 31;
+    if (k < cnt) {
+        const unsigned li = Gs + 8u * (unsigned)(k * FTMPC_RIC_GSTG + 361), z = zu + 8u * (unsigned)(k * FTMPC_NU);
+        double yk[FTMPC_NU], wk[FTMPC_NU];
+#pragma unroll
+        for (int m = 0; m < FTMPC_NU; ++m) yk[m] = ric_lds(z + 8u * m);
+#pragma unroll
+        for (int i = 0; i < FTMPC_NU; ++i) {
+            double a = 0.0;
+#pragma unroll
+            for (int m = 0; m < FTMPC_NU; ++m) a += ric_lds(li + 8u * (i * 6 + m)) * yk[m];
+            wk[i] = a;
+        }
+#pragma unroll
+        for (int i = 0; i < FTMPC_NU; ++i) ric_sts(z + 8u * i, wk[i]);
+    }
+    __syncwarp();
+}
+// lane 0 of warp 0: request stages t0 .. t0 + cnt - 1 as one bulk copy; every lane of warp 0 then waits with ric_chunk_wait
+__device__ __forceinline__ void ric_chunk_request(const RicStage& sg, const double* G, double* dst, int t0, int cnt) {
+    const unsigned bytes = (unsigned)cnt * FTMPC_RIC_GSTG * 8u;
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sg.mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+                 "l"(G + (size_t)t0 * FTMPC_RIC_GSTG), "r"(bytes), "r"(sg.mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void ric_chunk_wait(const RicStage& sg, unsigned& par) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(sg.mbar), "r"(par)
+                     : "memory");
+    }
+    par ^= 1u;
 }
 __device__ __forceinline__ void ric_apply_staged(CudaBlock& blk, const RicOp& op, const double* G, const RicStage& sg, const double* v,
                                                  double* out, int t_top, bool has_e) {
     const int N = op.N, n = op.n, nv = op.nv, tid = threadIdx.x, nt = blockDim.x, ne = nv + FTMPC_NE;
     double* mu0 = op.scr;
     double* dxb = op.scr + 32;
-    WarpBlock wb;
+    double* ub = op.scr + 58;
+    const unsigned mu_sh = (unsigned)__cvta_generic_to_shared(mu0), dx_sh = (unsigned)__cvta_generic_to_shared(dxb);
+    const unsigned ub_sh = (unsigned)__cvta_generic_to_shared(ub), sv_sh = (unsigned)__cvta_generic_to_shared(sg.sv);
+    const unsigned so_sh = (unsigned)__cvta_generic_to_shared(sg.so);
     if (has_e) t_top = N - 1;
+    const size_t half = (size_t)FTMPC_RIC_CH * FTMPC_RIC_GSTG;
+    if (tid == 0) {                                                   // first chunk of the adjoint sweep: in flight during the set-up
+        const int lo = (t_top - FTMPC_RIC_CH + 1 > 0) ? t_top - FTMPC_RIC_CH + 1 : 0;
+        ric_chunk_request(sg, G, sg.buf, lo, t_top - lo + 1);
+    }
     for (int i = tid; i < ne; i += nt) { sg.sv[i] = v[i]; sg.so[i] = 0.0; }
     if (tid < 13) mu0[((t_top + 1) & 1) * 13 + tid] = (has_e && tid < FTMPC_NE) ? v[nv + tid] : 0.0;
     if (tid >= 32 && tid < 45) dxb[tid - 32] = 0.0;
-    const size_t half = (size_t)FTMPC_RIC_CH * FTMPC_RIC_GSTG;
-    // ---- backward, chunks from the top stage down (w = Lam^-1 y of a chunk right behind its sweep)
-    int hi = t_top, b = 0;
-    {
-        const int lo = (hi - FTMPC_RIC_CH + 1 > 0) ? hi - FTMPC_RIC_CH + 1 : 0;
-        ric_stage_chunk(G, sg.buf, lo, hi - lo + 1, tid, nt);
-    }
     blk.sync();
-    while (hi >= 0) {
-        const int lo = (hi - FTMPC_RIC_CH + 1 > 0) ? hi - FTMPC_RIC_CH + 1 : 0;
-        const double* cur = sg.buf + (size_t)b * half;
-        if (tid < 32) {
+    if (tid < 32) {
+        unsigned par = *sg.par;
+        // ---- backward, chunks from the top stage down (w = Lam^-1 y of a chunk right behind its sweep)
+        int hi = t_top, b = 0;
+        while (hi >= 0) {
+            const int lo = (hi - FTMPC_RIC_CH + 1 > 0) ? hi - FTMPC_RIC_CH + 1 : 0;
+            ric_chunk_wait(sg, par);
+            if (tid == 0) {                                           // next chunk (or the first one of the rollout) into the other half
+                if (lo > 0) {
+                    const int nhi = lo - 1, nlo = (nhi - FTMPC_RIC_CH + 1 > 0) ? nhi - FTMPC_RIC_CH + 1 : 0;
+                    ric_chunk_request(sg, G, sg.buf + (size_t)(b ^ 1) * half, nlo, nhi - nlo + 1);
+                } else {
+                    ric_chunk_request(sg, G, sg.buf + (size_t)(b ^ 1) * half, 0, (N < FTMPC_RIC_CH) ? N : FTMPC_RIC_CH);
+                }
+            }
+            const unsigned c_sh = (unsigned)__cvta_generic_to_shared(sg.buf + (size_t)b * half);
             for (int t = hi; t >= lo; --t)
-                ric_g_step<true>(wb, cur + (size_t)(t - lo) * FTMPC_RIC_GSTG, mu0 + ((t + 1) & 1) * 13, sg.sv + FTMPC_NU * t,
-                                 mu0 + (t & 1) * 13, sg.so + FTMPC_NU * t);
-            ric_g_scale(wb, cur, sg.so + FTMPC_NU * lo, hi - lo + 1);
-        } else if (lo > 0) {
-            const int nhi = lo - 1, nlo = (nhi - FTMPC_RIC_CH + 1 > 0) ? nhi - FTMPC_RIC_CH + 1 : 0;
-            ric_stage_chunk(G, sg.buf + (size_t)(b ^ 1) * half, nlo, nhi - nlo + 1, tid - 32, nt - 32);
+                ric_g_step_sh<true>(c_sh + 8u * (unsigned)((t - lo) * FTMPC_RIC_GSTG), mu_sh + 8u * (((t + 1) & 1) * 13),
+                                    sv_sh + 8u * (FTMPC_NU * t), mu_sh + 8u * ((t & 1) * 13), so_sh + 8u * (FTMPC_NU * t), 0u, 0u, false);
+            ric_g_scale_sh(c_sh, so_sh + 8u * (FTMPC_NU * lo), hi - lo + 1);
+            hi = lo - 1;
+            b ^= 1;
         }
-        blk.sync();
-        hi = lo - 1;
-        b ^= 1;
-    }
-    // ---- forward, chunks from stage 0 up
-    int lo = 0;
-    b = 0;
-    ric_stage_chunk(G, sg.buf, 0, (N < FTMPC_RIC_CH) ? N : FTMPC_RIC_CH, tid, nt);
-    blk.sync();
-    while (lo < N) {
-        const int cnt = (N - lo < FTMPC_RIC_CH) ? N - lo : FTMPC_RIC_CH;
-        const double* cur = sg.buf + (size_t)b * half;
-        if (tid < 32) {
+        // ---- forward, chunks from stage 0 up (the first one was requested behind the last chunk of the adjoint sweep)
+        int lo = 0;
+        while (lo < N) {
+            const int cnt = (N - lo < FTMPC_RIC_CH) ? N - lo : FTMPC_RIC_CH;
+            ric_chunk_wait(sg, par);
+            if (tid == 0 && lo + cnt < N) {
+                const int nlo = lo + cnt, ncnt = (N - nlo < FTMPC_RIC_CH) ? N - nlo : FTMPC_RIC_CH;
+                ric_chunk_request(sg, G, sg.buf + (size_t)(b ^ 1) * half, nlo, ncnt);
+            }
+            const unsigned c_sh = (unsigned)__cvta_generic_to_shared(sg.buf + (size_t)b * half);
             for (int t = lo; t < lo + cnt; ++t)
-                ric_g_step<false>(wb, cur + (size_t)(t - lo) * FTMPC_RIC_GSTG, dxb + (t & 1) * 13, sg.so + FTMPC_NU * t,
-                                  dxb + ((t + 1) & 1) * 13, sg.so + FTMPC_NU * t);
-        } else if (lo + cnt < N) {
-            const int nlo = lo + cnt, ncnt = (N - nlo < FTMPC_RIC_CH) ? N - nlo : FTMPC_RIC_CH;
-            ric_stage_chunk(G, sg.buf + (size_t)(b ^ 1) * half, nlo, ncnt, tid - 32, nt - 32);
+                ric_g_step_sh<false>(c_sh + 8u * (unsigned)((t - lo) * FTMPC_RIC_GSTG), dx_sh + 8u * ((t & 1) * 13), so_sh + 8u * (FTMPC_NU * t),
+                                     dx_sh + 8u * (((t + 1) & 1) * 13), ub_sh + 8u * ((t & 1) * 6), so_sh + 8u * (FTMPC_NU * (t > 0 ? t - 1 : 0)),
+                                     ub_sh + 8u * (((t - 1) & 1) * 6), t > 0);
+            lo += cnt;
+            b ^= 1;
         }
-        blk.sync();
-        lo += cnt;
-        b ^= 1;
+        if (tid == 0) *sg.par = par;
     }
+    blk.sync();
     const double* dx = dxb + (N & 1) * 13;
-    for (int i = tid; i < ne; i += nt) out[i] = (i < n) ? sg.so[i] : ((i == n) ? v[n] * op.inv_rho : dx[i - nv]);
+    for (int i = tid; i < ne; i += nt)
+        out[i] = (i < n) ? ((i >= FTMPC_NU * (N - 1)) ? ub[((N - 1) & 1) * 6 + i - FTMPC_NU * (N - 1)] : sg.so[i])
+                         : ((i == n) ? v[n] * op.inv_rho : dx[i - nv]);
     blk.sync();
 }
 #endif

@@ -2137,13 +2137,15 @@ struct RicKOp<CudaBlock> {
 };
 #endif
 template <class Blk>
-FT_HD void qp_op_stage(RicKOp<Blk>&, double*, int) {}
+FT_HD void qp_op_stage(RicKOp<Blk>&, double*, int, unsigned, unsigned*) {}
 #if defined(__CUDACC__)
-__device__ __forceinline__ void qp_op_stage(RicKOp<CudaBlock>& kop, double* fast_work, int ne) {
-    kop.staged = fast_work != nullptr;
+__device__ __forceinline__ void qp_op_stage(RicKOp<CudaBlock>& kop, double* fast_work, int ne, unsigned mbar, unsigned* par) {
+    kop.staged = fast_work != nullptr && mbar != 0u;
     kop.sg.buf = fast_work ? fast_work + FTMPC_RIC_WORK : nullptr;
     kop.sg.sv = fast_work ? kop.sg.buf + 2 * (size_t)FTMPC_RIC_CH * FTMPC_RIC_GSTG : nullptr;
     kop.sg.so = fast_work ? kop.sg.sv + ne : nullptr;
+    kop.sg.mbar = mbar;
+    kop.sg.par = par;
 }
 #endif
 // horizons above FTMPC_LONG_N run the QP in operator form (qp_method bit 5 forces it at any horizon, bit 6 forbids it)
@@ -2157,7 +2159,8 @@ FT_HD bool qp_operator_form(const ftmpc_config& cfg, int N) {
 template <class Blk>
 FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst, int slot, double* scratch,
                    bool staged = false /* Jz, Wz already sit in the scratch (CUDA linearisation) */,
-                   double* fast_work = nullptr /* FTMPC_RIC_WORK doubles of on-chip memory when the scratch itself is not */) {
+                   double* fast_work = nullptr /* gs_fast_doubles() of on-chip memory when the scratch itself is not */,
+                   unsigned op_mbar = 0u, unsigned* op_par = nullptr /* mbarrier + parity word of the operator's bulk copies */) {
     double* w = ws_slot(io, L, slot);
     double* sc = w + L.oSc;
     if (sc[SC_STATUS] != FTMPC_ST_RUNNING) return;
@@ -2242,12 +2245,13 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         kop.op.N = N; kop.op.n = n; kop.op.nv = nv; kop.op.Jz = Jz; kop.op.Rec = Wz; kop.op.dt = cfg.dt;
         kop.op.inv_rho = 1.0 / cfg.rho_slack;
         kop.op.scr = s.G;                           // on-chip when the caller provided fast_work
-        qp_op_stage(kop, fast_work, ne);
+        qp_op_stage(kop, fast_work, ne, op_mbar, op_par);
         // G-form when the scratch has the room (the GL region of long horizons), else the two-interval form
         kop.G = nullptr;
         if (s.GL) {
-            ric_build_g(blk, N, cfg.dt, Jz, Wz, s.GL);
-            kop.G = s.GL;
+            double* g16 = s.GL + ((reinterpret_cast<unsigned long long>(s.GL) >> 3) & 1ull);      // bulk copies: 16-byte aligned source
+            ric_build_g(blk, N, cfg.dt, Jz, Wz, g16);
+            kop.G = g16;
         }
         // work vectors carved from the (unused) E region; R^-1 goes behind them: the RS region holds the stage records
         double* p = s.E;
