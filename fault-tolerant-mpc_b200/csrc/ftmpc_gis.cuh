@@ -318,10 +318,29 @@ FT_HD void gis_gather(Blk& blk, const Cons& cons, const GisWork& w, int ne, int 
     blk.sync();
 }
 
+// the row table of Yw follows the working set: member l leaves, its row goes to the free end (call BEFORE gis_drop, q = old size)
+template <class Blk>
+FT_HD void gis_yslot_drop(Blk& blk, int* yslot, bool on, int q, int l) {
+    if (!on) return;
+    if (blk.tid() == 0) {
+        const int freed = yslot[l];
+        for (int i = l; i < q - 1; ++i) yslot[i] = yslot[i + 1];
+        yslot[q - 1] = freed;
+    }
+    blk.sync();
+}
+// Yw (optional, [qcap][ne]) keeps  K n_k  of every member of the working set (it is the `ye` computed when the member was
+// added; yslot[k] = its row).  With it  ze = ye - K N_W r = ye - sum_k r_k Yw[k]  is a dense combination of q stored vectors
+// instead of a second operator product per iteration (the product is still used by the refinement step).
 template <class Blk, class Cons, class KOp>
 FT_HD int gis_solve_op(Blk& blk, const Cons& cons, const GisWork& w, KOp& kop, double* vin, int ne, int m, double* lam, int maxit,
-                       double tol, int* iters_out, int* nact_out) {
+                       double tol, int* iters_out, int* nact_out, double* Yw = nullptr, int* yslot = nullptr, int ycap = 0) {
     const int tid = blk.tid(), nt = blk.nthreads();
+    // ycap rows of Yw: once the working set outgrows them the rest of this QP goes back to two products per iteration
+    if (Yw) {
+        for (int k = tid; k < ycap; k += nt) yslot[k] = k;
+        blk.sync();
+    }
     const double dep_tol = 1e-14, refine_tol = 1e-13;
     const int nh = FTMPC_NH * cons.N;
     int q = 0, iters = 0, status = GI_OK;
@@ -364,10 +383,24 @@ FT_HD int gis_solve_op(Blk& blk, const Cons& cons, const GisWork& w, KOp& kop, d
             blk.sync();
             if (q > 0) {
                 gis_schur_solve(blk, w, q);
-                gis_gather(blk, cons, w, ne, q);
-                blk.mark(PH_GI_UPD);
-                kop.apply(blk, w.c, vin, cons.N - 1, true);
-                for (int i = tid; i < ne; i += nt) w.ze[i] = w.ye[i] - vin[i];
+                if (Yw) {
+                    blk.mark(PH_GI_UPD);
+                    for (int i = tid; i < ne; i += nt) {
+                        double a0 = 0.0, a1 = 0.0;
+                        int k = 0;
+                        for (; k + 1 < q; k += 2) {
+                            a0 += w.r[k] * Yw[(size_t)yslot[k] * ne + i];
+                            a1 += w.r[k + 1] * Yw[(size_t)yslot[k + 1] * ne + i];
+                        }
+                        if (k < q) a0 += w.r[k] * Yw[(size_t)yslot[k] * ne + i];
+                        w.ze[i] = w.ye[i] - (a0 + a1);
+                    }
+                } else {
+                    gis_gather(blk, cons, w, ne, q);
+                    blk.mark(PH_GI_UPD);
+                    kop.apply(blk, w.c, vin, cons.N - 1, true);
+                    for (int i = tid; i < ne; i += nt) w.ze[i] = w.ye[i] - vin[i];
+                }
                 blk.sync();
                 blk.mark(PH_GI_Z);
                 double emax = 0.0;
@@ -409,6 +442,7 @@ FT_HD int gis_solve_op(Blk& blk, const Cons& cons, const GisWork& w, KOp& kop, d
             if (t2 == INFINITY) {
                 for (int j = tid; j <= q; j += nt) w.u[j] += t * ((j < q) ? -w.r[j] : 1.0);
                 blk.sync();
+                gis_yslot_drop(blk, yslot, Yw != nullptr, q, l);
                 gis_drop(blk, w, q, l);
                 blk.count(CT_GI_DROP);
                 continue;
@@ -429,10 +463,19 @@ FT_HD int gis_solve_op(Blk& blk, const Cons& cons, const GisWork& w, KOp& kop, d
                     w.pos[p] = q;
                     w.s[p] = 0.0;
                 }
+                if (Yw) {
+                    if (q < ycap) {
+                        double* yrow = Yw + (size_t)yslot[q] * ne;
+                        for (int i = tid; i < ne; i += nt) yrow[i] = w.ye[i];
+                    } else {
+                        Yw = nullptr;                             // (uniform over the block)
+                    }
+                }
                 blk.sync();
                 q += 1;
                 added = true;
             } else {
+                gis_yslot_drop(blk, yslot, Yw != nullptr, q, l);
                 gis_drop(blk, w, q, l);
                 blk.count(CT_GI_DROP);
             }

@@ -2265,14 +2265,19 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         gw.cs = p; p += 2 * (gw.qcap + 2); gw.tmp = p; p += gw.qcap + 2; gw.sub = p; p += gw.qcap + 2;
         gw.act = reinterpret_cast<int*>(p); p += (gw.qcap + 3) / 2 + 1;
         gw.itmp = reinterpret_cast<int*>(p); p += (gw.qcap + 3) / 2 + 1;
-        gw.Ui = p;
+        gw.Ui = p; p += (size_t)gw.qcap * (gw.qcap + 1) / 2 + 2;
+        // K n_k of the working set, when the E region has the room (long horizons: it is the memory E itself would have taken)
+        int* yslot = reinterpret_cast<int*>(p); p += (gw.qcap + 3) / 2 + 1;
+        const size_t yroom = ((size_t)ne * nv > (size_t)(p - s.E)) ? ((size_t)ne * nv - (size_t)(p - s.E)) / ne : 0;
+        const int ycap = (yroom > (size_t)gw.qcap + 1) ? gw.qcap + 1 : (int)yroom;
+        double* Yw = (ycap >= 16) ? p : nullptr;
         // unconstrained minimiser  x = -K [ga ; 0 ; 0]
         for (int i = tid; i < ne; i += nt) vin[i] = (i < n) ? -s.ga[i] : 0.0;
         blk.sync();
         kop.apply(blk, vin, s.gi.xe, N - 1, false);
         blk.mark(PH_QPSETUP);
         blk.count(CT_QP);
-        st = gis_solve_op(blk, cons, gw, kop, vin, ne, L.m, w + L.oLam + L.m, cfg.max_qp_iter, cfg.qp_tol, &qit1, &nact);
+        st = gis_solve_op(blk, cons, gw, kop, vin, ne, L.m, w + L.oLam + L.m, cfg.max_qp_iter, cfg.qp_tol, &qit1, &nact, Yw, yslot, ycap);
         have_j = false; have_w = false;
     } else {
     // slack variable column/row, extension rows  X J  (X = d x_N[0:9] / d U)
