@@ -15,6 +15,6 @@ timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_$
 timeout 600 python bench.py --steps 10 --warmup 3 --batch 1024 --no-latency --no-cpu-baseline > $OUT/bench_${TAG}_b1k.json 2>/dev/null; echo "b1k rc=$?"
 timeout 600 python bench.py --steps 3 --warmup 2 --batch 65536 --no-latency --no-cpu-baseline > $OUT/bench_${TAG}_b64k.json 2>/dev/null; echo "b64k rc=$?"
 timeout 600 python bench.py --steps 5 --warmup 3 --horizon 15 --no-latency --no-cpu-baseline > $OUT/bench_${TAG}_N15.json 2>/dev/null; echo "N15 rc=$?"
-timeout 600 python bench.py --steps 3 --warmup 2 --horizon 30 --batch 4096 --no-latency --no-cpu-baseline > $OUT/bench_${TAG}_N30.json 2>/dev/null; echo "N30 rc=$?"
-timeout 900 python bench.py --steps 3 --warmup 2 --horizon 100 --batch 2048 --no-latency --no-cpu-baseline > $OUT/bench_${TAG}_N100.json 2>/dev/null; echo "N100 rc=$?"
+timeout 600 python bench.py --steps 4 --warmup 2 --horizon 30 --batch 4096 --no-latency --no-cpu-baseline > $OUT/bench_${TAG}_N30.json 2>/dev/null; echo "N30 rc=$?"
+timeout 900 python bench.py --steps 4 --warmup 2 --horizon 100 --batch 2048 --no-latency --no-cpu-baseline > $OUT/bench_${TAG}_N100.json 2>/dev/null; echo "N100 rc=$?"
 bash tools/gpu_ncu.sh $TAG
