@@ -129,3 +129,21 @@ def test_gpu_long_horizon_equals_cpu_port(ft, built):
     assert np.abs(g["iters"][:, 0] - ref["iters"][:, 0]).max() <= 1
     assert np.abs(g["u0"] - ref["u0"]).max() < 2e-6
 
+
+
+def test_cpu_long_horizon_accelerating_reference_operator_equals_dense(port):
+    """N = 30 with a non-zero nominal wrench (the input-cost coupling terms of ftmpc_riccati.cuh on the operator path)"""
+    N, B = 30, 3
+    cells, st, scen, xref = _long_inputs(N, B, 7)
+    uref = np.zeros((B, N + 1, 6)); uref[:, :, 0] = 1.5; uref[:, :, 1] = -0.7; uref[:, :, 2] = 0.4
+    sets = [c["faults"] for c in cells]
+    outs = {}
+    for qm in (0, 64):
+        cfg, table, masks, ffs, _ = H.host_tables(sets, N, qp_method=qm)
+        outs[qm] = port.step(cfg, table, st, xref, uref, masks[scen], ffs[scen], scen)
+    a, b = outs[0], outs[64]
+    assert (a["status"] == b["status"]).all() and (a["status"] == 0).any()
+    ok = a["status"] == 0
+    assert np.abs(a["iters"][ok, 0] - b["iters"][ok, 0]).max() <= 1
+    assert np.abs(a["u0"][ok] - b["u0"][ok]).max() < 2e-6
+    assert np.allclose(a["cost"][ok], b["cost"][ok], rtol=1e-9)
