@@ -380,6 +380,7 @@ __device__ __noinline__ void rollout_attitude(const ftmpc_config& cfg, int N, co
                                               const double* ur_conv /* u_ref when U still holds u (first rollout) */,
                                               const double* x0, double* Xs) {
     const DynConsts k = dyn_consts(cfg);
+    const AttConsts ac = att_consts(k);
     double w[3], q[4];
 #pragma unroll
     for (int i = 0; i < 3; ++i) w[i] = x0[6 + i];
@@ -401,6 +402,8 @@ __device__ __noinline__ void rollout_attitude(const ftmpc_config& cfg, int N, co
         for (int i = 0; i < 3; ++i) aw[i] = w[i];
 #pragma unroll
         for (int i = 0; i < 4; ++i) aq[i] = q[i];
+        // the chain form of the attitude right-hand side (dyn_wq_chain): per-step constants outside the serial RK stages
+        const double tq[3] = {tau[0] * k.iJ[0], tau[1] * k.iJ[1], tau[2] * k.iJ[2]};
 #pragma unroll
         for (int st = 0; st < 4; ++st) {
             double sw[3], sq[4];
@@ -408,7 +411,7 @@ __device__ __noinline__ void rollout_attitude(const ftmpc_config& cfg, int N, co
             for (int i = 0; i < 3; ++i) sw[i] = w[i] + cs[st] * kw[i];
 #pragma unroll
             for (int i = 0; i < 4; ++i) sq[i] = q[i] + cs[st] * kq[i];
-            dyn_wq(k, sw, sq, tau, kw, kq);
+            dyn_wq_chain(ac, tq, sw, sq, kw, kq);
 #pragma unroll
             for (int i = 0; i < 3; ++i) aw[i] += bs[st] * kw[i];
 #pragma unroll
@@ -456,6 +459,8 @@ __device__ __noinline__ void rollout_stage_task(const ftmpc_config& cfg, int t, 
     const double cs[4] = {0.0, 0.5 * k.dt, 0.5 * k.dt, k.dt};
     const double bs[4] = {k.dt / 6.0, k.dt / 3.0, k.dt / 3.0, k.dt / 6.0};
     const double cq = k.dt * k.dt / 6.0;
+    const AttConsts ac = att_consts(k);
+    const double tq[3] = {Wr[3] * k.iJ[0], Wr[4] * k.iJ[1], Wr[5] * k.iJ[2]};
 #pragma unroll
     for (int st = 0; st < 4; ++st) {
         double sw[3], sq[4], kv[3];
@@ -463,7 +468,7 @@ __device__ __noinline__ void rollout_stage_task(const ftmpc_config& cfg, int t, 
         for (int i = 0; i < 3; ++i) sw[i] = w[i] + cs[st] * kw[i];
 #pragma unroll
         for (int i = 0; i < 4; ++i) sq[i] = q[i] + cs[st] * kq[i];
-        dyn_wq(k, sw, sq, Wr + 3, kw, kq);
+        dyn_wq_chain(ac, tq, sw, sq, kw, kq);                       // (the same arithmetic as rollout_attitude: identical stage values)
         dyn_v(k, sw, sq, kw, Wr, kv);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
