@@ -403,7 +403,7 @@ def test_gpu_matches_cpu_port(L, built, golden):
     ffs = np.stack([eng.fault_force_tab[s] for s in scen])
     c = port.step(eng.cfg, eng.hull_table, st, xref, None, masks, ffs, scen)
     ok = (g["status"] == 0) & (c["status"] == 0)
-    assert ok.sum() >= 0.9 * B
+    assert ok.sum() >= B - 1, (g["status"], c["status"])          # (all 48 converge on both; one straggler tolerated)
     # both stop within the SQP termination tolerance (step <= 1e-6 once the predicted decrease is rounding noise)
     assert np.abs(g["u0"] - c["u0"])[ok].max() < 2e-6 and np.abs(g["thrust"] - c["thrust"])[ok].max() < 2e-6
     assert np.array_equal(g["active"].view(np.uint32)[ok], c["active"][ok])
@@ -464,7 +464,7 @@ def test_batch_1024_properties_and_sharding(L, oracle):
     torch.cuda.synchronize()
     g = {k: v.cpu().numpy().copy() for k, v in out.items() if k != "ws"}
     ok = g["status"] == 0
-    assert ok.mean() > 0.95, np.bincount(g["status"], minlength=6)
+    assert ok.mean() > 0.995, np.bincount(g["status"], minlength=6)     # (the host build of the same solver converges on all 1024)
     th = g["thrust"]
     assert np.isfinite(th).all() and (th >= 0).all() and (th <= 3.4 + 1e-12).all()
     for k in range(B):                                                   # failed thrusters are never commanded
