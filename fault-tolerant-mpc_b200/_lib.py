@@ -59,7 +59,7 @@ def load_terminal(path=None) -> dict:
 
 
 def make_config(horizon: int, Q, R, *, dt: float, mass: float, inertia, r, f_virt, max_thrust: float, D,
-                terminal: dict | None = None, n_hull_sets: int = 1, max_sqp_iter: int = 80, max_qp_iter: int = 0,
+                terminal: dict | None = None, n_hull_sets: int = 1, max_sqp_iter: int = 60, max_qp_iter: int = 0,
                 stall_window: int = 10, sqp_tol: float = 1e-8, qp_tol: float = 1e-10, feas_tol: float = 1e-7,
                 act_tol: float = 1e-7, rho_slack: float = 1e4, clip_tol: float = 1e-9, theta_first: float = 0.5,
                 theta_growth: float = 2.0, blend_dmax: float = 1.0, warm_qp: int = 0, fast_dmax: float = 1e-5,

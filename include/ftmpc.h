@@ -60,8 +60,10 @@ enum {
 typedef struct ftmpc_config {
     int32_t horizon;           /* N                                   reactive.yaml:26, spiraling_mpc.py:38 */
     int32_t dtype;             /* 0 = fp64 (only mode implemented)                                          */
-    int32_t max_sqp_iter;      /* outer iteration cap (default 80: two of the three bench scenarios that hit 60 reach the oracle's KKT
-                                  point after 64 / 68 iterations, tools/hard_instances.py)                     */
+    int32_t max_sqp_iter;      /* outer iteration cap (default 60).  Of the three bench scenarios (of 8192) that hit it, two reach
+                                  the oracle's KKT point after 64 / 68 iterations and one has two local minima
+                                  (tools/hard_instances.py); a cap of 80 converts the two but costs 2.6 % of the 8-GPU throughput
+                                  (every hopeless instance then runs a third longer at the tail of its launch)           */
     int32_t max_qp_iter;       /* active-set iteration cap per QP (default 20*(n+m))                        */
     int32_t stall_window;      /* stall detector (sqp_stalled): give up (FTMPC_ST_MAXITER) when the step has not halved over this many
                                   iterations, checked from 2 windows on (default 10; 0 = run to max_sqp_iter)                  */

@@ -239,12 +239,12 @@ def test_early_stop_in_the_quadratic_regime_changes_nothing_but_the_count(port):
 def test_stall_detector_only_stops_hopeless_instances(port):
     """ftmpc_config.stall_window: instance 249 of the bench workload creeps along a flat non-convex valley (step ~2e-4,
     objective moving by 1e-11 relative per iteration; it reaches a KKT point after 250 iterations, a different local minimum
-    than the oracle's -- tools/hard_instances.py) and is given up after 30 iterations instead of the cap of 80; every instance
+    than the oracle's -- tools/hard_instances.py) and is given up after 30 iterations instead of the cap of 60; every instance
     that converges without the detector still converges with it, to the same point"""
     on = _bench_sample(port, 64, offset=224)
     off = _bench_sample(port, 64, offset=224, stall_window=0)
     k = 249 - 224
-    assert off["status"][k] == 1 and off["iters"][k, 0] == 80
+    assert off["status"][k] == 1 and off["iters"][k, 0] == 60
     assert on["status"][k] == 1 and on["iters"][k, 0] <= 30
     conv = off["status"] == 0
     assert conv.sum() == 63 and np.array_equal(on["status"] == 0, conv)
