@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(FTMPC_QP_THREADS, 1)
             if (sc[SC_STATUS] != (double)FTMPC_ST_RUNNING) break;      // uniform: written before the last barrier
             // with the shared-memory scratch the linearisation leaves Jz / Wz where condensing reads them
             const bool staged = !GS && lin_scratch_doubles(L.N) <= (size_t)(L.nv + FTMPC_NE) * L.nv && condense_fast_path(L, blockDim.x);
-            phase_lin(blk, cfg, L, io, inst, slot, lin_place_v1(scratch, L.N, staged));
+            phase_lin(blk, cfg, L, io, inst, slot, lin_place_v1(scratch, L.N, staged), true);
             phase_qp(blk, cfg, L, io, inst, slot, scratch, staged, GS ? smem : nullptr,
                      GS ? (unsigned)__cvta_generic_to_shared(&s_mbar) : 0u, GS ? &s_op_par : nullptr);
             phase_ls_block(blk, cfg, L, io, inst, slot, 0, scratch);

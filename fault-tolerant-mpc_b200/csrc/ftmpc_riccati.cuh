@@ -196,7 +196,7 @@ __device__ __forceinline__ int ric_backward_cuda(CudaBlock& blk, const ftmpc_con
             }
             v += h_diag;
             if (h_o1 >= 0) {
-                double hsv = theta * 0.5 * (wz[h_o1] + wz[h_o2]);
+                double hsv = (theta != 0.0) ? theta * 0.5 * (wz[h_o1] + wz[h_o2]) : 0.0;     // theta = 0: W_t was not computed
                 if (Cq && h_cq >= 0) hsv += Cq[(size_t)t * FTMPC_CQ + h_cq];
                 if (aug && h_au >= 0) hsv += hau[t * 21 + h_au];
                 v += hsv;
@@ -557,7 +557,7 @@ FT_HD int riccati_factor(Blk& blk, const ftmpc_config& cfg, const Lay& L, const 
             v += dg;
             if (c2 >= 6) {
                 const int k1 = c1 - 6, k2 = c2 - 6;
-                double hsv = theta * 0.5 * (wz[k1 * 13 + k2] + wz[k2 * 13 + k1]);
+                double hsv = (theta != 0.0) ? theta * 0.5 * (wz[k1 * 13 + k2] + wz[k2 * 13 + k1]) : 0.0;   // theta = 0: W_t was not computed
                 if (Cq) {
                     const double* cq = Cq + (size_t)t * FTMPC_CQ;
                     if (k1 >= 3 && k1 < 7 && k2 >= 3) hsv += cq[16 + (k1 - 3) * 4 + (k2 - 3)];                 // (q, q)

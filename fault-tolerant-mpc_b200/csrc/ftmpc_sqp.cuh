@@ -767,6 +767,37 @@ FT_HD void rk4_column_call(const DynConsts& k, const double* x, const double* Wr
 }
 #endif
 
+// ---- Hessian schedule: the blend the next QP STARTS from --------------------------------------------------------------
+// (phase_qp only ever lowers theta inside an iteration, so theta = 0 here means the exact second-order terms W_t are never
+//  read in this SQP iteration: the linearisation then skips the costate recursion and the Hessian sweeps -- 38 % of the SQP
+//  iterations of the bench workload, 9 % of the kernel's time.  ONE function for both phases, so they cannot disagree.)
+struct QpStart {
+    double theta, sigma;
+    bool can_aug, skip_exact;
+};
+FT_HD QpStart qp_start(const ftmpc_config& cfg, const double* sc) {
+    QpStart q;
+    // the convexified QP equals the plain one whenever the predicted rows stay active, whatever the feasibility of the
+    // iterate; it is only kept away from the first, wildly infeasible iterations (elastic variable far from zero)
+    const double feas_aug = 1e-2;
+    q.can_aug = (sc[SC_ITER] > 0.0 || sc[SC_THETA] >= 0.0) && sc[SC_CSUM] <= feas_aug;
+    double theta = sc[SC_THETA];
+    q.sigma = 0.0;
+    theta = (theta < 0.0) ? 0.0 : ((theta == 0.0) ? cfg.theta_first : fmin(1.0, cfg.theta_growth * theta));
+    if (q.can_aug && sc[SC_SIGMA] > 0.0) { theta = 1.0; q.sigma = sc[SC_SIGMA]; }
+    // while the iterate is still infeasible the exact Hessian is almost always indefinite and no convexification is
+    // allowed: once an attempt has fallen all the way back to Gauss-Newton, do not pay for the failing attempts again
+    // until feasibility is reached
+    // far from the solution (last QP step still large) the blended Hessian is almost always indefinite: start the
+    // blend only once the steps have become moderate (|d|_inf <= blend_dmax; measured: 2x fewer failed attempts for
+    // +0.5 % iterations)
+    const bool far = sc[SC_ITER] > 0.0 && sc[SC_THETA] <= 0.0 && sc[SC_DMAX] > cfg.blend_dmax;
+    q.skip_exact = (sc[SC_HFAIL] != 0.0 && sc[SC_CSUM] > feas_aug) || far;
+    if (q.skip_exact) theta = 0.0;
+    q.theta = theta;
+    return q;
+}
+
 // ---- phase_lin: Jacobians, costates, stage Hessians (lanes of one warp / a serial loop) -------------
 template <class Blk>
 FT_HD void phase_lin(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const StepIO& io, int inst, int slot) {
@@ -798,6 +829,7 @@ FT_HD void phase_lin(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const
             stage_cost_coupling(cfg, U + t * FTMPC_NU, uref + t * FTMPC_NU, X + t * FTMPC_NX + 9, Cq + (size_t)t * FTMPC_CQ);
     blk.sync();
     blk.mark(PH_LIN_JAC);
+    if (qp_start(cfg, sc).theta == 0.0) { blk.mark(PH_LIN); return; }        // Gauss-Newton iteration: W_t is never read
     // costates  mu_N = [grad V_f + A_f' lam_term ; 0],  mu_t = [2Q e_t ; 0] + A_t' mu_{t+1}
     for (int i = tid; i < FTMPC_NX; i += nt) {
         double v = 0.0;
@@ -1014,7 +1046,7 @@ FT_HD void condense_long(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, c
     for (int r = tid; r < FTMPC_NX; r += nt) s.G[r * ld + n] = 0.0;
     blk.sync();
     auto gl_base = [&](int j, int ja) { return GL + (size_t)FTMPC_NX * ((size_t)FTMPC_NU * ((size_t)j * N - (size_t)j * (j - 1) / 2) + (size_t)ja * (N - j)); };
-    auto symw = [&](const double* wz, int r, int c) { return 0.5 * (wz[r * 13 + c] + wz[c * 13 + r]); };
+    auto symw = [&](const double* wz, int r, int c) { return (theta != 0.0) ? 0.5 * (wz[r * 13 + c] + wz[c * 13 + r]) : 0.0; };   // theta = 0: W_t was not computed
     // A_t' p  (A_t = [[I, dt I, *], [0, I, *], [0, 0, *]] with the (omega, q) columns in jz[l*13 + r], l < 7)
     auto at_times = [&](const double* jz, const double* p, double* out) {
         for (int c = 0; c < 3; ++c) out[c] = p[c];
@@ -1176,7 +1208,7 @@ FT_HD void condense(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
         for (int idx = tid; idx < 7 * nc; idx += nt) {
             const int kk = idx / nc, b = idx % nc;
             double v = 0.0;
-            for (int l = 0; l < 7; ++l) v += 0.5 * (wz[kk * 13 + l] + wz[l * 13 + kk]) * G[(6 + l) * ld + b];
+            if (theta != 0.0) for (int l = 0; l < 7; ++l) v += 0.5 * (wz[kk * 13 + l] + wz[l * 13 + kk]) * G[(6 + l) * ld + b];
             v *= theta;
             if (Cq && kk >= 3)
                 for (int l = 0; l < 4; ++l) v += Cq[(size_t)t * FTMPC_CQ + 16 + (kk - 3) * 4 + l] * G[(9 + l) * ld + b];
@@ -1200,13 +1232,13 @@ FT_HD void condense(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
             const int j = idx / (nc + 6), b = idx % (nc + 6);
             double v = 0.0;
             if (b < nc) {
-                for (int l = 0; l < 7; ++l) v += 0.5 * (wz[(7 + j) * 13 + l] + wz[l * 13 + 7 + j]) * G[(6 + l) * ld + b];
+                if (theta != 0.0) for (int l = 0; l < 7; ++l) v += 0.5 * (wz[(7 + j) * 13 + l] + wz[l * 13 + 7 + j]) * G[(6 + l) * ld + b];
                 v *= theta;
                 if (Cq && j < 3)
                     for (int l = 0; l < 4; ++l) v += Cq[(size_t)t * FTMPC_CQ + 4 + j * 4 + l] * G[(9 + l) * ld + b];
             } else {
                 const int j2 = b - nc;
-                v = theta * 0.5 * (wz[(7 + j) * 13 + 7 + j2] + wz[(7 + j2) * 13 + 7 + j]);
+                v = (theta != 0.0) ? theta * 0.5 * (wz[(7 + j) * 13 + 7 + j2] + wz[(7 + j2) * 13 + 7 + j]) : 0.0;
                 if (j2 == j) v += 2.0 * cfg.R[j];
                 if (sigma > 0.0) {
                     double av = 0.0;
@@ -1331,7 +1363,8 @@ struct LinPlace {
     double* WzS;       // N * 169 or nullptr
 };
 __device__ __forceinline__ void phase_lin(CudaBlock& blk, const ftmpc_config& cfg, const WsLayout& L, const StepIO& io,
-                                          int inst, int slot, const LinPlace& place) {
+                                          int inst, int slot, const LinPlace& place,
+                                          bool skip_unused_w = false /* the caller's QP phase starts from qp_start() */) {
     double* w = ws_slot(io, L, slot);
     const double* sc = w + L.oSc;
     if (sc[SC_STATUS] != FTMPC_ST_RUNNING) return;
@@ -1399,6 +1432,8 @@ __device__ __forceinline__ void phase_lin(CudaBlock& blk, const ftmpc_config& cf
     }
     blk.sync();
     blk.mark(PH_LIN_JAC);
+    // a QP that starts from the Gauss-Newton model never reads W_t (qp_start): no costates, no Hessian sweeps
+    if (skip_unused_w && qp_start(cfg, sc).theta == 0.0) { blk.mark(PH_LIN); return; }
     // costates  mu_t = [2Q e_t ; 0] + A_t' mu_{t+1}   (one warp, 13 lanes)
     if (tid < 32) {
         for (int t = N - 1; t >= 1; --t) {
@@ -1525,7 +1560,7 @@ __device__ __forceinline__ void condense(CudaBlock& blk, const ftmpc_config& cfg
         const int c = e / 13, r = e - c * 13;
         if (c < r) continue;                       // the pair (c >= r) is written by one thread
         double* wz = Wp + (size_t)t * 169;
-        double v = theta * 0.5 * (wz[c * 13 + r] + wz[r * 13 + c]);
+        double v = (theta != 0.0) ? theta * 0.5 * (wz[c * 13 + r] + wz[r * 13 + c]) : 0.0;
         if (c == r && c < 3) v += 2.0 * cfg.Q[6 + c];
         wz[c * 13 + r] = v;
         wz[r * 13 + c] = v;
@@ -2185,24 +2220,12 @@ FT_HD void phase_qp(Blk& blk, const ftmpc_config& cfg, const WsLayout& L, const 
     // Hessian schedule: exact second-order terms blended by theta; when the exact Hessian is indefinite,
     // first try the augmented-Lagrangian convexification (sigma > 0), then fall back to smaller theta.
     const double* lam_prev = w + L.oLam;
-    // the convexified QP equals the plain one whenever the predicted rows stay active, whatever the feasibility of the
-    // iterate; it is only kept away from the first, wildly infeasible iterations (elastic variable far from zero)
-    const double feas_aug = 1e-2;
-    const bool can_aug = (sc[SC_ITER] > 0.0 || sc[SC_THETA] >= 0.0) && sc[SC_CSUM] <= feas_aug;
+    const QpStart qs = qp_start(cfg, sc);
+    const bool can_aug = qs.can_aug, skip_exact = qs.skip_exact;
     // |d| of the previous iteration is remembered for sqp_fast_converged when that iteration was an exact-Hessian full step
     const double dprev_keep = (sc[SC_ITER] > 0.0 && sc[SC_THETA] == 1.0 && sc[SC_ALPHA] == 1.0) ? sc[SC_DMAX] : 0.0;
-    double theta = sc[SC_THETA], sigma = 0.0;
-    theta = (theta < 0.0) ? 0.0 : ((theta == 0.0) ? cfg.theta_first : fmin(1.0, cfg.theta_growth * theta));
-    if (can_aug && sc[SC_SIGMA] > 0.0) { theta = 1.0; sigma = sc[SC_SIGMA]; }
-    // while the iterate is still infeasible the exact Hessian is almost always indefinite and no convexification is
-    // allowed: once an attempt has fallen all the way back to Gauss-Newton, do not pay for the failing attempts again
-    // until feasibility is reached
-    // far from the solution (last QP step still large) the blended Hessian is almost always indefinite: start the
-    // blend only once the steps have become moderate (|d|_inf <= blend_dmax; measured: 2x fewer failed attempts for
-    // +0.5 % iterations)
-    const bool far = sc[SC_ITER] > 0.0 && sc[SC_THETA] <= 0.0 && sc[SC_DMAX] > cfg.blend_dmax;
-    const bool skip_exact = (sc[SC_HFAIL] != 0.0 && sc[SC_CSUM] > feas_aug) || far;
-    if (skip_exact) theta = 0.0;
+    double theta = qs.theta, sigma = qs.sigma;
+    FT_DBG_COUNT(theta == 0.0 ? 6 : 7);            // (host development counter: pure Gauss-Newton iterations vs blended)
     bool aug_allowed = can_aug;
     int fails = 0, qit = 0, nact = 0, st = GI_OK, aug_retry = 0;
     bool have_j = staged, have_w = staged;
