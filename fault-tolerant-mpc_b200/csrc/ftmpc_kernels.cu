@@ -3,10 +3,12 @@
 // Kernel map:
 //   k_solve : ONE PERSISTENT CTA PER SM runs whole MPC solves back to back (dynamic instance queue):
 //               K4 step acceptance (all backtracking step lengths rolled out at once by the lanes of a warp)
-//               K1 RK4 Jacobians + costates + exact stage Hessians (one (stage, column) task per thread)
-//               K2 condensing  ->  K3 Cholesky, J = L^-T, dual active-set QP
+//               K1 RK4 Jacobians (+ costates and exact stage Hessians when the QP blends them in), one (stage, column) task per thread
+//               K2+K3 Riccati factorisation of the condensed QP (J = Phi^-1 blkdiag(C_t^-T), ftmpc_riccati.cuh), dual active-set QP
 //             every matrix of the QP lives in shared memory (224 KB at N = 20); the per-CTA iterate (U, X,
 //             multipliers, stage Jacobians) sits in a per-CTA global slot that stays L1/L2 resident.
+//             k_solve<true> (N > 20): per-CTA global scratch, operator-form QP (no matrix of size N^2), stage matrices
+//             staged through shared memory by cp.async.bulk.
 //   k_alloc : K5 clip + thrust allocation QP, one thread per instance
 //   k_plant : K6 plant step for closed-loop rollouts
 // There is no CPU fallback in this translation unit: without a CUDA device ftmpc_create fails.

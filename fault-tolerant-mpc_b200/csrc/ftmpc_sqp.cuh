@@ -5,10 +5,13 @@
 //   SpiralingController.solve_mpc      ft_mpc/controllers/spiraling_mpc.py:319-354
 // Here the same NLP is solved in its reduced (single-shooting) form by an SQP whose sub-problem is
 // the condensed QP the north star names:
-//   phase_ls   : step acceptance (l1 merit), forward RK4 rollout, cost/constraint values     [thread / instance]
-//   phase_lin  : RK4 Jacobians, costates, exact stage Hessians of the Lagrangian              [warp   / instance]
-//   phase_qp   : condensing (H, g, rows), Cholesky, dual active-set QP                         [CTA    / instance]
-//   phase_out  : u0, active set, thrust allocation                                            [thread / instance]
+//   phase_ls   : step acceptance (l1 merit), forward RK4 rollout, cost/constraint values
+//   phase_lin  : RK4 Jacobians; costates + exact stage Hessians of the Lagrangian when the QP will blend them in (qp_start)
+//   phase_qp   : Hessian schedule, stage-wise (Riccati) factorisation of the condensed QP (ftmpc_riccati.cuh), dual active-set
+//                QP -- null-space form on E = [J ; X J] (ftmpc_gi.cuh) up to N = 20, operator form (ftmpc_gis.cuh) above;
+//                the round-1 factorisation (condense + Cholesky + L^-T below) stays in host builds as a cross-check
+//   phase_out  : u0, active set, thrust allocation
+// One CUDA block per instance on the device (k_solve, ftmpc_kernels.cu), one host thread per instance in the CPU port.
 // Decision vector and constraint order follow the reference: z = [u_0..u_{N-1} | x_0..x_N]
 // (:110-114), inequalities [hull_0 .. hull_{N-1} | terminal] (:206-214).
 #pragma once
