@@ -9,7 +9,7 @@ shard is fixed at 65,536 / 8 = 8,192 instances): Monte-Carlo fault scenarios -- 
 double thruster failures (dead / stuck-on), seeded random initial robot states, hover reference, horizon
 N = 20, cold start.  One "step" = one ftmpc_step over the rank's shard = B complete get_control equivalents
 (state -> SQP on the reference NLP -> 16 thrusts).  Only converged instances (status 0) count as solves.
-Consecutive steps are independent batches; they are enqueued on `--streams` (default 2) alternating CUDA streams, each
+Consecutive steps are independent batches; they are enqueued on `--streams` (default 4) alternating CUDA streams, each
 with its own output / workspace buffers, so the SMs that run out of instances at the tail of one launch start on the next
 batch (`--streams 1`: strictly serial steps).  The timing events sit on the main stream, which all side streams wait
 for at the start and which waits for all of them at the end.
@@ -213,13 +213,13 @@ def cpu_solve_rate(N: int, cells, states, scen, xref, sample: int, steps: int, w
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)           # even: the steps alternate over two streams
+    ap.add_argument("--steps", type=int, default=8)           # a multiple of the number of streams
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=8192, help="instances per GPU (weak scaling)")
     ap.add_argument("--horizon", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="instances per CPU step (0 = auto)")
-    ap.add_argument("--streams", type=int, default=2, help="independent batches in flight (1 = strictly serial steps)")
+    ap.add_argument("--streams", type=int, default=4, help="independent batches in flight (1 = strictly serial steps)")
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--solver-opts", default="{}", help='JSON dict of ftmpc_config overrides for experiments, e.g. {"warm_qp": 1}')
