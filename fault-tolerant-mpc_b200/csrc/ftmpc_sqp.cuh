@@ -2196,7 +2196,7 @@ FT_HD bool qp_operator_form(const ftmpc_config& cfg, int N) {
     if (cfg.qp_method & 64) return false;
     return N > FTMPC_LONG_N || (cfg.qp_method & 32) != 0;
 }
-#define FTMPC_OP_QCAP 320        /* capacity of the working set in operator form */
+#define FTMPC_OP_QCAP 640        /* capacity of the working set in operator form (R^-1 packed: 1.6 MB of the per-CTA global slice at most) */
 
 // ---- phase_qp ------------------------------------------------------------------------------------------
 template <class Blk>
