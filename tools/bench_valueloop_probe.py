@@ -1,6 +1,7 @@
 """Probe: why is the device-resident loop of bench.py slower than the e2e loop?  Variants of the timed loop on one GPU."""
 import sys, time
-sys.path.insert(0, "/root/repo")
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np, torch
 import bench
 import ftmpc_import; ftmpc_import.load()
